@@ -1,0 +1,1063 @@
+// libb200t5.so - C ABI (include/b200t5.h) over the sm_100a kernels in this directory.
+// Host side: weight store + repacking, per-shape execution plans (workspace, TMA tensor
+// maps, KV arenas, the CUDA graph of one decode step), the greedy loop.
+//
+// Reference path being replaced: HuggingFaceModelPredictor._predict_numpy ->
+// model.generate() (NLP_workloads/Anyscale_job/predictor.py:97-102), whose arithmetic is
+// transformers' T5ForConditionalGeneration + GenerationMixin._sample (greedy).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200t5.h"
+#include "attention_decode.cuh"
+#include "attention_encoder.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+
+// ================================================================== error plumbing
+static thread_local char g_err[512] = "";
+static void set_gerr(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct b200t5_ctx;
+static int fail(b200t5_ctx* h, int code, const char* fmt, ...);
+
+#define CU_OK(h, expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(h, B200T5_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ================================================================== TMA tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+// bf16 row-major [rows, cols] (cols contiguous); box = 64 cols x box_rows rows, 128-B swizzle.
+static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_gerr("cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_gerr("cuTensorMapEncodeTiled failed with %d (rows=%llu cols=%llu box_rows=%u base=%p)", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, box_rows, base);
+    return false;
+  }
+  return true;
+}
+
+// ================================================================== small device helpers
+__global__ void convert_to_bf16_kernel(const void* src, int dtype, bf16* dst, size_t n) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float v;
+    if (dtype == B200T5_DTYPE_F32) v = reinterpret_cast<const float*>(src)[i];
+    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void geglu_elementwise_kernel(const bf16* gate, const bf16* up, bf16* out, long long n, int pow_mode) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(geglu_bf16(__bfloat162float(gate[i]), __bfloat162float(up[i]), pow_mode));
+}
+__global__ void set_state_kernel(DecodeState* st, int step) {
+  st->step = step;
+  st->finished_rows = 0;
+}
+
+// ================================================================== model description
+struct Cfg {
+  int V, d, F, H, I, Le, Ld, nb, maxdist;
+  float eps;
+  int pad, eos, start;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) {
+    o.p = nullptr;
+    o.bytes = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = n;
+    return cudaMalloc(&p, n ? n : 16);
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// Which epilogue/tile a GEMM uses.
+enum GemmKind { G_STORE256, G_RES256, G_GEGLU256, G_CROSSKV256, G_QKVDEC64, G_STORE32, G_RES32, G_GEGLU64, G_ARGMAX128, G_LOGITS128 };
+
+struct GemmOp {
+  CUtensorMap tmA, tmB;
+  int M = 0, N = 0, K = 0;
+  GemmKind kind = G_STORE256;
+  int m_fastest = 0;
+};
+
+struct EncLayerW {
+  DevBuf ln0, ln1, wqkv, wo, wi, wff_o;  // wi interleaved for BN=256
+  CUtensorMap tm_qkv, tm_o, tm_wi, tm_ffo;
+};
+struct DecLayerW {
+  DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved for BN=64
+  CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
+};
+
+struct Plan {
+  int B = 0, S = 0, Tmax = 0;
+  // encoder workspace
+  DevBuf x, xn, qkv, ctx, hff;          // [B*S, d], [B*S, d], [B*S, 3I], [B*S, I], [B*S, F]
+  DevBuf key_ok, extent, enc_bias;      // uint8 [B,S], int [B], float [H][2S-1]
+  DevBuf cross_kv;                      // [Ld][2][B][H][S][64]
+  // decoder workspace
+  DevBuf dx, dxn, dq, dctx, dh;         // [B,d], [B,d], [B,I], [B,I], [B,F]
+  DevBuf self_kv;                       // [Ld][2][B][H][Tmax][64]
+  DevBuf dec_bias;                      // float [H][Tmax]
+  DevBuf pval, pidx;                    // [B][n_tiles]
+  DevBuf state, unfinished, out_ids, out_len, ids_dev, mask_dev;
+  int n_vtiles = 0;
+  // tensor maps for activations (A operands)
+  CUtensorMap tm_xn, tm_ctx, tm_hff, tm_dxn, tm_dctx, tm_dh;
+  // decode-step graph
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int graph_nodes = 0;
+  long long g_eos = -1, g_pad = -1;
+  int g_min_new = -1;
+  // pinned staging for the host-buffer entry point and polling
+  long long* h_ids = nullptr;
+  long long* h_mask = nullptr;
+  long long* h_out = nullptr;
+  int* h_len = nullptr;
+  DecodeState* h_state = nullptr;
+  ~Plan() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    if (h_ids) cudaFreeHost(h_ids);
+    if (h_mask) cudaFreeHost(h_mask);
+    if (h_out) cudaFreeHost(h_out);
+    if (h_len) cudaFreeHost(h_len);
+    if (h_state) cudaFreeHost(h_state);
+  }
+};
+
+struct b200t5_ctx {
+  Cfg c;
+  int device = 0;
+  int num_sms = 148;
+  bool finalized = false;
+  char err[512] = "";
+  std::map<std::string, std::unique_ptr<DevBuf>> raw;  // HF name -> bf16 copy (until finalize)
+  std::map<std::string, std::vector<int64_t>> raw_shape;
+  DevBuf shared, lm_head, enc_final_ln, dec_final_ln, enc_relbias, dec_relbias, wcrosskv;
+  CUtensorMap tm_lm, tm_crosskv;
+  std::vector<float> enc_relbias_h, dec_relbias_h;  // [nb][H] as float
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  std::unique_ptr<Plan> plan;
+  cudaStream_t cap_stream = nullptr, exec_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  int pow_mode = 0;
+  // stats of the last generate
+  int64_t launches = 0;
+  int last_steps = 0;
+  double last_decode_bytes = 0, last_enc_flops = 0;
+};
+
+static int fail(b200t5_ctx* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) snprintf(h->err, sizeof(h->err), "%s", buf);
+  snprintf(g_err, sizeof(g_err), "%s", buf);
+  return code;
+}
+
+static int check_device(b200t5_ctx* h, int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(h, B200T5_ENODEV, "no CUDA device available (%s); libb200t5 has no CPU fallback",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(h, B200T5_EINVAL, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp p;
+  CU_OK(h, cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return fail(h, B200T5_ENODEV, "device %d is sm_%d%d; libb200t5 is built for sm_100a only", device, p.major, p.minor);
+  CU_OK(h, cudaSetDevice(device));
+  return p.multiProcessorCount;
+}
+
+// ================================================================== relative position buckets
+// T5Attention._relative_position_bucket (modeling_t5.py:188-234), fp32 log + truncation.
+extern "C" int b200t5_relative_bucket(int rel, int bidirectional, int num_buckets, int max_distance) {
+  int ret = 0, n;
+  if (bidirectional) {
+    num_buckets /= 2;
+    if (rel > 0) ret += num_buckets;
+    n = rel < 0 ? -rel : rel;
+  } else {
+    n = rel < 0 ? -rel : 0;
+  }
+  const int max_exact = num_buckets / 2;
+  if (n < max_exact) return ret + n;
+  const float ratio = static_cast<float>(n) / static_cast<float>(max_exact);
+  const float denom = static_cast<float>(log(static_cast<double>(max_distance) / static_cast<double>(max_exact)));
+  const float scaled = logf(ratio) / denom * static_cast<float>(num_buckets - max_exact);
+  int large = max_exact + static_cast<int>(scaled);
+  if (large > num_buckets - 1) large = num_buckets - 1;
+  return ret + large;
+}
+
+// ================================================================== GEMM dispatch
+static cudaError_t run_gemm(b200t5_ctx* h, const GemmOp& g, const void* ep, cudaStream_t s) {
+  h->launches++;
+  switch (g.kind) {
+    case G_STORE256:
+      return launch_gemm<256, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s);
+    case G_RES256:
+      return launch_gemm<256, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s);
+    case G_GEGLU256:
+      return launch_gemm<256, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s);
+    case G_CROSSKV256:
+      return launch_gemm<256, EpiCrossKV>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiCrossKV::Params*>(ep), h->num_sms, s);
+    case G_QKVDEC64:
+      return launch_gemm<64, EpiQkvDecode>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiQkvDecode::Params*>(ep), h->num_sms, s);
+    case G_STORE32:
+      return launch_gemm<32, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s);
+    case G_RES32:
+      return launch_gemm<32, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s);
+    case G_GEGLU64:
+      return launch_gemm<64, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s);
+    case G_ARGMAX128:
+      return launch_gemm<128, EpiArgmax>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiArgmax::Params*>(ep), h->num_sms, s);
+    case G_LOGITS128:
+      return launch_gemm<128, EpiStoreF32>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStoreF32::Params*>(ep), h->num_sms, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+static cudaError_t run_rmsnorm(b200t5_ctx* h, const bf16* x, const bf16* w, bf16* y, int M, int d, float eps,
+                               cudaStream_t s) {
+  if (h) h->launches++;
+  const int wpb = 8;
+  const int grid = (M + wpb - 1) / wpb;
+  if (d <= 1024) rmsnorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, w, y, M, d, eps);
+  else if (d <= 4096) rmsnorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, w, y, M, d, eps);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+static cudaError_t init_kernel_attrs() {
+  cudaError_t e;
+#define PREP(BN, EPI)                         \
+  if ((e = prepare_gemm<BN, EPI>()) != cudaSuccess) return e;
+  PREP(256, EpiStore) PREP(256, EpiResidual) PREP(256, EpiGeglu) PREP(256, EpiCrossKV) PREP(64, EpiQkvDecode)
+  PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
+  PREP(64, EpiStore) PREP(128, EpiStore)
+#undef PREP
+  return cudaFuncSetAttribute(encoder_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+// ================================================================== lifecycle
+extern "C" const char* b200t5_version(void) { return "b200t5 0.1 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* b200t5_last_global_error(void) { return g_err; }
+extern "C" const char* b200t5_last_error(b200t5_handle h) { return h ? h->err : g_err; }
+
+extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle* out) {
+  if (!cfg || !out) return fail(nullptr, B200T5_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->d_kv != 64) return fail(nullptr, B200T5_EINVAL, "d_kv=%d unsupported (kernels are specialised for 64)", cfg->d_kv);
+  if (!cfg->is_gated_gelu) return fail(nullptr, B200T5_EINVAL, "only feed_forward_proj='gated-gelu' (T5 v1.1 / FLAN-T5) is supported");
+  if (cfg->scale_decoder_outputs) return fail(nullptr, B200T5_EINVAL, "scale_decoder_outputs (tied-embedding T5 v1.0) is not supported");
+  if (cfg->d_model % 8 || cfg->d_ff % 32 || cfg->d_model > 4096 || cfg->vocab_size < 2 || cfg->num_heads < 1 ||
+      cfg->num_layers < 1 || cfg->num_decoder_layers < 1)
+    return fail(nullptr, B200T5_EINVAL, "unsupported shape: d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
+  int sms = check_device(nullptr, device);
+  if (sms < 0) return sms;
+  b200t5_ctx* h = new (std::nothrow) b200t5_ctx();
+  if (!h) return fail(nullptr, B200T5_ENOMEM, "out of host memory");
+  h->c = Cfg{cfg->vocab_size, cfg->d_model, cfg->d_ff, cfg->num_heads, cfg->num_heads * 64, cfg->num_layers,
+             cfg->num_decoder_layers, cfg->relative_attention_num_buckets, cfg->relative_attention_max_distance,
+             cfg->layer_norm_epsilon, cfg->pad_token_id, cfg->eos_token_id, cfg->decoder_start_token_id};
+  h->device = device;
+  h->num_sms = sms;
+  h->enc.resize(h->c.Le);
+  h->dec.resize(h->c.Ld);
+  const char* pm = getenv("B200T5_POW_MODE");
+  h->pow_mode = pm ? atoi(pm) : 0;
+  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->exec_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, B200T5_ECUDA, "cudaStreamCreate failed");
+  }
+  {
+    cudaError_t ke = init_kernel_attrs();
+    if (ke != cudaSuccess) {
+      delete h;
+      return fail(nullptr, B200T5_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ke));
+    }
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_destroy(b200t5_handle h) {
+  if (!h) return B200T5_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  h->plan.reset();
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->exec_stream) cudaStreamDestroy(h->exec_stream);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_set_weight(b200t5_handle h, const char* name, const void* dev_ptr, int dtype,
+                                 const int64_t* shape, int ndim) {
+  if (!h || !name || !dev_ptr || !shape || ndim < 1 || ndim > 2) return fail(h, B200T5_EINVAL, "set_weight: bad argument");
+  if (h->finalized) return fail(h, B200T5_ESTATE, "set_weight after finalize");
+  if (dtype < 0 || dtype > 2) return fail(h, B200T5_EINVAL, "set_weight(%s): unknown dtype %d", name, dtype);
+  CU_OK(h, cudaSetDevice(h->device));
+  size_t n = 1;
+  std::vector<int64_t> shp(shape, shape + ndim);
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail(h, B200T5_EINVAL, "set_weight(%s): bad shape", name);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  std::unique_ptr<DevBuf> buf(new DevBuf());
+  CU_OK(h, buf->alloc(n * sizeof(bf16)));
+  if (dtype == B200T5_DTYPE_BF16) {
+    CU_OK(h, cudaMemcpy(buf->p, dev_ptr, n * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  } else {
+    convert_to_bf16_kernel<<<1024, 256>>>(dev_ptr, dtype, buf->as<bf16>(), n);
+    CU_OK(h, cudaGetLastError());
+    CU_OK(h, cudaDeviceSynchronize());
+  }
+  h->raw[name] = std::move(buf);
+  h->raw_shape[name] = shp;
+  return B200T5_OK;
+}
+
+// fetch a raw tensor, checking its shape
+static bf16* take(b200t5_ctx* h, const std::string& name, int64_t r, int64_t c, int* rc) {
+  auto it = h->raw.find(name);
+  if (it == h->raw.end()) {
+    *rc = fail(h, B200T5_ESTATE, "finalize: missing weight '%s'", name.c_str());
+    return nullptr;
+  }
+  const auto& s = h->raw_shape[name];
+  const bool ok = (c == 0) ? (s.size() == 1 && s[0] == r) : (s.size() == 2 && s[0] == r && s[1] == c);
+  if (!ok) {
+    *rc = fail(h, B200T5_EINVAL, "finalize: weight '%s' has the wrong shape", name.c_str());
+    return nullptr;
+  }
+  return it->second->as<bf16>();
+}
+
+// dst[ntiles*bn, d]: per tile, bn/2 rows of wi_0 followed by the matching bn/2 rows of wi_1.
+static int interleave_geglu(b200t5_ctx* h, const bf16* wi0, const bf16* wi1, DevBuf& dst, int F, int d, int bn,
+                            int* rows_out) {
+  const int half = bn / 2;
+  const int ntiles = (F + half - 1) / half;
+  CU_OK(h, dst.alloc(static_cast<size_t>(ntiles) * bn * d * sizeof(bf16)));
+  CU_OK(h, cudaMemset(dst.p, 0, dst.bytes));
+  for (int j = 0; j < ntiles; ++j) {
+    const int rows = (j + 1) * half <= F ? half : F - j * half;
+    bf16* base = dst.as<bf16>() + static_cast<size_t>(j) * bn * d;
+    CU_OK(h, cudaMemcpy(base, wi0 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(bf16), cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(base + static_cast<size_t>(half) * d, wi1 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  }
+  *rows_out = ntiles * bn;
+  return B200T5_OK;
+}
+
+static int clone_buf(b200t5_ctx* h, DevBuf& dst, const bf16* src, size_t n) {
+  CU_OK(h, dst.alloc(n * sizeof(bf16)));
+  CU_OK(h, cudaMemcpy(dst.p, src, n * sizeof(bf16), cudaMemcpyDeviceToDevice));
+  return B200T5_OK;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != B200T5_OK) return _rc; \
+  } while (0)
+#define TMAP(h, tm, base, rows, cols, box) \
+  do {                                     \
+    if (!make_tmap(tm, base, rows, cols, box)) return fail(h, B200T5_ECUDA, "%s", g_err); \
+  } while (0)
+
+extern "C" int b200t5_finalize(b200t5_handle h) {
+  if (!h) return fail(nullptr, B200T5_EINVAL, "null handle");
+  if (h->finalized) return B200T5_OK;
+  CU_OK(h, cudaSetDevice(h->device));
+  const Cfg& c = h->c;
+  int rc = B200T5_OK;
+  const int d = c.d, I = c.I, F = c.F;
+
+  bf16* shared = take(h, "shared.weight", c.V, d, &rc);
+  if (!shared) return rc;
+  TRY(clone_buf(h, h->shared, shared, static_cast<size_t>(c.V) * d));
+  // real FLAN-T5 checkpoints carry a separate lm_head; a checkpoint without one is tied
+  const bf16* lm = h->raw.count("lm_head.weight") ? take(h, "lm_head.weight", c.V, d, &rc) : shared;
+  if (!lm) return rc;
+  TRY(clone_buf(h, h->lm_head, lm, static_cast<size_t>(c.V) * d));
+  TMAP(h, &h->tm_lm, h->lm_head.p, c.V, d, 128);
+
+  bf16* p;
+  if (!(p = take(h, "encoder.final_layer_norm.weight", d, 0, &rc))) return rc;
+  TRY(clone_buf(h, h->enc_final_ln, p, d));
+  if (!(p = take(h, "decoder.final_layer_norm.weight", d, 0, &rc))) return rc;
+  TRY(clone_buf(h, h->dec_final_ln, p, d));
+
+  // relative attention bias tables -> host floats
+  for (int side = 0; side < 2; ++side) {
+    const std::string nm = std::string(side ? "decoder" : "encoder") + ".block.0.layer.0.SelfAttention.relative_attention_bias.weight";
+    if (!(p = take(h, nm, c.nb, c.H, &rc))) return rc;
+    std::vector<bf16> tmp(static_cast<size_t>(c.nb) * c.H);
+    CU_OK(h, cudaMemcpy(tmp.data(), p, tmp.size() * sizeof(bf16), cudaMemcpyDeviceToHost));
+    std::vector<float>& dst = side ? h->dec_relbias_h : h->enc_relbias_h;
+    dst.resize(tmp.size());
+    for (size_t i = 0; i < tmp.size(); ++i) dst[i] = __bfloat162float(tmp[i]);
+  }
+
+  char nm[256];
+  for (int l = 0; l < c.Le; ++l) {
+    EncLayerW& w = h->enc[l];
+    auto key = [&](const char* suffix) {
+      snprintf(nm, sizeof(nm), "encoder.block.%d.%s", l, suffix);
+      return std::string(nm);
+    };
+    if (!(p = take(h, key("layer.0.layer_norm.weight"), d, 0, &rc))) return rc;
+    TRY(clone_buf(h, w.ln0, p, d));
+    if (!(p = take(h, key("layer.1.layer_norm.weight"), d, 0, &rc))) return rc;
+    TRY(clone_buf(h, w.ln1, p, d));
+    const bf16* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
+    const bf16* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
+    const bf16* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
+    if (!v) return rc;
+    CU_OK(h, w.wqkv.alloc(static_cast<size_t>(3) * I * d * sizeof(bf16)));
+    const size_t blk = static_cast<size_t>(I) * d;
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>(), q, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
+    if (!(p = take(h, key("layer.0.SelfAttention.o.weight"), d, I, &rc))) return rc;
+    TRY(clone_buf(h, w.wo, p, static_cast<size_t>(d) * I));
+    const bf16* wi0 = take(h, key("layer.1.DenseReluDense.wi_0.weight"), F, d, &rc);
+    const bf16* wi1 = wi0 ? take(h, key("layer.1.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
+    if (!wi1) return rc;
+    int wi_rows = 0;
+    TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, 256, &wi_rows));
+    if (!(p = take(h, key("layer.1.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
+    TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
+    TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, 256);
+    TMAP(h, &w.tm_o, w.wo.p, d, I, 256);
+    TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, 256);
+    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, 256);
+  }
+
+  CU_OK(h, h->wcrosskv.alloc(static_cast<size_t>(c.Ld) * 2 * I * d * sizeof(bf16)));
+  for (int l = 0; l < c.Ld; ++l) {
+    DecLayerW& w = h->dec[l];
+    auto key = [&](const char* suffix) {
+      snprintf(nm, sizeof(nm), "decoder.block.%d.%s", l, suffix);
+      return std::string(nm);
+    };
+    if (!(p = take(h, key("layer.0.layer_norm.weight"), d, 0, &rc))) return rc;
+    TRY(clone_buf(h, w.ln0, p, d));
+    if (!(p = take(h, key("layer.1.layer_norm.weight"), d, 0, &rc))) return rc;
+    TRY(clone_buf(h, w.ln1, p, d));
+    if (!(p = take(h, key("layer.2.layer_norm.weight"), d, 0, &rc))) return rc;
+    TRY(clone_buf(h, w.ln2, p, d));
+    const bf16* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
+    const bf16* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
+    const bf16* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
+    if (!v) return rc;
+    const size_t blk = static_cast<size_t>(I) * d;
+    CU_OK(h, w.wqkv.alloc(3 * blk * sizeof(bf16)));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>(), q, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
+    if (!(p = take(h, key("layer.0.SelfAttention.o.weight"), d, I, &rc))) return rc;
+    TRY(clone_buf(h, w.wo, p, static_cast<size_t>(d) * I));
+    if (!(p = take(h, key("layer.1.EncDecAttention.q.weight"), I, d, &rc))) return rc;
+    TRY(clone_buf(h, w.wcq, p, blk));
+    const bf16* ck = take(h, key("layer.1.EncDecAttention.k.weight"), I, d, &rc);
+    const bf16* cv = ck ? take(h, key("layer.1.EncDecAttention.v.weight"), I, d, &rc) : nullptr;
+    if (!cv) return rc;
+    CU_OK(h, cudaMemcpy(h->wcrosskv.as<bf16>() + (static_cast<size_t>(l) * 2 + 0) * blk, ck, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(h->wcrosskv.as<bf16>() + (static_cast<size_t>(l) * 2 + 1) * blk, cv, blk * 2, cudaMemcpyDeviceToDevice));
+    if (!(p = take(h, key("layer.1.EncDecAttention.o.weight"), d, I, &rc))) return rc;
+    TRY(clone_buf(h, w.wco, p, static_cast<size_t>(d) * I));
+    const bf16* wi0 = take(h, key("layer.2.DenseReluDense.wi_0.weight"), F, d, &rc);
+    const bf16* wi1 = wi0 ? take(h, key("layer.2.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
+    if (!wi1) return rc;
+    int wi_rows = 0;
+    TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, 64, &wi_rows));
+    if (!(p = take(h, key("layer.2.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
+    TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
+    TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, 64);
+    TMAP(h, &w.tm_o, w.wo.p, d, I, 32);
+    TMAP(h, &w.tm_cq, w.wcq.p, I, d, 32);
+    TMAP(h, &w.tm_co, w.wco.p, d, I, 32);
+    TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, 64);
+    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, 32);
+  }
+  TMAP(h, &h->tm_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 256);
+
+  h->raw.clear();
+  h->raw_shape.clear();
+  h->finalized = true;
+  return B200T5_OK;
+}
+
+// ================================================================== plans
+static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
+  const Cfg& c = h->c;
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->B = B;
+  pl->S = S;
+  pl->Tmax = Tmax;
+  const size_t M = static_cast<size_t>(B) * S;
+  const int d = c.d, I = c.I, F = c.F, H = c.H;
+  CU_OK(h, pl->x.alloc(M * d * 2));
+  CU_OK(h, pl->xn.alloc(M * d * 2));
+  CU_OK(h, pl->qkv.alloc(M * 3 * I * 2));
+  CU_OK(h, pl->ctx.alloc(M * I * 2));
+  CU_OK(h, pl->hff.alloc(M * F * 2));
+  CU_OK(h, pl->key_ok.alloc(M));
+  CU_OK(h, pl->extent.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->cross_kv.alloc(static_cast<size_t>(c.Ld) * 2 * M * I * 2));
+  CU_OK(h, pl->dx.alloc(static_cast<size_t>(B) * d * 2));
+  CU_OK(h, pl->dxn.alloc(static_cast<size_t>(B) * d * 2));
+  CU_OK(h, pl->dq.alloc(static_cast<size_t>(B) * I * 2));
+  CU_OK(h, pl->dctx.alloc(static_cast<size_t>(B) * I * 2));
+  CU_OK(h, pl->dh.alloc(static_cast<size_t>(B) * F * 2));
+  CU_OK(h, pl->self_kv.alloc(static_cast<size_t>(c.Ld) * 2 * B * I * Tmax * 2));
+  pl->n_vtiles = (c.V + 127) / 128;
+  CU_OK(h, pl->pval.alloc(static_cast<size_t>(B) * pl->n_vtiles * 4));
+  CU_OK(h, pl->pidx.alloc(static_cast<size_t>(B) * pl->n_vtiles * 4));
+  CU_OK(h, pl->state.alloc(sizeof(DecodeState)));
+  CU_OK(h, pl->unfinished.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->out_ids.alloc(static_cast<size_t>(B) * (Tmax + 1) * 8));
+  CU_OK(h, pl->out_len.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->ids_dev.alloc(M * 8));
+  CU_OK(h, pl->mask_dev.alloc(M * 8));
+  CU_OK(h, cudaMallocHost(&pl->h_ids, M * 8));
+  CU_OK(h, cudaMallocHost(&pl->h_mask, M * 8));
+  CU_OK(h, cudaMallocHost(&pl->h_out, static_cast<size_t>(B) * (Tmax + 1) * 8));
+  CU_OK(h, cudaMallocHost(&pl->h_len, static_cast<size_t>(B) * 4));
+  CU_OK(h, cudaMallocHost(&pl->h_state, sizeof(DecodeState)));
+
+  // bias tables (values are the bf16 embedding entries widened to fp32)
+  {
+    std::vector<float> eb(static_cast<size_t>(H) * (2 * S - 1));
+    for (int rel = -(S - 1); rel <= S - 1; ++rel) {
+      const int bk = b200t5_relative_bucket(rel, 1, c.nb, c.maxdist);
+      for (int hh = 0; hh < H; ++hh) eb[static_cast<size_t>(hh) * (2 * S - 1) + rel + S - 1] = h->enc_relbias_h[static_cast<size_t>(bk) * H + hh];
+    }
+    CU_OK(h, pl->enc_bias.alloc(eb.size() * 4));
+    CU_OK(h, cudaMemcpy(pl->enc_bias.p, eb.data(), eb.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<float> db(static_cast<size_t>(H) * Tmax);
+    for (int n = 0; n < Tmax; ++n) {
+      const int bk = b200t5_relative_bucket(-n, 0, c.nb, c.maxdist);
+      for (int hh = 0; hh < H; ++hh) db[static_cast<size_t>(hh) * Tmax + n] = h->dec_relbias_h[static_cast<size_t>(bk) * H + hh];
+    }
+    CU_OK(h, pl->dec_bias.alloc(db.size() * 4));
+    CU_OK(h, cudaMemcpy(pl->dec_bias.p, db.data(), db.size() * 4, cudaMemcpyHostToDevice));
+  }
+  TMAP(h, &pl->tm_xn, pl->xn.p, M, d, 128);
+  TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
+  TMAP(h, &pl->tm_hff, pl->hff.p, M, F, 128);
+  TMAP(h, &pl->tm_dxn, pl->dxn.p, B, d, 128);
+  TMAP(h, &pl->tm_dctx, pl->dctx.p, B, I, 128);
+  TMAP(h, &pl->tm_dh, pl->dh.p, B, F, 128);
+  h->plan = std::move(pl);
+  return B200T5_OK;
+}
+
+static int ensure_plan(b200t5_ctx* h, int B, int S, int Tmax) {
+  if (h->plan && h->plan->B == B && h->plan->S == S && h->plan->Tmax == Tmax) return B200T5_OK;
+  CU_OK(h, cudaDeviceSynchronize());
+  h->plan.reset();
+  return build_plan(h, B, S, Tmax);
+}
+
+static GemmOp mk(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K, GemmKind k, int m_fastest) {
+  GemmOp g;
+  g.tmA = a;
+  g.tmB = b;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.kind = k;
+  g.m_fastest = m_fastest;
+  return g;
+}
+
+// ================================================================== encoder
+static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mask, cudaStream_t s) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  const int B = p.B, S = p.S, M = B * S, d = c.d, I = c.I, F = c.F, H = c.H;
+  prep_mask_kernel<<<B, 128, 0, s>>>(mask, p.key_ok.as<unsigned char>(), p.extent.as<int>(), B, S);
+  embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), M, d, c.V);
+  h->launches += 2;
+  CU_OK(h, cudaGetLastError());
+  const size_t attn_smem = encoder_attn_smem_bytes(S);
+  if (attn_smem > 96 * 1024) return fail(h, B200T5_EINVAL, "encoder length S=%d too long for the attention kernel", S);
+  const int wi_tiles = (F + 127) / 128;
+  for (int l = 0; l < c.Le; ++l) {
+    EncLayerW& w = h->enc[l];
+    CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln0.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+    {
+      EpiStore::Params ep{p.qkv.as<bf16>(), 3 * I};
+      CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
+    }
+    encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
+        p.qkv.as<bf16>(), p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+    h->launches++;
+    CU_OK(h, cudaGetLastError());
+    {
+      EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
+      CU_OK(h, run_gemm(h, mk(p.tm_ctx, w.tm_o, M, d, I, G_RES256, 0), &ep, s));
+    }
+    CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln1.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+    {
+      EpiGeglu::Params ep{p.hff.as<bf16>(), F, h->pow_mode};
+      CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
+    }
+    {
+      EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
+      CU_OK(h, run_gemm(h, mk(p.tm_hff, w.tm_ffo, M, d, F, G_RES256, 0), &ep, s));
+    }
+  }
+  CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), h->enc_final_ln.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+  return B200T5_OK;
+}
+
+static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  EpiCrossKV::Params ep{p.cross_kv.as<bf16>(), p.B, c.H, p.S};
+  CU_OK(h, run_gemm(h, mk(p.tm_xn, h->tm_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, G_CROSSKV256, 0), &ep, s));
+  return B200T5_OK;
+}
+
+// ================================================================== one decode step
+// logits_out == nullptr: fused arg-max + bookkeeping; otherwise fp32 logits are written to
+// logits_out (row stride ldl) and no token is chosen (teacher forcing).
+static int run_decode_step(b200t5_ctx* h, cudaStream_t s, float* logits_out, int ldl, long long eos, long long pad,
+                           int min_new) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  const int B = p.B, S = p.S, d = c.d, I = c.I, F = c.F, H = c.H, T = p.Tmax;
+  DecodeState* st = p.state.as<DecodeState>();
+  const int* step = &st->step;
+  const size_t self_layer = static_cast<size_t>(2) * B * I * T;
+  const size_t cross_layer = static_cast<size_t>(2) * B * I * S;
+  const int wi_tiles = (F + 31) / 32;
+  for (int l = 0; l < c.Ld; ++l) {
+    DecLayerW& w = h->dec[l];
+    bf16* skv = p.self_kv.as<bf16>() + l * self_layer;
+    bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
+    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln0.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    {
+      EpiQkvDecode::Params ep{p.dq.as<bf16>(), skv, step, B, H, T};
+      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_qkv, B, 3 * I, d, G_QKVDEC64, 1), &ep, s));
+    }
+    attn_decode_kernel<true><<<B * H, kAttnDecThreads, T * sizeof(float), s>>>(
+        p.dq.as<bf16>(), skv, skv + static_cast<size_t>(B) * I * T, p.dctx.as<bf16>(), H, T, nullptr, nullptr, step,
+        p.dec_bias.as<float>());
+    h->launches++;
+    {
+      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
+      CU_OK(h, run_gemm(h, mk(p.tm_dctx, w.tm_o, B, d, I, G_RES32, 1), &ep, s));
+    }
+    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln1.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    {
+      EpiStore::Params ep{p.dq.as<bf16>(), I};
+      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_cq, B, I, d, G_STORE32, 1), &ep, s));
+    }
+    attn_decode_kernel<false><<<B * H, kAttnDecThreads, S * sizeof(float), s>>>(
+        p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(B) * I * S, p.dctx.as<bf16>(), H, S, p.extent.as<int>(),
+        p.key_ok.as<unsigned char>(), nullptr, nullptr);
+    h->launches++;
+    {
+      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
+      CU_OK(h, run_gemm(h, mk(p.tm_dctx, w.tm_co, B, d, I, G_RES32, 1), &ep, s));
+    }
+    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln2.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    {
+      EpiGeglu::Params ep{p.dh.as<bf16>(), F, h->pow_mode};
+      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_wi, B, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s));
+    }
+    {
+      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
+      CU_OK(h, run_gemm(h, mk(p.tm_dh, w.tm_ffo, B, d, F, G_RES32, 1), &ep, s));
+    }
+  }
+  CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), h->dec_final_ln.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+  if (logits_out) {
+    EpiStoreF32::Params ep{logits_out, ldl};
+    CU_OK(h, run_gemm(h, mk(p.tm_dxn, h->tm_lm, B, c.V, d, G_LOGITS128, 1), &ep, s));
+  } else {
+    EpiArgmax::Params ep{p.pval.as<float>(), p.pidx.as<int>(), p.n_vtiles, step, static_cast<int>(eos), min_new};
+    CU_OK(h, run_gemm(h, mk(p.tm_dxn, h->tm_lm, B, c.V, d, G_ARGMAX128, 1), &ep, s));
+    finalize_step_kernel<<<B, 128, 0, s>>>(p.pval.as<float>(), p.pidx.as<int>(), p.n_vtiles, st, p.unfinished.as<int>(),
+                                           p.out_ids.as<long long>(), p.out_len.as<int>(), T + 1, eos, pad,
+                                           h->shared.as<bf16>(), p.dx.as<bf16>(), d);
+    h->launches++;
+  }
+  advance_step_kernel<<<1, 1, 0, s>>>(st);
+  h->launches++;
+  CU_OK(h, cudaGetLastError());
+  return B200T5_OK;
+}
+
+// Graph of one decode step; eos/pad/min_new are baked in, so the graph is rebuilt when they change.
+static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new) {
+  Plan& p = *h->plan;
+  if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new) return B200T5_OK;
+  if (p.gexec) {
+    cudaGraphExecDestroy(p.gexec);
+    p.gexec = nullptr;
+  }
+  if (p.graph) {
+    cudaGraphDestroy(p.graph);
+    p.graph = nullptr;
+  }
+  const int64_t before = h->launches;
+  CU_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_decode_step(h, h->cap_stream, nullptr, 0, eos, pad, min_new);
+  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &p.graph);
+  p.graph_nodes = static_cast<int>(h->launches - before);
+  h->launches = before;
+  if (rc != B200T5_OK) return rc;
+  CU_OK(h, e);
+  CU_OK(h, cudaGraphInstantiate(&p.gexec, p.graph, 0));
+  p.g_eos = eos;
+  p.g_pad = pad;
+  p.g_min_new = min_new;
+  return B200T5_OK;
+}
+
+static int validate(b200t5_ctx* h, int B, int S, const b200t5_gen_params* gp) {
+  if (!h) return fail(nullptr, B200T5_EINVAL, "null handle");
+  if (!h->finalized) return fail(h, B200T5_ESTATE, "model not finalized");
+  if (B < 1 || S < 1 || B > 65535) return fail(h, B200T5_EINVAL, "bad batch shape B=%d S=%d", B, S);
+  if (gp && (gp->max_new_tokens < 1 || gp->max_new_tokens > 4096)) return fail(h, B200T5_EINVAL, "max_new_tokens=%d out of range", gp->max_new_tokens);
+  return B200T5_OK;
+}
+
+static void fill_stats_model(b200t5_ctx* h, int steps) {
+  const Cfg& c = h->c;
+  const Plan& p = *h->plan;
+  // weights once per step + cross-KV + self-KV read/write, bf16.
+  const double wstep = static_cast<double>(c.Ld) * (6.0 * c.d * c.I + 3.0 * c.d * c.F) + static_cast<double>(c.V) * c.d;
+  std::vector<int> ext(p.B);
+  cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost);
+  double sum_s = 0;
+  for (int v : ext) sum_s += v;
+  double bytes = 0;
+  for (int t = 1; t <= steps; ++t)
+    bytes += 2.0 * (wstep + static_cast<double>(c.Ld) * 2 * c.I * sum_s + static_cast<double>(c.Ld) * 2 * c.I * p.B * t +
+                    static_cast<double>(c.Ld) * 2 * c.I * p.B);
+  h->last_decode_bytes = bytes;
+  const double BS = static_cast<double>(p.B) * p.S;
+  h->last_enc_flops = 2.0 * c.Le * (4.0 * c.d * c.I + 3.0 * c.d * c.F) * BS + c.Le * 4.0 * p.S * static_cast<double>(p.S) * c.I * p.B +
+                      2.0 * c.Ld * 2.0 * c.d * c.I * BS;
+}
+
+static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* mask, int B, int S,
+                         const b200t5_gen_params* gp, long long* out_ids, int* out_len, cudaStream_t s) {
+  const Cfg& c = h->c;
+  const long long eos = gp->eos_token_id >= 0 ? gp->eos_token_id : c.eos;
+  const long long pad = gp->pad_token_id >= 0 ? gp->pad_token_id : c.pad;
+  const long long start = gp->decoder_start_token_id >= 0 ? gp->decoder_start_token_id : c.start;
+  if (start >= c.V || pad >= c.V) return fail(h, B200T5_EINVAL, "special token id out of range");
+  const int T = gp->max_new_tokens;
+  const int min_new = gp->min_new_tokens > 0 ? gp->min_new_tokens : 0;
+  const int poll = gp->poll_interval > 0 ? gp->poll_interval : 8;
+  TRY(ensure_plan(h, B, S, T));
+  Plan& p = *h->plan;
+  TRY(ensure_graph(h, eos, pad, min_new));
+  h->launches = 0;
+  CU_OK(h, cudaEventRecord(h->ev[0], s));
+  TRY(run_encoder(h, ids, mask, s));
+  TRY(run_cross_kv(h, s));
+  decode_init_kernel<<<B, 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.out_ids.as<long long>(),
+                                       p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+  h->launches++;
+  CU_OK(h, cudaGetLastError());
+  CU_OK(h, cudaEventRecord(h->ev[1], s));
+  int steps = 0;
+  for (int t = 0; t < T; ++t) {
+    CU_OK(h, cudaGraphLaunch(p.gexec, s));
+    h->launches += p.graph_nodes;
+    ++steps;
+    if ((t + 1) % poll == 0 && t + 1 < T && min_new < T) {
+      // every row emitted EOS -> the remaining steps would only append pad tokens
+      CU_OK(h, cudaMemcpyAsync(p.h_state, p.state.p, sizeof(DecodeState), cudaMemcpyDeviceToHost, s));
+      CU_OK(h, cudaStreamSynchronize(s));
+      if (p.h_state->finished_rows >= B) break;
+    }
+  }
+  CU_OK(h, cudaEventRecord(h->ev[2], s));
+  CU_OK(h, cudaMemcpyAsync(out_ids, p.out_ids.p, static_cast<size_t>(B) * (T + 1) * 8, cudaMemcpyDeviceToDevice, s));
+  CU_OK(h, cudaMemcpyAsync(out_len, p.out_len.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
+  h->last_steps = steps;
+  h->ev_valid = true;
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_generate(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                               const b200t5_gen_params* params, int64_t* out_ids, int32_t* out_len, void* stream) {
+  TRY(validate(h, B, S, params));
+  if (!params || !input_ids || !out_ids || !out_len) return fail(h, B200T5_EINVAL, "null argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  return generate_impl(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask),
+                       B, S, params, reinterpret_cast<long long*>(out_ids), out_len, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200t5_generate_host(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B,
+                                    int S, const b200t5_gen_params* params, int64_t* out_ids, int32_t* out_len) {
+  TRY(validate(h, B, S, params));
+  if (!params || !input_ids || !out_ids || !out_len) return fail(h, B200T5_EINVAL, "null argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  TRY(ensure_plan(h, B, S, params->max_new_tokens));
+  Plan& p = *h->plan;
+  cudaStream_t s = h->exec_stream;
+  const size_t nb = static_cast<size_t>(B) * S * 8;
+  memcpy(p.h_ids, input_ids, nb);
+  CU_OK(h, cudaMemcpyAsync(p.ids_dev.p, p.h_ids, nb, cudaMemcpyHostToDevice, s));
+  if (attention_mask) {
+    memcpy(p.h_mask, attention_mask, nb);
+    CU_OK(h, cudaMemcpyAsync(p.mask_dev.p, p.h_mask, nb, cudaMemcpyHostToDevice, s));
+  }
+  // results land in the plan's own buffers; copy them out through pinned staging
+  DevBuf tmp_ids, tmp_len;
+  const int T = params->max_new_tokens;
+  CU_OK(h, tmp_ids.alloc(static_cast<size_t>(B) * (T + 1) * 8));
+  CU_OK(h, tmp_len.alloc(static_cast<size_t>(B) * 4));
+  TRY(generate_impl(h, p.ids_dev.as<long long>(), attention_mask ? p.mask_dev.as<long long>() : nullptr, B, S, params,
+                    tmp_ids.as<long long>(), tmp_len.as<int>(), s));
+  CU_OK(h, cudaMemcpyAsync(p.h_out, tmp_ids.p, static_cast<size_t>(B) * (T + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CU_OK(h, cudaMemcpyAsync(p.h_len, tmp_len.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+  CU_OK(h, cudaStreamSynchronize(s));
+  memcpy(out_ids, p.h_out, static_cast<size_t>(B) * (T + 1) * 8);
+  memcpy(out_len, p.h_len, static_cast<size_t>(B) * 4);
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
+  if (!h || !out) return fail(h, B200T5_EINVAL, "null argument");
+  memset(out, 0, sizeof(*out));
+  if (!h->ev_valid || !h->plan) return fail(h, B200T5_ESTATE, "no generate call recorded");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaEventSynchronize(h->ev[2]));
+  CU_OK(h, cudaEventElapsedTime(&out->encoder_ms, h->ev[0], h->ev[1]));
+  CU_OK(h, cudaEventElapsedTime(&out->decode_ms, h->ev[1], h->ev[2]));
+  out->decode_steps = h->last_steps;
+  out->kernel_launches = h->launches;
+  fill_stats_model(h, h->last_steps);
+  out->decode_algo_bytes = h->last_decode_bytes;
+  out->encoder_flops = h->last_enc_flops;
+  return B200T5_OK;
+}
+
+// ================================================================== parity hooks
+extern "C" int b200t5_encode(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                             void* enc_out_bf16, void* stream) {
+  TRY(validate(h, B, S, nullptr));
+  if (!input_ids || !enc_out_bf16) return fail(h, B200T5_EINVAL, "null argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int T = h->plan && h->plan->B == B && h->plan->S == S ? h->plan->Tmax : 1;
+  TRY(ensure_plan(h, B, S, T));
+  TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
+  CU_OK(h, cudaMemcpyAsync(enc_out_bf16, h->plan->xn.p, static_cast<size_t>(B) * S * h->c.d * 2, cudaMemcpyDeviceToDevice, s));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B,
+                                    int S, const int64_t* decoder_input_ids, int T, float* logits, void* stream) {
+  TRY(validate(h, B, S, nullptr));
+  if (!input_ids || !decoder_input_ids || !logits || T < 1) return fail(h, B200T5_EINVAL, "bad argument");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TRY(ensure_plan(h, B, S, T));
+  Plan& p = *h->plan;
+  const Cfg& c = h->c;
+  TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
+  TRY(run_cross_kv(h, s));
+  set_state_kernel<<<1, 1, 0, s>>>(p.state.as<DecodeState>(), 0);
+  DevBuf col;
+  CU_OK(h, col.alloc(static_cast<size_t>(B) * 8));
+  for (int t = 0; t < T; ++t) {
+    CU_OK(h, cudaMemcpy2DAsync(col.p, 8, reinterpret_cast<const long long*>(decoder_input_ids) + t, static_cast<size_t>(T) * 8, 8, B, cudaMemcpyDeviceToDevice, s));
+    force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+    TRY(run_decode_step(h, s, logits + static_cast<size_t>(t) * c.V, T * c.V, c.eos, c.pad, 0));
+  }
+  CU_OK(h, cudaStreamSynchronize(s));
+  return B200T5_OK;
+}
+
+// ================================================================== single-kernel hooks
+static int hook_device(int device) {
+  int sms = check_device(nullptr, device);
+  if (sms < 0) return sms;
+  cudaError_t e = init_kernel_attrs();
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+  return sms;
+}
+
+extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
+                                int pow_mode, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+  b200t5_ctx dummy;
+  dummy.num_sms = sms;
+  cudaError_t e = cudaErrorInvalidValue;
+  bf16* Cb = static_cast<bf16*>(C);
+  if (mode == 0) {
+    EpiStore::Params ep{Cb, N};
+    if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_STORE256, 0), &ep, s);
+    else if (bn == 32) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_STORE32, 1), &ep, s);
+    else if (bn == 64) e = launch_gemm<64, EpiStore>(ta, tb, M, N, K, 0, ep, sms, s);
+    else if (bn == 128) e = launch_gemm<128, EpiStore>(ta, tb, M, N, K, 0, ep, sms, s);
+  } else if (mode == 1) {
+    EpiResidual::Params ep{Cb, Cb, N};
+    if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_RES256, 0), &ep, s);
+    else if (bn == 32) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_RES32, 1), &ep, s);
+  } else if (mode == 2) {
+    EpiGeglu::Params ep{Cb, N / 2, pow_mode};
+    if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_GEGLU256, 0), &ep, s);
+    else if (bn == 64) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_GEGLU64, 1), &ep, s);
+  } else if (mode == 3) {
+    EpiStoreF32::Params ep{static_cast<float*>(C), N};
+    if (bn == 128) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_LOGITS128, 1), &ep, s);
+  }
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm(bn=%d, mode=%d): %s", bn, mode, cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  cudaError_t e = run_rmsnorm(nullptr, static_cast<const bf16*>(x), static_cast<const bf16*>(w), static_cast<bf16*>(y), M, d, eps, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "rmsnorm: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx,
+                                       int B, int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
+                                       const float* dist_bias, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (self) {
+    DevBuf st;
+    if (st.alloc(sizeof(DecodeState)) != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "alloc");
+    set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
+    attn_decode_kernel<true><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
+        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,
+        Tk, nullptr, nullptr, &st.as<DecodeState>()->step, dist_bias);
+    cudaStreamSynchronize(s);
+  } else {
+    attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
+        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,
+        Tk, extent, key_ok, nullptr, nullptr);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "attn_decode: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, const float* rel_bias,
+                                        const uint8_t* key_ok, const int32_t* extent, int B, int S, int H, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  const size_t smem = encoder_attn_smem_bytes(S);
+  cudaError_t e = smem <= 96 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
+  if (e == cudaSuccess) {
+    encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx), rel_bias, key_ok, extent, S, H);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_test_geglu(int device, const void* gate, const void* up, void* out, int64_t n, int pow_mode, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  geglu_elementwise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(gate), static_cast<const bf16*>(up), static_cast<bf16*>(out), n, pow_mode);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "geglu: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+}

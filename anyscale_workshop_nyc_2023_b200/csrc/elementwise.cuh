@@ -1,0 +1,203 @@
+// Memory-bound row kernels: embedding gather, T5 RMSNorm, mask preparation,
+// per-step arg-max finalisation + stopping bookkeeping.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------- embedding gather
+// x[m, :] = E[ids[m], :]   (modeling_t5.py:682).  One warp per row, 16-B vectors.
+__global__ void embed_rows_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ E,
+                                  __nv_bfloat16* __restrict__ x, int M, int d, int vocab) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  long long id = ids[row];
+  if (id < 0 || id >= vocab) id = 0;  // HF would raise an index error; ids are validated on the host
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(id) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * d);
+  for (int i = lane_id(); i < d / 8; i += 32) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------- T5 RMSNorm
+// HF (modeling_t5.py:55-68), bf16 weights:
+//   var = mean(float(x)^2)                      fp32
+//   y1  = bf16( float(x) * rsqrt(var + eps) )   first rounding
+//   y   = bf16( float(w) * float(y1) )          second rounding
+// One warp per row; the row stays in registers between the two passes.
+template <int kMaxVec>  // uint4 vectors per lane: d <= kMaxVec * 256
+__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                               __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = lane_id();
+  const int nvec = d >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  uint4 v[kMaxVec];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      const uint32_t wds[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(wds[j]), b = bf16_hi(wds[j]);
+        ss = fmaf(a, a, ss);
+        ss = fmaf(b, b, ss);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = rsqrtf(ss * (1.0f / static_cast<float>(d)) + eps);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const uint4 wv = wr[idx];
+      const uint32_t xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_round(bf16_lo(xs[j]) * inv);
+        const float b = bf16_round(bf16_hi(xs[j]) * inv);
+        o[j] = pack_bf16x2(bf16_lo(ws[j]) * a, bf16_hi(ws[j]) * b);
+      }
+      yr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- attention-mask preparation
+// attention_mask int64 [B,S] -> key_ok uint8 [B,S] and extent[b] = 1 + index of the last
+// attended key. A row with no attended key gets extent = S: every score is then
+// finfo(bf16).min and the fp32 softmax is uniform over all S keys, exactly what
+// HF's additive mask produces (masking_utils.py:610-612, modeling_t5.py:323-331).
+__global__ void prep_mask_kernel(const long long* __restrict__ mask, unsigned char* __restrict__ key_ok,
+                                 int* __restrict__ extent, int B, int S) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  int last = -1;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const bool ok = mask == nullptr ? true : mask[static_cast<size_t>(b) * S + j] != 0;
+    key_ok[static_cast<size_t>(b) * S + j] = ok ? 1 : 0;
+    if (ok) last = j;
+  }
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = -1;
+  __syncthreads();
+  atomicMax(&s_last, last);
+  __syncthreads();
+  if (threadIdx.x == 0) extent[b] = s_last < 0 ? S : s_last + 1;
+}
+
+// ---------------------------------------------------------------- decode state
+struct DecodeState {
+  int step;            // current decode position t (0-based)
+  int finished_rows;   // rows that have emitted EOS
+  int pad0, pad1;
+};
+
+// Start of generate(): x_dec[b] = E[decoder_start], out[b][0] = decoder_start, flags reset.
+__global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished, long long* __restrict__ out_ids,
+                                   int* __restrict__ out_len, int out_ld, int B, long long start_tok,
+                                   long long pad_tok, const __nv_bfloat16* __restrict__ E,
+                                   __nv_bfloat16* __restrict__ x, int d) {
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) {
+    st->step = 0;
+    st->finished_rows = 0;
+  }
+  if (b >= B) return;
+  for (int j = threadIdx.x; j < out_ld; j += blockDim.x)
+    out_ids[static_cast<size_t>(b) * out_ld + j] = j == 0 ? start_tok : pad_tok;
+  if (threadIdx.x == 0) {
+    unfinished[b] = 1;
+    out_len[b] = 0;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(start_tok) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// One CTA per row: reduce the per-tile (max, index) partials of the fused lm_head
+// epilogue with the torch.argmax tie rule (lowest index), then HF's greedy
+// bookkeeping (generation/utils.py:2793-2805):
+//   tok = unfinished ? argmax : pad ; out[b, t+1] = tok ; unfinished &= tok != eos
+// and fetch the embedding of tok as the next step's decoder input.
+__global__ void finalize_step_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int n_tiles,
+                                     DecodeState* st, int* __restrict__ unfinished,
+                                     long long* __restrict__ out_ids, int* __restrict__ out_len, int out_ld,
+                                     long long eos_tok, long long pad_tok, const __nv_bfloat16* __restrict__ E,
+                                     __nv_bfloat16* __restrict__ x, int d) {
+  const int b = blockIdx.x;
+  const int t = st->step;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+    const float v = pval[static_cast<size_t>(b) * n_tiles + i];
+    const int ix = pidx[static_cast<size_t>(b) * n_tiles + i];
+    if (v > best || (v == best && ix < bidx)) {
+      best = v;
+      bidx = ix;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) {
+      best = ov;
+      bidx = oi;
+    }
+  }
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ long long s_tok;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (lane_id() == 0) {
+    s_v[warp] = best;
+    s_i[warp] = bidx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nwarp; ++w) {
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bidx)) {
+        best = s_v[w];
+        bidx = s_i[w];
+      }
+    }
+    const int unf = unfinished[b];
+    const long long tok = unf ? static_cast<long long>(bidx) : pad_tok;
+    out_ids[static_cast<size_t>(b) * out_ld + t + 1] = tok;
+    if (unf) {
+      out_len[b] = t + 1;
+      if (tok == eos_tok) {
+        unfinished[b] = 0;
+        atomicAdd(&st->finished_rows, 1);
+      }
+    }
+    s_tok = tok;
+  }
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(s_tok) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void advance_step_kernel(DecodeState* st) { st->step += 1; }
+
+// teacher forcing (test hook): overwrite the next decoder input with a given token
+__global__ void force_token_kernel(const long long* __restrict__ toks, const __nv_bfloat16* __restrict__ E,
+                                   __nv_bfloat16* __restrict__ x, int d) {
+  const int b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(toks[b]) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace b200

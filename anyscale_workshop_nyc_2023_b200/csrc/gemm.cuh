@@ -1,0 +1,467 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   D[M,N] = A[M,K] * W[N,K]^T      (both operands K-major, i.e. nn.Linear layout)
+// TMA (128-B swizzle) -> smem ring -> tcgen05.mma (one elected thread) -> fp32
+// accumulators double-buffered in TMEM -> epilogue warps (tcgen05.ld) apply a
+// fused epilogue functor and write HBM directly.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+//
+// The epilogue functors are where the T5 rounding contract lives: HF eager bf16
+// rounds every Linear output to bf16 before anything else touches it
+// (transformers/models/t5/modeling_t5.py:277,298-299,338),
+// so each functor first rounds the fp32 accumulator to bf16 and only then fuses
+// the residual add / GeGLU / KV scatter / arg-max.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int m_tile, n_tile;
+};
+DEVINL TileCoord tile_coord(int tile, int tiles_m, int tiles_n, int m_fastest) {
+  TileCoord c;
+  if (m_fastest) {
+    c.m_tile = tile % tiles_m;
+    c.n_tile = tile / tiles_m;
+  } else {
+    c.n_tile = tile % tiles_n;
+    c.m_tile = tile / tiles_n;
+  }
+  return c;
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, int m_fastest, typename Epi::Params ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + kBM - 1) / kBM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kblocks = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < Cfg::kStages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, m_fastest);
+        const int m0 = tc.m_tile * kBM, n0 = tc.n_tile * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(sA, &tmA, &full[stage], kb * kBK, m0);
+          tma_load_2d(sB, &tmB, &full[stage], kb * kBK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
+          const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+            umma_bf16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, m_fastest);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const int m = tc.m_tile * kBM + q * 32 + lane;
+      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ======================================================================== epilogues
+// acc[32]: 32 consecutive fp32 accumulator columns of this thread's row.
+
+DEVINL void round_pack_32(const uint32_t (&acc)[32], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+}
+
+// Store 32 bf16 (64 B) to dst; columns [n0, n0+32) clipped to N in groups of 8.
+DEVINL void store_row_chunk(__nv_bfloat16* dst, const uint32_t (&p)[16], int n0, int N) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (n0 + g * 8 + 8 <= N) d4[g] = make_uint4(p[4 * g], p[4 * g + 1], p[4 * g + 2], p[4 * g + 3]);
+  }
+}
+
+// ---- plain store: C = bf16(acc)
+struct EpiStore {
+  struct Params {
+    __nv_bfloat16* C;
+    int ldc;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+      if (m_ok && n0 < N) {
+        uint32_t o[16];
+        round_pack_32(acc, o);
+        store_row_chunk(p.C + static_cast<size_t>(m) * p.ldc + n0, o, n0, N);
+      }
+    }
+  }
+};
+
+// ---- residual: C = bf16( float(R) + float(bf16(acc)) )   (modeling_t5.py:375,406,149)
+struct EpiResidual {
+  struct Params {
+    __nv_bfloat16* C;
+    const __nv_bfloat16* R;
+    int ld;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+      if (m_ok && n0 < N) {
+        const size_t off = static_cast<size_t>(m) * p.ld + n0;
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.R + off);
+        uint32_t o[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (n0 + g * 8 + 8 <= N) {
+            const uint4 r = r4[g];
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]));
+              const float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]));
+              o[g * 4 + j] = pack_bf16x2(bf16_lo(rw[j]) + y0, bf16_hi(rw[j]) + y1);
+            }
+          }
+        }
+        store_row_chunk(p.C + off, o, n0, N);
+      }
+    }
+  }
+};
+
+// gelu_new is evaluated exactly as HF eager evaluates it on bf16 tensors: every
+// elementwise op rounds its result to bf16 (transformers/activations.py:59-66;
+// SURVEY Appendix A.5). torch.pow(x, 3.0) on a bf16 CUDA tensor is x*x*x in bf16
+// arithmetic (two roundings, pow_mode 0); pow_mode 1 keeps the single-rounding variant
+// selectable so the exhaustive GPU test can pin whichever the installed torch does.
+// value of bf16(gelu_new(x) * lin) before the final rounding (pack_bf16x2 rounds it)
+DEVINL float geglu_bf16(float x, float lin, int pow_mode) {
+  const float half_x = bf16_round(0.5f * x);
+  const float x3 = pow_mode == 0 ? bf16_round(bf16_round(x * x) * x) : bf16_round(x * x * x);
+  const float t1 = bf16_round(0.044715f * x3);
+  const float t2 = bf16_round(x + t1);
+  const float t3 = bf16_round(0.7978845608028654f * t2);
+  const float t4 = bf16_round(tanhf(t3));
+  const float t5 = bf16_round(1.0f + t4);
+  return bf16_round(half_x * t5) * lin;
+}
+
+// ---- GeGLU: tile columns [0,BN/2) are wi_0 (gate) features, [BN/2,BN) the matching
+// wi_1 features (weights are interleaved per tile at finalize).
+//   out = bf16( gelu_new(bf16(gate)) * bf16(up) )          (modeling_t5.py:115-118)
+struct EpiGeglu {
+  struct Params {
+    __nv_bfloat16* out;  // [M, F]
+    int F;
+    int pow_mode;  // 0: x3 = bf16(bf16(x*x)*x)   1: x3 = bf16(x*x*x)   (set from the measured torch behaviour)
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/) {
+    constexpr int HALF = BN / 2;
+#pragma unroll 1
+    for (int c = 0; c < HALF / 32; ++c) {
+      uint32_t g[32], u[32];
+      tmem_ld_32x32(taddr + c * 32, g);
+      tmem_ld_32x32(taddr + HALF + c * 32, u);
+      tmem_ld_wait();
+      const int f0 = n_tile * HALF + c * 32;
+      if (m_ok && f0 < p.F) {
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float r[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float x = bf16_round(__uint_as_float(g[2 * i + e]));
+            const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
+            r[e] = geglu_bf16(x, lin, p.pow_mode);
+          }
+          o[i] = pack_bf16x2(r[0], r[1]);
+        }
+        store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
+      }
+    }
+  }
+};
+
+// ---- cross-attention K/V projection for all decoder layers at once (X1):
+// row m = (b, s) of the encoder output; column n = ((layer*2 + kv)*H + h)*64 + d.
+// Written straight into the decode arena  [layer][kv][B][H][S][64].
+struct EpiCrossKV {
+  struct Params {
+    __nv_bfloat16* arena;
+    int B, H, S;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+    const int b = m / p.S, s = m - b * p.S;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+      if (m_ok && n0 < N) {
+        const int hd = p.H * 64;
+        const int lkv = n0 / hd;
+        const int rem = n0 - lkv * hd;
+        const int h = rem >> 6, d0 = rem & 63;
+        uint32_t o[16];
+        round_pack_32(acc, o);
+        __nv_bfloat16* dst =
+            p.arena + ((((static_cast<size_t>(lkv) * p.B + b) * p.H + h) * p.S + s) << 6) + d0;
+        store_row_chunk(dst, o, n0, N);
+      }
+    }
+  }
+};
+
+// ---- decoder self-attention QKV for one new token: q -> q buffer, k/v appended in
+// place at row *step of the preallocated cache [kv][B][H][Tmax][64] (replaces the
+// torch.cat regrowth of transformers/cache_utils.py:119-120).
+struct EpiQkvDecode {
+  struct Params {
+    __nv_bfloat16* q;      // [B, I]
+    __nv_bfloat16* cache;  // this layer: [2][B][H][Tmax][64]
+    const int* step;       // device scalar: current decode position t
+    int B, H, Tmax;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+    const int I = p.H * 64;
+    const int t = *p.step;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+      if (m_ok && n0 < N) {
+        uint32_t o[16];
+        round_pack_32(acc, o);
+        __nv_bfloat16* dst;
+        if (n0 < I) {
+          dst = p.q + static_cast<size_t>(m) * I + n0;
+        } else {
+          const int r = n0 - I;
+          const int kv = r / I;
+          const int rem = r - kv * I;
+          const int h = rem >> 6, d0 = rem & 63;
+          dst = p.cache + ((((static_cast<size_t>(kv) * p.B + m) * p.H + h) * p.Tmax + t) << 6) + d0;
+        }
+        store_row_chunk(dst, o, n0, N);
+      }
+    }
+  }
+};
+
+// ---- lm_head + greedy arg-max: logits never reach HBM. Each (row, n_tile) emits the
+// max bf16-rounded logit of its BN columns and the lowest column index attaining it
+// (torch.argmax first-index contract; generation/utils.py:2762,2793). EOS is masked
+// to -inf while step < min_new_tokens (generation/logits_process.py:225-233).
+struct EpiArgmax {
+  struct Params {
+    float* pval;  // [M, n_tiles]
+    int* pidx;    // [M, n_tiles]
+    int n_tiles;
+    const int* step;
+    int eos, min_new;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+    float best = -INFINITY;
+    int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
+    const bool block_eos = *p.step < p.min_new;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + j;
+        float v = bf16_round(__uint_as_float(acc[j]));
+        if (n >= N || (block_eos && n == p.eos)) v = -INFINITY;
+        if (v > best) {  // ascending scan + strict '>' keeps the lowest index among equal maxima
+          best = v;
+          bidx = n;
+        }
+      }
+    }
+    if (m_ok) {
+      p.pval[static_cast<size_t>(m) * p.n_tiles + n_tile] = best;
+      p.pidx[static_cast<size_t>(m) * p.n_tiles + n_tile] = bidx;
+    }
+  }
+};
+
+// ---- fp32 logits store (test hook / teacher-forced parity): C = float(bf16(acc))
+struct EpiStoreF32 {
+  struct Params {
+    float* C;
+    int ldc;
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      tmem_ld_wait();
+      const int n0 = n_tile * BN + c * 32;
+      if (m_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < N) p.C[static_cast<size_t>(m) * p.ldc + n0 + j] = bf16_round(__uint_as_float(acc[j]));
+      }
+    }
+  }
+};
+
+// ======================================================================== host launch
+// Opt in to the large dynamic shared memory carve-out once per process/device
+// (done at b200t5_create so it never happens inside a stream capture).
+template <int BN, class Epi>
+cudaError_t prepare_gemm() {
+  return cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              GemmCfg<BN>::kSmemBytes);
+}
+
+template <int BN, class Epi>
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int m_fastest,
+                        const typename Epi::Params& ep, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tn_kernel<BN, Epi>;
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, m_fastest, ep);
+  return cudaGetLastError();
+}
+
+}  // namespace b200
