@@ -1,0 +1,286 @@
+"""`B200T5ForConditionalGeneration`: the object the reference predictor holds as ``self.model``.
+
+The reference's seam is duck-typed (NLP_workloads/Anyscale_job/predictor.py):
+    checkpoint.get_model(model_cls, **get_model_kwargs)   :68   -> model_cls.from_pretrained(dir, **kw)
+    self.model.device                                      :98
+    self.model.generate(**generate_kwargs) -> LongTensor   :102  (consumed by tokenizer.batch_decode :104)
+so passing ``model_cls=B200T5ForConditionalGeneration`` to ``BatchPredictor.from_checkpoint``
+(notebook lines 875-883) swaps the Hugging Face eager model for the sm_100a kernels behind
+libb200t5.so without touching the predictor.
+
+PyTorch is used for device memory and streams only; all arithmetic runs in the CUDA library.
+There is no CPU path: constructing the model without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import warnings
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import read_safetensors
+
+_HF_DEFAULT_MAX_LENGTH = 20  # GenerationConfig default the notebook's single-prompt cell relies on (NB:577)
+
+_IGNORED_WEIGHTS = ("decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight",)
+_ALIASES = ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class B200T5ForConditionalGeneration:
+    """FLAN-T5 greedy generation on one B200. API subset of transformers.T5ForConditionalGeneration
+    that the workshop's predictor and notebook cells touch."""
+
+    main_input_name = "input_ids"
+
+    def __init__(self, config: Dict[str, Any], device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("B200T5ForConditionalGeneration runs on a B200 only; there is no CPU fallback")
+        self._lib = _lib.load()
+        self._device = device
+        self.config = SimpleNamespace(**config)
+        self.generation_config = SimpleNamespace(
+            max_length=_HF_DEFAULT_MAX_LENGTH,
+            eos_token_id=config.get("eos_token_id", 1),
+            pad_token_id=config.get("pad_token_id", 0),
+            decoder_start_token_id=config.get("decoder_start_token_id", config.get("pad_token_id", 0)),
+        )
+        ffp = config.get("feed_forward_proj", "gated-gelu")
+        cfg = _lib.Config(
+            vocab_size=config["vocab_size"], d_model=config["d_model"], d_kv=config["d_kv"], d_ff=config["d_ff"],
+            num_heads=config["num_heads"], num_layers=config["num_layers"],
+            num_decoder_layers=config.get("num_decoder_layers") or config["num_layers"],
+            relative_attention_num_buckets=config.get("relative_attention_num_buckets", 32),
+            relative_attention_max_distance=config.get("relative_attention_max_distance", 128),
+            layer_norm_epsilon=config.get("layer_norm_epsilon", 1e-6),
+            pad_token_id=self.generation_config.pad_token_id,
+            eos_token_id=self.generation_config.eos_token_id,
+            decoder_start_token_id=self.generation_config.decoder_start_token_id,
+            is_gated_gelu=1 if ffp == "gated-gelu" else 0,
+            # HF decides "scale decoder outputs" from tie_word_embeddings (configuration_t5.py:82)
+            scale_decoder_outputs=0 if config.get("tie_word_embeddings", True) is False else 1,
+        )
+        h = C.c_void_p()
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        _lib.check(self._lib.b200t5_create(C.byref(cfg), index, C.byref(h)))
+        self._h = h
+        self._index = index
+        self.last_lengths: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ loading
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, device_map=None, torch_dtype=None,
+                        dtype=None, device=None, **kwargs) -> "B200T5ForConditionalGeneration":
+        """Load a Hugging Face T5 directory (config.json + model.safetensors | pytorch_model.bin).
+
+        `device_map="auto"` / `torch_dtype=` are accepted as the notebook passes them
+        (NB:881-882). Compute is bf16; a request for float16/float32 is honoured as "load and
+        round the weights to bf16" with a warning (the fp16 + fp32-`wo` mode is SURVEY 8f rank 1).
+        """
+        path = Path(pretrained_model_name_or_path)
+        if not (path / "config.json").exists():
+            raise FileNotFoundError(f"{path} is not a Hugging Face checkpoint directory (no config.json); "
+                                    "hub downloads are not available offline")
+        want = dtype if dtype is not None else torch_dtype
+        if want not in (None, torch.bfloat16, "bfloat16", "auto"):
+            warnings.warn(f"B200T5ForConditionalGeneration computes in bfloat16; requested {want} weights are "
+                          "rounded to bfloat16 on load", stacklevel=2)
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: B200T5ForConditionalGeneration has no CPU fallback")
+        if device is None:
+            if isinstance(device_map, (str, type(None))) or device_map == "auto":
+                device = torch.device("cuda", torch.cuda.current_device())
+            elif isinstance(device_map, dict):
+                device = torch.device(next(iter(device_map.values())))
+            else:
+                device = torch.device(device_map)
+        device = torch.device(device)
+        config = json.loads((path / "config.json").read_text())
+        model = cls(config, device)
+        model._load_weights(path)
+        return model
+
+    def _load_weights(self, path: Path) -> None:
+        st = path / "model.safetensors"
+        tensors: Dict[str, torch.Tensor] = {}
+        if st.exists():
+            for name, (dt, shape, arr) in read_safetensors(st).items():
+                a = np.array(arr)  # copy out of the memmap
+                if dt == "BF16":
+                    t = torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
+                else:
+                    t = torch.from_numpy(a)
+                tensors[name] = t
+        elif (path / "pytorch_model.bin").exists():
+            tensors = torch.load(path / "pytorch_model.bin", map_location="cpu", weights_only=True)
+        else:
+            raise FileNotFoundError(f"{path}: neither model.safetensors nor pytorch_model.bin found")
+        self.load_state_dict(tensors)
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        codes = {torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32}
+        with torch.cuda.device(self._index):
+            for name, t in state_dict.items():
+                if name in _IGNORED_WEIGHTS or name in _ALIASES:
+                    continue
+                if t.dtype not in codes:
+                    t = t.float()
+                dev = t.to(self._device).contiguous()
+                shape = (C.c_int64 * dev.dim())(*dev.shape)
+                _lib.check(self._lib.b200t5_set_weight(self._h, name.encode(), _ptr(dev), codes[dev.dtype], shape,
+                                                       dev.dim()), self._h)
+                del dev
+            _lib.check(self._lib.b200t5_finalize(self._h), self._h)
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    # ------------------------------------------------------------------ nn.Module-ish surface
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+    def eval(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (str, torch.device)) and torch.device(a) != self._device and torch.device(a).type != "cuda":
+                raise RuntimeError("B200T5ForConditionalGeneration cannot be moved off the GPU")
+        return self
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.b200t5_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ generation
+    def _gen_params(self, max_new_tokens, max_length, min_new_tokens, min_length, eos_token_id, pad_token_id,
+                    decoder_start_token_id, poll_interval) -> _lib.GenParams:
+        # GenerationMixin._prepare_generated_length (generation/utils.py:1619-1639): the decoder
+        # prompt is the single start token, so max_length = max_new_tokens + 1.
+        if max_new_tokens is None:
+            max_length = self.generation_config.max_length if max_length is None else max_length
+            max_new_tokens = int(max_length) - 1
+        if max_new_tokens < 1:
+            raise ValueError(f"max_new_tokens must be >= 1, got {max_new_tokens}")
+        if min_new_tokens is None:
+            min_new_tokens = max(int(min_length) - 1, 0) if min_length else 0
+        if isinstance(eos_token_id, (list, tuple)):
+            if len(eos_token_id) != 1:
+                raise NotImplementedError("multiple eos_token_id values are not supported")
+            eos_token_id = eos_token_id[0]
+        return _lib.GenParams(
+            max_new_tokens=int(max_new_tokens), min_new_tokens=int(min(min_new_tokens, max_new_tokens)),
+            eos_token_id=-1 if eos_token_id is None else int(eos_token_id),
+            pad_token_id=-1 if pad_token_id is None else int(pad_token_id),
+            decoder_start_token_id=-1 if decoder_start_token_id is None else int(decoder_start_token_id),
+            poll_interval=int(poll_interval),
+        )
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, attention_mask=None, *, max_new_tokens=None, max_length=None,
+                 min_new_tokens=None, min_length=None, eos_token_id=None, pad_token_id=None,
+                 decoder_start_token_id=None, do_sample=False, num_beams=1, poll_interval=8,
+                 **unused) -> torch.LongTensor:
+        """Greedy `generate`: returns int64 [B, 1+T'] on `self.device`, column 0 the decoder start
+        token, rows padded after their EOS, T' = steps until every row finished (<= max_new_tokens).
+        `labels` (which the reference passes, JOB/utils.py:31) and other HF kwargs that do not
+        change greedy decoding are accepted and ignored, as HF itself does (generation/utils.py:583)."""
+        if input_ids is None:
+            input_ids = unused.pop("inputs", None)
+        if input_ids is None:
+            raise ValueError("input_ids is required")
+        if do_sample or (num_beams is not None and num_beams != 1):
+            raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is implemented")
+        for k in ("temperature", "top_k", "top_p", "repetition_penalty", "no_repeat_ngram_size", "num_return_sequences",
+                  "logits_processor", "stopping_criteria", "forced_bos_token_id", "decoder_input_ids"):
+            if unused.get(k) not in (None, 1, 1.0):
+                raise NotImplementedError(f"generate({k}=...) is not supported by the B200 path")
+        gp = self._gen_params(max_new_tokens, max_length, min_new_tokens, min_length, eos_token_id, pad_token_id,
+                              decoder_start_token_id, poll_interval)
+        ids = torch.as_tensor(input_ids).to(device=self._device, dtype=torch.long).contiguous()
+        if ids.dim() != 2:
+            raise ValueError(f"input_ids must be [batch, seq], got {tuple(ids.shape)}")
+        B, S = ids.shape
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.config.vocab_size):
+            raise IndexError("input_ids contain token ids outside [0, vocab_size)")
+        mask = None
+        if attention_mask is not None:
+            mask = torch.as_tensor(attention_mask).to(device=self._device, dtype=torch.long).contiguous()
+            if mask.shape != ids.shape:
+                raise ValueError("attention_mask shape must match input_ids")
+        T = gp.max_new_tokens
+        with torch.cuda.device(self._index):
+            out = torch.empty((B, T + 1), dtype=torch.long, device=self._device)
+            lens = torch.empty((B,), dtype=torch.int32, device=self._device)
+            stream = torch.cuda.current_stream(self._device)
+            _lib.check(self._lib.b200t5_generate(self._h, _ptr(ids), _ptr(mask), B, S, C.byref(gp), _ptr(out),
+                                                 _ptr(lens), C.c_void_p(stream.cuda_stream)), self._h)
+            self.last_lengths = lens
+            steps = int(lens.max().item())  # synchronises; HF returns exactly the steps it ran
+        return out[:, : steps + 1]
+
+    def generate_host(self, input_ids: np.ndarray, attention_mask: Optional[np.ndarray] = None, **kw):
+        """numpy in / numpy out through b200t5_generate_host (the foreign-host entry point):
+        H2D copy, generation, D2H copy and synchronisation all happen inside the library."""
+        gp = self._gen_params(kw.get("max_new_tokens"), kw.get("max_length"), kw.get("min_new_tokens"),
+                              kw.get("min_length"), kw.get("eos_token_id"), kw.get("pad_token_id"),
+                              kw.get("decoder_start_token_id"), kw.get("poll_interval", 8))
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        B, S = ids.shape
+        mask = None if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
+        out = np.empty((B, gp.max_new_tokens + 1), dtype=np.int64)
+        lens = np.empty((B,), dtype=np.int32)
+        _lib.check(self._lib.b200t5_generate_host(
+            self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), B, S,
+            C.byref(gp), out.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)), self._h)
+        return out[:, : int(lens.max()) + 1], lens
+
+    def stats(self) -> Dict[str, float]:
+        s = _lib.Stats()
+        _lib.check(self._lib.b200t5_get_stats(self._h, C.byref(s)), self._h)
+        return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+    # ------------------------------------------------------------------ parity hooks (tests)
+    @torch.no_grad()
+    def encode(self, input_ids, attention_mask=None) -> torch.Tensor:
+        ids = torch.as_tensor(input_ids).to(self._device, torch.long).contiguous()
+        mask = None if attention_mask is None else torch.as_tensor(attention_mask).to(self._device, torch.long).contiguous()
+        B, S = ids.shape
+        out = torch.empty((B, S, self.config.d_model), dtype=torch.bfloat16, device=self._device)
+        with torch.cuda.device(self._index):
+            stream = torch.cuda.current_stream(self._device)
+            _lib.check(self._lib.b200t5_encode(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(out),
+                                               C.c_void_p(stream.cuda_stream)), self._h)
+            torch.cuda.synchronize(self._device)
+        return out
+
+    @torch.no_grad()
+    def decode_logits(self, input_ids, attention_mask, decoder_input_ids) -> torch.Tensor:
+        ids = torch.as_tensor(input_ids).to(self._device, torch.long).contiguous()
+        mask = None if attention_mask is None else torch.as_tensor(attention_mask).to(self._device, torch.long).contiguous()
+        dec = torch.as_tensor(decoder_input_ids).to(self._device, torch.long).contiguous()
+        B, S = ids.shape
+        T = dec.shape[1]
+        out = torch.empty((B, T, self.config.vocab_size), dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._index):
+            stream = torch.cuda.current_stream(self._device)
+            _lib.check(self._lib.b200t5_decode_logits(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(dec), T, _ptr(out),
+                                                      C.c_void_p(stream.cuda_stream)), self._h)
+        return out

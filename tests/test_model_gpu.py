@@ -1,0 +1,245 @@
+"""End-to-end parity of the CUDA path (through libb200t5.so) on a B200.
+
+Anchors, strongest first:
+  1. committed golden fixtures: transformers' own generate()/forward on seeded checkpoints
+     (tests/golden/make_golden.py, HF eager bf16 + fp32 on CPU);
+  2. oracle/t5_oracle.py with bf16 rounding emulation (pinned to the same fixtures on CPU);
+  3. HF eager bf16 on this GPU (same dtype, cuBLAS) when transformers is importable.
+
+Token IDs are integers and must match exactly wherever the decision is not a numerical
+near-tie: a (row, step) whose top-1/top-2 logit gap in the oracle is below TAU is a
+coin-flip between implementations that differ only in fp32 accumulation order,
+so rows are compared up to their first such step ("margin-gated"), and the ungated match
+rate is printed. Logit tolerance: bf16 outputs, |err| <= LOGIT_ATOL (about 4 bf16 ulps at
+the logit scale of these models), mean |err| <= LOGIT_MEAN.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from anyscale_workshop_nyc_2023_b200.synth import SPECS, make_state_dict, save_checkpoint, synthetic_token_batch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).resolve().parent / "golden"
+TAU = 0.13          # margin gate, in logit units (bf16 ulp at |logit| in [4,8) is 0.03125)
+# Tolerances are set from the measured noise floor between independent bf16 implementations of
+# the same forward (tools/diag_parity.py on a B200, profiles/diag_parity_r1.json): HF-bf16-GPU vs
+# HF-bf16-CPU differ by mean |dlogit| 0.17-0.20 (max 2.7) on FLAN-T5-small; ours vs HF-bf16-GPU
+# by mean 0.04-0.05. The 2-3 layer test models sit well below that.
+LOGIT_ATOL = 0.5
+LOGIT_MEAN = 0.05
+
+CASES = {"tiny_a": ("tiny", 1, 12), "tiny_full": ("tiny", 1, 10), "mini_a": ("mini", 2, 16)}
+
+
+@pytest.fixture(scope="module")
+def models(tmp_path_factory):
+    from anyscale_workshop_nyc_2023_b200.modeling import B200T5ForConditionalGeneration
+
+    cache = {}
+
+    def get(spec_name, seed):
+        key = (spec_name, seed)
+        if key not in cache:
+            d = tmp_path_factory.mktemp(f"ckpt_{spec_name}_{seed}")
+            save_checkpoint(d, SPECS[spec_name], seed=seed)
+            cache[key] = (B200T5ForConditionalGeneration.from_pretrained(d, device_map="auto", torch_dtype=torch.bfloat16), d)
+        return cache[key]
+
+    return get
+
+
+def oracle_for(spec_name, seed, emulate=True):
+    from oracle.t5_oracle import T5Oracle
+
+    return T5Oracle(make_state_dict(SPECS[spec_name], seed), SPECS[spec_name], emulate_bf16=emulate)
+
+
+def pad_to(a, width, pad=0):
+    if a.shape[1] >= width:
+        return a
+    return np.concatenate([a, np.full((a.shape[0], width - a.shape[1]), pad, a.dtype)], axis=1)
+
+
+def gated_prefix_match(ours, ref, margins, tau=TAU):
+    """Rows must agree up to (excluding) the first step whose oracle margin is <= tau."""
+    w = max(ours.shape[1], ref.shape[1])
+    ours, ref = pad_to(ours, w), pad_to(ref, w)
+    n_rows, gated_ok, full_ok = ours.shape[0], 0, 0
+    for b in range(n_rows):
+        m = margins[b]
+        low = np.where(~(m > tau))[0]  # NaN (finished) counts as safe
+        low = [s for s in low if not np.isnan(m[s])]
+        first_low = low[0] if low else m.shape[0]
+        upto = 1 + first_low  # column 0 is the start token; step s writes column s+1
+        gated_ok += int((ours[b, :upto] == ref[b, :upto]).all())
+        full_ok += int((ours[b] == ref[b]).all())
+    return gated_ok / n_rows, full_ok / n_rows
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_generate(models, case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}.npz")
+    model, _ = models(spec_name, seed)
+    out = model.generate(input_ids=torch.from_numpy(g["ids"]), attention_mask=torch.from_numpy(g["mask"]),
+                         labels=torch.from_numpy(g["ids"]), max_new_tokens=T).cpu().numpy()
+    orc = oracle_for(spec_name, seed)
+    otoks, margins = orc.generate(g["ids"], g["mask"], max_new_tokens=T, return_margins=True)
+    assert out[:, 0].tolist() == [0] * out.shape[0]
+    gated_o, full_o = gated_prefix_match(out, otoks, margins)
+    gated_h, full_h = gated_prefix_match(out, g["tokens_bf16"], margins)
+    print(f"{case}: vs oracle gated={gated_o:.2f} full={full_o:.2f} | vs HF-bf16 golden gated={gated_h:.2f} full={full_h:.2f}")
+    assert gated_o == 1.0 and gated_h == 1.0
+    # forced length: min_new_tokens == max_new_tokens -> every row is exactly T tokens long
+    forced = model.generate(input_ids=torch.from_numpy(g["ids"]), attention_mask=torch.from_numpy(g["mask"]),
+                            max_new_tokens=T, min_new_tokens=T).cpu().numpy()
+    assert forced.shape == (g["ids"].shape[0], T + 1)
+    assert (forced[:, 1:] != SPECS[spec_name].eos_token_id).all()
+    ftoks, fm = orc.generate(g["ids"], g["mask"], max_new_tokens=T, min_new_tokens=T, return_margins=True)
+    gated_f, full_f = gated_prefix_match(forced, ftoks, fm)
+    gated_fh, full_fh = gated_prefix_match(forced, g["forced_bf16"], fm)
+    print(f"{case} forced: vs oracle gated={gated_f:.2f} full={full_f:.2f} | vs golden gated={gated_fh:.2f} full={full_fh:.2f}")
+    assert gated_f == 1.0 and gated_fh == 1.0
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_golden_logits_and_encoder(models, case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}.npz")
+    model, _ = models(spec_name, seed)
+    valid = g["mask"].astype(bool)
+    enc = model.encode(g["ids"], g["mask"]).float().cpu().numpy()
+    e_err = np.abs(enc - g["enc_bf16"])[valid]
+    print(f"{case}: encoder max err {e_err.max():.4f} mean {e_err.mean():.5f} (scale {np.abs(g['enc_bf16'])[valid].max():.2f})")
+    assert e_err.max() <= 0.15 and e_err.mean() <= 0.01
+    dec_in = g["tokens_bf16"][:, :-1]
+    logits = model.decode_logits(g["ids"], g["mask"], dec_in).cpu().numpy()
+    ref = g["logits_bf16"]
+    # positions after a row's EOS are fed pad tokens in both; compare everything
+    err = np.abs(logits - ref)
+    print(f"{case}: logits max err {err.max():.4f} mean {err.mean():.5f} (scale {np.abs(ref).max():.2f})")
+    assert err.max() <= LOGIT_ATOL and err.mean() <= LOGIT_MEAN
+    # and against the fp32 dependency run: bf16 noise only
+    err32 = np.abs(logits - g["logits_fp32"])
+    assert err32.max() <= 1.0 and err32.mean() <= 0.1
+
+
+def test_host_entry_point_and_lengths(models):
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(7, 19, SPECS["tiny"].vocab_size, seed=5, lengths="uniform")
+    dev = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=14).cpu().numpy()
+    host, lens = model.generate_host(ids, mask, max_new_tokens=14)
+    assert dev.shape == host.shape and (dev == host).all()
+    eos, pad = 1, 0
+    for b in range(ids.shape[0]):
+        row = host[b, 1:]
+        n = int(lens[b])
+        assert (row[n:] == pad).all()
+        assert (row[: max(n - 1, 0)] != eos).all()
+        if n < row.shape[0]:
+            assert row[n - 1] == eos
+    st = model.stats()
+    assert st["kernel_launches"] > 0 and st["decode_steps"] >= int(lens.max())
+
+
+def test_default_max_length_and_validation(models):
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(2, 8, SPECS["tiny"].vocab_size, seed=6, lengths="full")
+    out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), min_length=20)
+    assert out.shape == (2, 20)  # HF default max_length=20 -> 19 new tokens + start token
+    with pytest.raises(NotImplementedError):
+        model.generate(input_ids=torch.from_numpy(ids), do_sample=True)
+    with pytest.raises(IndexError):
+        model.generate(input_ids=torch.full((1, 4), 10 ** 6))
+    assert model.device.type == "cuda"
+
+
+@pytest.mark.parametrize("B,S,lengths", [(1, 1, "full"), (3, 5, "uniform"), (9, 130, "uniform"), (2, 64, "full")])
+def test_edge_shapes_vs_oracle(models, B, S, lengths):
+    spec = SPECS["tiny"]
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(B, S, spec.vocab_size, seed=B * 100 + S, lengths=lengths, min_len=1)
+    T = 8
+    out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=T).cpu().numpy()
+    otoks, margins = oracle_for("tiny", 1).generate(ids, mask, max_new_tokens=T, return_margins=True)
+    gated, full = gated_prefix_match(out, otoks, margins)
+    print(f"edge B={B} S={S}: gated={gated:.2f} full={full:.2f}")
+    assert gated == 1.0
+
+
+def test_mask_holes_and_fully_masked_row(models):
+    """Non-prefix masks and an all-zero mask row follow HF's additive-mask semantics."""
+    spec = SPECS["tiny"]
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(4, 20, spec.vocab_size, seed=77, lengths="full")
+    mask[1, 3:7] = 0
+    mask[2, :] = 0
+    T = 6
+    orc = oracle_for("tiny", 1)
+    dec = np.zeros((4, T), dtype=np.int64)
+    dec[:, 1:] = np.random.default_rng(0).integers(3, spec.vocab_size, size=(4, T - 1))
+    ref = orc.decode_logits(ids, mask, dec)
+    got = model.decode_logits(ids, mask, dec).cpu().numpy()
+    err = np.abs(got - ref)
+    print(f"mask holes: logits max err {err.max():.4f} mean {err.mean():.5f}")
+    assert err.max() <= LOGIT_ATOL and err.mean() <= LOGIT_MEAN
+
+
+def test_no_attention_mask_equals_all_ones(models):
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(3, 12, SPECS["tiny"].vocab_size, seed=8, lengths="full")
+    a = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=6)
+    b = model.generate(input_ids=torch.from_numpy(ids), max_new_tokens=6)
+    assert torch.equal(a, b)
+
+
+def test_determinism_and_batch_invariance(models):
+    """Same inputs -> identical tokens; a row's result does not depend on its batch neighbours
+    (each (b,h) problem is independent and tile shapes do not change the per-row arithmetic)."""
+    spec = SPECS["mini"]
+    model, _ = models("mini", 2)
+    ids, mask = synthetic_token_batch(6, 33, spec.vocab_size, seed=9, lengths="uniform")
+    a = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=10, min_new_tokens=10).cpu()
+    b = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=10, min_new_tokens=10).cpu()
+    assert torch.equal(a, b)
+    solo = model.generate(input_ids=torch.from_numpy(ids[2:3]), attention_mask=torch.from_numpy(mask[2:3]), max_new_tokens=10, min_new_tokens=10).cpu()
+    assert torch.equal(a[2:3], solo)
+
+
+def test_flan_t5_small_vs_hf_gpu(models):
+    """Real FLAN-T5-small architecture; anchor = HF eager bf16 on this same GPU."""
+    pytest.importorskip("transformers")
+    from oracle.hf_anchor import hf_generate, hf_teacher_forced_logits, load_hf_model
+
+    spec = SPECS["flan-t5-small"]
+    model, ckpt = models("flan-t5-small", 3)
+    B, S, T = 16, 96, 24
+    ids, mask = synthetic_token_batch(B, S, spec.vocab_size, seed=21, lengths="uniform")
+    hf = load_hf_model(ckpt, dtype=torch.bfloat16, device="cuda")
+    ref = hf_generate(hf, ids, mask, T, min_new_tokens=T)
+    out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=T, min_new_tokens=T).cpu().numpy()
+    assert out.shape == ref.shape
+    # margins from HF's own teacher-forced bf16 logits along HF's path
+    lg = hf_teacher_forced_logits(hf, ids, mask, ref[:, :-1])
+    lg[:, :, spec.eos_token_id] = -np.inf
+    top2 = np.partition(lg, -2, axis=-1)[:, :, -2:]
+    margins = top2[:, :, 1] - top2[:, :, 0]
+    gated, full = gated_prefix_match(out, ref, margins)
+    tok_rate = (out == ref).mean()
+    print(f"flan-t5-small vs HF-bf16-GPU: gated rows={gated:.2f} ungated rows={full:.2f} token agreement={tok_rate:.3f}")
+    ours_lg = model.decode_logits(ids, mask, ref[:, :-1]).cpu().numpy()
+    gpu_lg = hf_teacher_forced_logits(hf, ids, mask, ref[:, :-1])
+    cpu_lg = hf_teacher_forced_logits(load_hf_model(ckpt, dtype=torch.bfloat16, device="cpu"), ids, mask, ref[:, :-1])
+    err = np.abs(ours_lg - gpu_lg)
+    floor = np.abs(gpu_lg - cpu_lg)
+    print(f"flan-t5-small teacher-forced logits: ours vs HF-bf16-GPU max {err.max():.4f} mean {err.mean():.5f} | "
+          f"noise floor HF-bf16-GPU vs HF-bf16-CPU max {floor.max():.4f} mean {floor.mean():.5f}")
+    assert gated == 1.0
+    # the CUDA path must track the same-dtype GPU anchor at least twice as closely as two
+    # stock bf16 runs of the dependency (GPU vs CPU) track each other
+    assert err.mean() <= 0.5 * floor.mean() and err.max() <= 1.5 * floor.max()
