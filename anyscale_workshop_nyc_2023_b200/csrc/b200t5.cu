@@ -925,6 +925,49 @@ extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
   return B200T5_OK;
 }
 
+// ================================================================== measurement hook
+// Times the roofline-setting kernel (cross-attention decode, D7) alone, on the cross-KV arena
+// of the last generate call: `reps` sweeps over all decoder layers (each launch streams a
+// different 2*B*I*S*2-byte slab, far larger than L2), CUDA events on the launching stream.
+extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_per_launch, double* bytes_per_launch,
+                                       void* stream) {
+  if (!h || !avg_ms_per_launch || !bytes_per_launch || reps < 1) return fail(h, B200T5_EINVAL, "bad argument");
+  if (!h->plan) return fail(h, B200T5_ESTATE, "no plan: call generate first");
+  CU_OK(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan& p = *h->plan;
+  const Cfg& c = h->c;
+  const size_t cross_layer = static_cast<size_t>(2) * p.B * c.I * p.S;
+  auto sweep = [&]() {
+    for (int l = 0; l < c.Ld; ++l) {
+      bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
+      attn_decode_kernel<false><<<p.B * c.H, kAttnDecThreads, p.S * sizeof(float), s>>>(
+          p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<bf16>(), c.H, p.S,
+          p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr);
+    }
+  };
+  sweep();  // warm-up
+  cudaEvent_t e0, e1;
+  CU_OK(h, cudaEventCreate(&e0));
+  CU_OK(h, cudaEventCreate(&e1));
+  CU_OK(h, cudaEventRecord(e0, s));
+  for (int r = 0; r < reps; ++r) sweep();
+  CU_OK(h, cudaEventRecord(e1, s));
+  CU_OK(h, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU_OK(h, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CU_OK(h, cudaGetLastError());
+  *avg_ms_per_launch = ms / (static_cast<float>(reps) * c.Ld);
+  std::vector<int> ext(p.B);
+  CU_OK(h, cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost));
+  double sum_s = 0;
+  for (int v : ext) sum_s += v;
+  *bytes_per_launch = 2.0 * 2.0 * c.I * sum_s;  // K and V rows of every attended key, bf16
+  return B200T5_OK;
+}
+
 // ================================================================== parity hooks
 extern "C" int b200t5_encode(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
                              void* enc_out_bf16, void* stream) {

@@ -97,12 +97,14 @@ class B200T5ForConditionalGeneration:
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: B200T5ForConditionalGeneration has no CPU fallback")
         if device is None:
-            if isinstance(device_map, (str, type(None))) or device_map == "auto":
-                device = torch.device("cuda", torch.cuda.current_device())
+            if device_map is None or device_map in ("auto", "balanced", "sequential"):
+                device = torch.device("cuda", torch.cuda.current_device())  # one replica per process/GPU
             elif isinstance(device_map, dict):
                 device = torch.device(next(iter(device_map.values())))
             else:
                 device = torch.device(device_map)
+        if torch.device(device).type == "cuda" and torch.device(device).index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         device = torch.device(device)
         config = json.loads((path / "config.json").read_text())
         model = cls(config, device)
@@ -256,6 +258,15 @@ class B200T5ForConditionalGeneration:
         s = _lib.Stats()
         _lib.check(self._lib.b200t5_get_stats(self._h, C.byref(s)), self._h)
         return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
+
+    def bench_cross_attention(self, reps: int = 5) -> Dict[str, float]:
+        """Average launch time of the cross-attention decode kernel on the last call's KV arena."""
+        ms, nbytes = C.c_float(), C.c_double()
+        with torch.cuda.device(self._index):
+            stream = torch.cuda.current_stream(self._device)
+            _lib.check(self._lib.b200t5_bench_cross_attn(self._h, reps, C.byref(ms), C.byref(nbytes),
+                                                         C.c_void_p(stream.cuda_stream)), self._h)
+        return {"ms_per_launch": ms.value, "bytes_per_launch": nbytes.value}
 
     # ------------------------------------------------------------------ parity hooks (tests)
     @torch.no_grad()

@@ -113,6 +113,13 @@ int b200t5_generate_host(b200t5_handle h, const int64_t* input_ids, const int64_
                          const b200t5_gen_params* params, int64_t* out_ids, int32_t* out_len);
 int b200t5_get_stats(b200t5_handle h, b200t5_stats* out);
 
+/* ---- measurement hook (bench.py) ---------------------------------------------------- */
+/* Times the cross-attention decode kernel alone over the cross-KV arena of the last generate
+ * call (reps sweeps over all decoder layers, CUDA events on `stream`); returns the average
+ * launch duration and the algorithmic bytes one launch must read (K+V rows of attended keys). */
+int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_per_launch, double* bytes_per_launch,
+                            void* stream);
+
 /* ---- parity hooks (used by tests/ only) --------------------------------------------- */
 /* Encoder last hidden state after the final RMSNorm, bf16 [B,S,d_model] (device). */
 int b200t5_encode(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,

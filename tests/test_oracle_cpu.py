@@ -1,0 +1,78 @@
+"""CPU-only: the oracle against the committed golden vectors (outputs of the reference's own
+dependency, transformers' T5ForConditionalGeneration, see tests/golden/make_golden.py) and against
+the known-answer vectors of SURVEY Appendix B."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from anyscale_workshop_nyc_2023_b200.synth import SPECS, make_state_dict, round_bf16
+from oracle.t5_oracle import T5Oracle, gelu_new_f32, relative_bucket
+
+GOLD = Path(__file__).resolve().parent / "golden"
+CASES = {"tiny_a": ("tiny", 1, 12), "tiny_full": ("tiny", 1, 10), "mini_a": ("mini", 2, 16)}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp32_oracle_matches_hf_fp32_exactly(case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}.npz")
+    o = T5Oracle(make_state_dict(SPECS[spec_name], seed), SPECS[spec_name], emulate_bf16=False)
+    (toks,) = o.generate(g["ids"], g["mask"], max_new_tokens=T)
+    assert toks.shape == g["tokens_fp32"].shape and (toks == g["tokens_fp32"]).all()  # integer work: bit-exact
+    (forced,) = o.generate(g["ids"], g["mask"], max_new_tokens=T, min_new_tokens=T)
+    assert (forced == g["forced_fp32"]).all()
+    logits = o.decode_logits(g["ids"], g["mask"], g["tokens_fp32"][:, :-1])
+    assert np.abs(logits - g["logits_fp32"]).max() <= 1e-4  # fp32 vs fp32: accumulation order only
+    enc = o.encode(g["ids"], g["mask"])
+    assert np.abs(enc - g["enc_fp32"])[g["mask"].astype(bool)].max() <= 1e-4
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_bf16_emulation_tracks_hf_bf16(case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}.npz")
+    o = T5Oracle(make_state_dict(SPECS[spec_name], seed), SPECS[spec_name], emulate_bf16=True)
+    (toks,) = o.generate(g["ids"], g["mask"], max_new_tokens=T)
+    assert toks.shape == g["tokens_bf16"].shape and (toks == g["tokens_bf16"]).all()
+    (forced,) = o.generate(g["ids"], g["mask"], max_new_tokens=T, min_new_tokens=T)
+    assert (forced == g["forced_bf16"]).all()
+    logits = o.decode_logits(g["ids"], g["mask"], g["tokens_bf16"][:, :-1])
+    # bf16 outputs: at most ~2 ulps (0.0625 at |logit| in [4,8)) where a rounding flipped upstream
+    assert np.abs(logits - g["logits_bf16"]).max() <= 0.13
+    assert (logits == round_bf16(logits)).all()
+
+
+def test_bucket_known_answers():
+    # value holds from each listed rel upward
+    bi = {-200: 15, -90: 14, -63: 13, -45: 12, -31: 11, -22: 10, -15: 9, -11: 8, -7: 7, -6: 6, -5: 5, -4: 4, -3: 3, -2: 2,
+          -1: 1, 0: 0, 1: 17, 2: 18, 3: 19, 4: 20, 5: 21, 6: 22, 7: 23, 8: 24, 12: 25, 16: 26, 23: 27, 32: 28, 46: 29,
+          64: 30, 91: 31, 300: 31}
+    for rel, want in bi.items():
+        assert int(relative_bucket(np.array([rel]), True)[0]) == want, rel
+    causal = {0: 0, 15: 15, 16: 16, 18: 16, 19: 17, 20: 17, 21: 18, 24: 19, 27: 20, 31: 21, 35: 22, 40: 23, 46: 24, 52: 25,
+              59: 26, 67: 27, 77: 28, 87: 29, 99: 30, 112: 30, 113: 31, 5000: 31}
+    for n, want in causal.items():
+        assert int(relative_bucket(np.array([-n]), False)[0]) == want, n
+    assert int(relative_bucket(np.array([5]), False)[0]) == 0  # future positions are invalid for the decoder
+
+
+def test_bucket_matches_dependency_and_c_abi():
+    torch = pytest.importorskip("torch")
+    from transformers.models.t5.modeling_t5 import T5Attention
+
+    from anyscale_workshop_nyc_2023_b200 import _lib
+
+    lib = _lib.load()
+    rel = np.arange(-700, 701)
+    for bidir in (True, False):
+        hf = T5Attention._relative_position_bucket(torch.from_numpy(rel), bidirectional=bidir, num_buckets=32, max_distance=128).numpy()
+        assert (relative_bucket(rel, bidir) == hf).all()
+        c = np.array([lib.b200t5_relative_bucket(int(r), int(bidir), 32, 128) for r in rel])
+        assert (c == hf).all()
+
+
+def test_gelu_new_known_answers():
+    x = np.array([-3, -1, -0.5, 0, 0.5, 1, 3], dtype=np.float32)
+    want = np.array([-0.00363743, -0.15880799, -0.15428600, 0, 0.34571400, 0.84119201, 2.99636269], dtype=np.float32)
+    assert np.abs(gelu_new_f32(x) - want).max() < 1e-6

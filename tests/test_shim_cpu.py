@@ -1,0 +1,107 @@
+"""CPU-only: the Ray-compatible shim and the predictor/preprocess mirrors, driven exactly as the
+notebook drives them (BASELINE config 1: CPU map_batches path with the HF model)."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from anyscale_workshop_nyc_2023_b200 import rayshim
+from anyscale_workshop_nyc_2023_b200.parallel import restore_order, shard_block_indices
+from anyscale_workshop_nyc_2023_b200.preprocess import make_preprocess_function
+from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_alpaca_rows
+from anyscale_workshop_nyc_2023_b200.workload import ASSETS, checkpoint_dir, make_batch_predictor
+
+
+class HFOnCpu:
+    """model_cls stand-in with from_pretrained(dir, **kw): the dependency's own model on CPU."""
+
+    @staticmethod
+    def from_pretrained(path, **kw):
+        from oracle.hf_anchor import load_hf_model
+
+        return load_hf_model(path, dtype=torch.float32, device="cpu")
+
+
+def test_dataset_ops_preserve_order():
+    ds = rayshim.data.from_huggingface(synthetic_alpaca_rows(23))
+    assert ds.count() == 23 and set(ds.columns()) == {"instruction", "input", "output", "text"}
+    lim = ds.limit(10)
+    assert lim.count() == 10
+    df = lim.to_pandas()
+    assert df["instruction"].tolist() == synthetic_alpaca_rows(23)["instruction"][:10]
+    doubled = lim.map_batches(lambda b: pd.DataFrame({"n": b["instruction"].str.len()}), batch_size=3)
+    assert doubled.to_pandas()["n"].tolist() == [len(s) for s in df["instruction"]]
+    assert len(lim.take(4)) == 4
+    both = rayshim.data.from_huggingface({"train": synthetic_alpaca_rows(5), "test": synthetic_alpaca_rows(4)})
+    assert both["train"].count() == 5 and both["test"].count() == 4
+
+
+def test_preprocess_pair_template_and_padding():
+    fn = make_preprocess_function(str(ASSETS / "tokenizer"))
+    out = fn(pd.DataFrame({"instruction": ["Describe the water cycle.", "vi"], "input": ["2, 4, 8", ""]}))
+    assert set(out) == {"input_ids", "attention_mask", "labels"}
+    assert out["input_ids"].shape == (2, 512) and out["input_ids"].dtype == np.int64
+    assert (out["labels"] == out["input_ids"]).all()
+    row = out["input_ids"][1]
+    n = int(out["attention_mask"][1].sum())
+    assert row[n - 1] == 1 and row[n - 2] == 1  # "A </s> B </s>" with an empty B still has two EOS
+    assert (row[n:] == 0).all()
+
+
+def test_install_registers_ray_modules():
+    assert rayshim.install() or True
+    import ray
+    from ray.data.preprocessors import BatchMapper  # noqa: F401
+    from ray.train.batch_predictor import BatchPredictor  # noqa: F401
+    from ray.train.predictor import Predictor  # noqa: F401
+
+    assert getattr(ray, "__b200_shim__", False)
+    with pytest.raises(NotImplementedError):
+        from ray.train.huggingface import HuggingFaceTrainer
+
+        HuggingFaceTrainer()
+
+
+def test_notebook_flow_on_cpu_config1():
+    """from_checkpoint -> predict -> to_pandas -> join, as notebook :875-934, tiny model on CPU."""
+    from ray.data.preprocessors import BatchMapper
+
+    ckpt = checkpoint_dir("tiny", seed=1)
+    rows = synthetic_alpaca_rows(12)
+    validation = rayshim.data.from_huggingface(rows).limit(10)
+    prep = BatchMapper(make_preprocess_function(str(ckpt), max_length=32), batch_format="pandas", batch_size=4096)
+    bp = make_batch_predictor(ckpt, model_cls=HFOnCpu, preprocessor=prep)
+    prediction = bp.predict(validation, batch_size=4, max_new_tokens=6)
+    input_pd, pred_pd = validation.to_pandas(), prediction.to_pandas()
+    joined = input_pd.join(pred_pd, how="inner")
+    assert len(joined) == 10 and "generated_output" in joined.columns
+    assert all(isinstance(s, str) for s in joined["generated_output"])
+    # row alignment: predicting one row alone gives the same text as the batched run
+    single = bp.predict(validation.limit(1), batch_size=4, max_new_tokens=6).to_pandas()
+    assert single["generated_output"][0] == pred_pd["generated_output"][0]
+
+
+def test_predictor_matches_direct_generate():
+    from anyscale_workshop_nyc_2023_b200.predictor import HuggingFaceModelPredictor
+    from anyscale_workshop_nyc_2023_b200.synth import synthetic_token_batch
+    from oracle.hf_anchor import hf_generate, load_hf_model
+    from transformers import T5Tokenizer
+
+    ckpt = checkpoint_dir("tiny", seed=1)
+    model = load_hf_model(ckpt)
+    tok = T5Tokenizer.from_pretrained(str(ckpt))
+    ids, mask = synthetic_token_batch(5, 16, SPECS["tiny"].vocab_size, seed=3, lengths="uniform")
+    p = HuggingFaceModelPredictor(model, tokenizer=tok)
+    df = p.predict(pd.DataFrame({"input_ids": list(ids), "attention_mask": list(mask), "labels": list(ids)}), max_new_tokens=5)
+    want = tok.batch_decode(hf_generate(model, ids, mask, 5), skip_special_tokens=True)
+    assert df["generated_output"].tolist() == want
+    only = p._predict_numpy({"input_ids": ids, "attention_mask": mask, "junk": ids}, feature_columns=["input_ids", "attention_mask"], max_new_tokens=5)
+    assert only["generated_output"].tolist() == want
+
+
+def test_sharding_roundtrip():
+    for n, w in [(10, 1), (10, 3), (7, 8), (0, 2)]:
+        per_rank = [[f"b{i}" for i in shard_block_indices(n, r, w)] for r in range(w)]
+        assert restore_order(per_rank, n) == [f"b{i}" for i in range(n)]
+    with pytest.raises(ValueError):
+        shard_block_indices(4, 2, 2)
