@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--lengths", default="full", choices=["full", "alpaca", "uniform"])
-    ap.add_argument("--cpu-sample", type=int, default=16, help="prompts in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="prompts in the CPU-baseline sample")
+    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the in-run CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -57,6 +58,22 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def log(msg: str) -> None:
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def effective_cores() -> int:
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(n, 1)
 
 
 def workload_name(a):
@@ -123,13 +140,18 @@ def run_cpu_path(a, steps: int, warmup: int, sample: int):
     from anyscale_workshop_nyc_2023_b200.predictor import HuggingFaceModelPredictor
     from transformers import T5Tokenizer
 
-    cores = os.cpu_count() or 1
+    # eager generate is ~4k tiny ATen ops per decode step: beyond a few dozen threads the
+    # per-op fork/join cost dominates, so the intra-op pool is capped (the count used is reported)
+    cores = min(effective_cores(), int(os.environ.get("B200T5_CPU_THREADS", "32")))
     torch.set_num_threads(cores)
+    log(f"cpu path: {cores} torch threads (host reports {os.cpu_count()} cpus), {sample} prompts/step")
     spec = SPECS[a.model]
     ckpt = checkpoint_dir(a.model, seed=0)
     model = load_hf_model(ckpt, dtype=torch.float32, device="cpu")
     tok = T5Tokenizer.from_pretrained(str(ckpt))
     pred = HuggingFaceModelPredictor(model, tokenizer=tok)
+    ids0, mask0 = synthetic_token_batch(1, 16, spec.vocab_size, seed=1, lengths="full")
+    pred._predict_numpy({"input_ids": ids0, "attention_mask": mask0}, max_new_tokens=2)  # lazy-init costs, untimed
     times = []
     for s in range(warmup + steps):
         ids, mask = synthetic_token_batch(sample, a.seq, spec.vocab_size, seed=1000 + s, lengths=a.lengths)
@@ -138,6 +160,7 @@ def run_cpu_path(a, steps: int, warmup: int, sample: int):
                                  max_new_tokens=a.new, min_new_tokens=a.new)
         dt = time.perf_counter() - t0
         assert len(df) == sample
+        log(f"cpu path step {s}: {dt:.1f} s")
         if s >= warmup:
             times.append(dt)
     total = sum(times)
@@ -153,7 +176,7 @@ def main_reference(a):
     if rank != 0:
         return 0
     steps = max(a.steps, 1)
-    warm = min(a.warmup, 1)  # CPU steps are seconds long; one warm-up pass pages the weights in
+    warm = min(a.warmup, 1)  # CPU steps are seconds long; at most one warm-up pass
     base = run_cpu_path(a, steps, warm, a.cpu_sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
@@ -194,6 +217,7 @@ def main_b200(a):
         dist.barrier()
     ckpt = checkpoint_dir(a.model, seed=0)
 
+    log(f"rank {rank}/{world}: checkpoint at {ckpt}; loading the model")
     bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.bfloat16)
     from anyscale_workshop_nyc_2023_b200.rayshim.train import _ScoringWorker
 
@@ -216,7 +240,11 @@ def main_b200(a):
 
     # ---------------- value: inputs resident in HBM, CUDA events
     for s in range(W):
+        t_w = time.perf_counter()
         model.generate(input_ids=dev_batches[s][0], attention_mask=dev_batches[s][1], **gen_kw)
+        torch.cuda.synchronize()
+        if rank == 0:
+            log(f"warm-up step {s}: {1e3 * (time.perf_counter() - t_w):.1f} ms {model.stats()}")
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -239,6 +267,8 @@ def main_b200(a):
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
+    if rank == 0:
+        log(f"device-resident: {elapsed_ms / K:.1f} ms/step")
     # ---------------- e2e: host numpy batch -> DataFrame of strings through the plug-in
     for s in range(min(W, 2)):
         predictor._predict_numpy({"input_ids": host[s][0], "attention_mask": host[s][1], "labels": host[s][0]}, **gen_kw)
@@ -298,9 +328,20 @@ def main_b200(a):
                         "achieved_tflops": enc_flops / (enc_ms / 1e3) / 1e12, "frac_of_bf16_sustained": enc_flops / (enc_ms / 1e3) / 1e12 / tf_peak},
         }
         if world == 1 and not a.no_cpu_baseline:
-            base = run_cpu_path(a, steps=1, warmup=1, sample=a.cpu_sample)
-            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+            log("timing the CPU baseline (bounded sample, own process)")
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                   "--model", a.model, "--batch", str(a.batch), "--seq", str(a.seq), "--new", str(a.new),
+                   "--lengths", a.lengths, "--cpu-sample", str(a.cpu_sample)]
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            env["CUDA_VISIBLE_DEVICES"] = ""
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=a.cpu_timeout, env=env)
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            except (subprocess.TimeoutExpired, IndexError, ValueError, KeyError) as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": effective_cores(), "kind": "port",
+                                        "sample": f"not finished within {a.cpu_timeout}s ({type(e).__name__})"}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

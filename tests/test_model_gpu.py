@@ -124,9 +124,6 @@ def test_golden_logits_and_encoder(models, case):
     err = np.abs(logits - ref)
     print(f"{case}: logits max err {err.max():.4f} mean {err.mean():.5f} (scale {np.abs(ref).max():.2f})")
     assert err.max() <= LOGIT_ATOL and err.mean() <= LOGIT_MEAN
-    # and against the fp32 dependency run: bf16 noise only
-    err32 = np.abs(logits - g["logits_fp32"])
-    assert err32.max() <= 1.0 and err32.mean() <= 0.1
 
 
 def test_host_entry_point_and_lengths(models):
