@@ -22,7 +22,7 @@ namespace b200 {
 
 constexpr float kBf16Min = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
 constexpr int kAttnDecThreads = 128;
-constexpr int kAttnDecUnroll = 4;
+constexpr int kAttnDecUnroll = 8;
 
 DEVINL float dot8(const uint4& kv, const float (&qf)[8]) {
   float s = bf16_lo(kv.x) * qf[0];
@@ -51,6 +51,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
   __shared__ float s_red[4][64];
   __shared__ float s_stat[8];
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = lane >> 3, dg = lane & 7;
@@ -162,6 +164,112 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
     const float o0 = (s_red[0][d0] + s_red[1][d0]) + (s_red[2][d0] + s_red[3][d0]);
     const float o1 = (s_red[0][d0 + 1] + s_red[1][d0 + 1]) + (s_red[2][d0 + 1] + s_red[3][d0 + 1]);
     *reinterpret_cast<uint32_t*>(ctx + (static_cast<size_t>(b) * H + h) * 64 + d0) = pack_bf16x2(o0, o1);
+  }
+}
+
+// ---------------------------------------------------------------- self-attention, one warp per (b,h)
+// The decoder's own cache holds at most max_new_tokens (128) keys: a (b,h) problem is 16-32 KB,
+// so a whole CTA with block-wide barriers is mostly overhead. Here each warp owns one (b,h):
+// same arithmetic and rounding points as attn_decode_kernel<true>, only warp-level syncs.
+constexpr int kSelfWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kSelfWarpsPerCta * 32)
+self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
+                             const __nv_bfloat16* __restrict__ Kc,  // [B][H][Tk][64]
+                             const __nv_bfloat16* __restrict__ Vc,
+                             __nv_bfloat16* __restrict__ ctx,       // [B, H*64]
+                             int BH, int H, int Tk, const int* __restrict__ step,
+                             const float* __restrict__ dist_bias) {  // [H][Tk]
+  extern __shared__ float s_all[];  // kSelfWarpsPerCta * Tk floats
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * kSelfWarpsPerCta + warp;
+  if (bh >= BH) return;
+  const int h = bh % H;
+  float* sc = s_all + warp * Tk;
+  const int ks = lane >> 3, dg = lane & 7;
+  const int t = *step;
+  const int nkeys = t + 1;
+  const size_t slab = static_cast<size_t>(bh) * Tk * 64;
+  const __nv_bfloat16* Kp = Kc + slab + dg * 8;
+  const __nv_bfloat16* Vp = Vc + slab + dg * 8;
+  float qf[8];
+  {
+    const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
+    qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
+    qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+  }
+  constexpr int U = 4;
+  for (int jb = 0; jb < nkeys; jb += 4 * U) {
+    uint4 kv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + ks + 4 * u;
+      kv[u] = j < nkeys ? ldg_nc_v4(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + ks + 4 * u;
+      float s = dot8(kv[u], qf);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (dg == 0 && j < nkeys) sc[j] = bf16_round(bf16_round(s) + dist_bias[h * Tk + (t - j)]);
+    }
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < nkeys; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int j = lane; j < nkeys; j += 32) sc[j] = bf16_round(sc[j] / sum);
+  __syncwarp();
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int jb = 0; jb < nkeys; jb += 4 * U) {
+    uint4 vv[U];
+    float p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + ks + 4 * u;
+      const bool ok = j < nkeys;
+      vv[u] = ok ? ldg_nc_v4(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      p[u] = ok ? sc[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc[0] = fmaf(p[u], bf16_lo(vv[u].x), acc[0]);
+      acc[1] = fmaf(p[u], bf16_hi(vv[u].x), acc[1]);
+      acc[2] = fmaf(p[u], bf16_lo(vv[u].y), acc[2]);
+      acc[3] = fmaf(p[u], bf16_hi(vv[u].y), acc[3]);
+      acc[4] = fmaf(p[u], bf16_lo(vv[u].z), acc[4]);
+      acc[5] = fmaf(p[u], bf16_hi(vv[u].z), acc[5]);
+      acc[6] = fmaf(p[u], bf16_lo(vv[u].w), acc[6]);
+      acc[7] = fmaf(p[u], bf16_hi(vv[u].w), acc[7]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (ks == 0) {
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]);
+    o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]);
+    o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(bh) * 64 + dg * 8) = o;
   }
 }
 

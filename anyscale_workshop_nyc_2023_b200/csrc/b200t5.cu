@@ -95,9 +95,19 @@ __global__ void convert_to_bf16_kernel(const void* src, int dtype, bf16* dst, si
     dst[i] = __float2bfloat16_rn(v);
   }
 }
-__global__ void geglu_elementwise_kernel(const bf16* gate, const bf16* up, bf16* out, long long n, int pow_mode) {
+// mode 0: the engine's path (table lookup); 1/2: op-by-op arithmetic with pow_mode 1/0
+__global__ void geglu_elementwise_kernel(const bf16* gate, const bf16* up, bf16* out, long long n, int mode, GeluLut lut) {
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(geglu_bf16(__bfloat162float(gate[i]), __bfloat162float(up[i]), pow_mode));
+  if (i >= n) return;
+  const float x = __bfloat162float(gate[i]);
+  const float g = mode == 0 ? gelu_from_lut(x, lut.table, lut.lo, lut.hi) : gelu_new_bf16_exact(x, mode == 1 ? 1 : 0);
+  out[i] = __float2bfloat16_rn(g * __bfloat162float(up[i]));
+}
+__global__ void build_gelu_table_kernel(uint16_t* full, int pow_mode) {
+  const uint32_t bits = blockIdx.x * blockDim.x + threadIdx.x;  // every bf16 bit pattern
+  if (bits >= 65536u) return;
+  const float g = gelu_new_bf16_exact(__uint_as_float(bits << 16), pow_mode);
+  full[bits] = static_cast<uint16_t>(__float_as_uint(g) >> 16);
 }
 __global__ void set_state_kernel(DecodeState* st, int step) {
   st->step = step;
@@ -155,6 +165,8 @@ struct DecLayerW {
   CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
 };
 
+constexpr int kMaxChains = 8;
+
 struct Plan {
   int B = 0, S = 0, Tmax = 0;
   // encoder workspace
@@ -169,7 +181,15 @@ struct Plan {
   DevBuf state, unfinished, out_ids, out_len, ids_dev, mask_dev;
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
-  CUtensorMap tm_xn, tm_ctx, tm_hff, tm_dxn, tm_dctx, tm_dh;
+  CUtensorMap tm_xn, tm_ctx, tm_hff;
+  // decode chains: the batch is cut into independent row ranges that run concurrently (one
+  // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
+  struct Chain {
+    int b0 = 0, nb = 0;
+    CUtensorMap tm_dxn, tm_dctx, tm_dh;
+  };
+  int n_chains = 1;
+  Chain chains[kMaxChains];
   // decode-step graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -211,6 +231,11 @@ struct b200t5_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   int pow_mode = 0;
+  bool use_pdl = true;
+  GeluLut gelu_lut{nullptr, 0, 0};
+  int chains_override = 0;
+  cudaStream_t chain_streams[kMaxChains] = {};
+  cudaEvent_t chain_ev[kMaxChains + 1] = {};
   // stats of the last generate
   int64_t launches = 0;
   int last_steps = 0;
@@ -265,42 +290,41 @@ extern "C" int b200t5_relative_bucket(int rel, int bidirectional, int num_bucket
 }
 
 // ================================================================== GEMM dispatch
-static cudaError_t run_gemm(b200t5_ctx* h, const GemmOp& g, const void* ep, cudaStream_t s) {
+static cudaError_t run_gemm(b200t5_ctx* h, const GemmOp& g, const void* ep, cudaStream_t s, bool pdl = false) {
   h->launches++;
   switch (g.kind) {
     case G_STORE256:
-      return launch_gemm<256, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s);
+      return launch_gemm<256, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s, pdl);
     case G_RES256:
-      return launch_gemm<256, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s);
+      return launch_gemm<256, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s, pdl);
     case G_GEGLU256:
-      return launch_gemm<256, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s);
+      return launch_gemm<256, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s, pdl);
     case G_CROSSKV256:
-      return launch_gemm<256, EpiCrossKV>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiCrossKV::Params*>(ep), h->num_sms, s);
+      return launch_gemm<256, EpiCrossKV>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiCrossKV::Params*>(ep), h->num_sms, s, pdl);
     case G_QKVDEC64:
-      return launch_gemm<64, EpiQkvDecode>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiQkvDecode::Params*>(ep), h->num_sms, s);
+      return launch_gemm<64, EpiQkvDecode>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiQkvDecode::Params*>(ep), h->num_sms, s, pdl);
     case G_STORE32:
-      return launch_gemm<32, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s);
+      return launch_gemm<32, EpiStore>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStore::Params*>(ep), h->num_sms, s, pdl);
     case G_RES32:
-      return launch_gemm<32, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s);
+      return launch_gemm<32, EpiResidual>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiResidual::Params*>(ep), h->num_sms, s, pdl);
     case G_GEGLU64:
-      return launch_gemm<64, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s);
+      return launch_gemm<64, EpiGeglu>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiGeglu::Params*>(ep), h->num_sms, s, pdl);
     case G_ARGMAX128:
-      return launch_gemm<128, EpiArgmax>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiArgmax::Params*>(ep), h->num_sms, s);
+      return launch_gemm<128, EpiArgmax>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiArgmax::Params*>(ep), h->num_sms, s, pdl);
     case G_LOGITS128:
-      return launch_gemm<128, EpiStoreF32>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStoreF32::Params*>(ep), h->num_sms, s);
+      return launch_gemm<128, EpiStoreF32>(g.tmA, g.tmB, g.M, g.N, g.K, g.m_fastest, *static_cast<const EpiStoreF32::Params*>(ep), h->num_sms, s, pdl);
   }
   return cudaErrorInvalidValue;
 }
 
 static cudaError_t run_rmsnorm(b200t5_ctx* h, const bf16* x, const bf16* w, bf16* y, int M, int d, float eps,
-                               cudaStream_t s) {
+                               cudaStream_t s, bool pdl = false) {
   if (h) h->launches++;
   const int wpb = 8;
   const int grid = (M + wpb - 1) / wpb;
-  if (d <= 1024) rmsnorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, w, y, M, d, eps);
-  else if (d <= 4096) rmsnorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, w, y, M, d, eps);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (d <= 1024) return launch_kernel(rmsnorm_kernel<4>, dim3(grid), dim3(wpb * 32), 0, s, pdl, x, w, y, M, d, eps);
+  if (d <= 4096) return launch_kernel(rmsnorm_kernel<16>, dim3(grid), dim3(wpb * 32), 0, s, pdl, x, w, y, M, d, eps);
+  return cudaErrorInvalidValue;
 }
 
 static cudaError_t init_kernel_attrs() {
@@ -311,7 +335,58 @@ static cudaError_t init_kernel_attrs() {
   PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
+  if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kSelfWarpsPerCta * 4096 * 4)) != cudaSuccess)
+    return e;
   return cudaFuncSetAttribute(encoder_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+// gelu_new over all 65536 bf16 inputs, evaluated once on the device with the exact op-by-op
+// arithmetic; the host keeps only the magnitude window in which neither shortcut holds.
+struct GeluLutOwner {
+  DevBuf table;
+  GeluLut lut{nullptr, 0, 0};
+  int pow_mode = -1;
+};
+static GeluLutOwner g_gelu;  // one process drives one GPU
+
+static int ensure_gelu_lut(b200t5_ctx* h, int pow_mode, GeluLut* out) {
+  if (g_gelu.lut.table && g_gelu.pow_mode == pow_mode) {
+    *out = g_gelu.lut;
+    return B200T5_OK;
+  }
+  DevBuf full;
+  CU_OK(h, full.alloc(65536 * 2));
+  build_gelu_table_kernel<<<256, 256>>>(full.as<uint16_t>(), pow_mode);
+  CU_OK(h, cudaGetLastError());
+  std::vector<uint16_t> t(65536);
+  CU_OK(h, cudaMemcpy(t.data(), full.p, 65536 * 2, cudaMemcpyDeviceToHost));
+  auto half_bits = [](uint16_t xb) {  // bf16(0.5 * x) for a bf16 bit pattern, round-to-nearest-even
+    uint32_t u = static_cast<uint32_t>(xb) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    f *= 0.5f;
+    memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+  };
+  int lo = 0;
+  while (lo < 0x7F80 && t[lo] == half_bits(static_cast<uint16_t>(lo)) && t[0x8000 | lo] == half_bits(static_cast<uint16_t>(0x8000 | lo))) ++lo;
+  int hi = 0x7F80;
+  while (hi > lo && t[hi - 1] == static_cast<uint16_t>(hi - 1) && t[0x8000 | (hi - 1)] == 0x8000) --hi;
+  const int n = hi - lo;
+  if (n < 0 || 2 * n * 2 > kEpiSmemBytes) return fail(h, B200T5_ECUDA, "gelu table window [%#x,%#x) does not fit the epilogue scratch", lo, hi);
+  std::vector<uint16_t> compact(static_cast<size_t>(2) * (n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) {
+    compact[i] = t[lo + i];
+    compact[n + i] = t[0x8000 | (lo + i)];
+  }
+  CU_OK(h, g_gelu.table.alloc(compact.size() * 2));
+  CU_OK(h, cudaMemcpy(g_gelu.table.p, compact.data(), compact.size() * 2, cudaMemcpyHostToDevice));
+  g_gelu.lut = GeluLut{g_gelu.table.as<uint16_t>(), lo, hi};
+  g_gelu.pow_mode = pow_mode;
+  *out = g_gelu.lut;
+  return B200T5_OK;
 }
 
 // ================================================================== lifecycle
@@ -341,6 +416,10 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   h->dec.resize(h->c.Ld);
   const char* pm = getenv("B200T5_POW_MODE");
   h->pow_mode = pm ? atoi(pm) : 0;
+  const char* pdl_env = getenv("B200T5_PDL");
+  h->use_pdl = pdl_env ? atoi(pdl_env) != 0 : true;
+  const char* ch_env = getenv("B200T5_CHAINS");
+  h->chains_override = ch_env ? atoi(ch_env) : 0;
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->exec_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
@@ -353,7 +432,16 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
       return fail(nullptr, B200T5_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ke));
     }
   }
+  {
+    int lrc = ensure_gelu_lut(nullptr, h->pow_mode, &h->gelu_lut);
+    if (lrc != B200T5_OK) {
+      delete h;
+      return lrc;
+    }
+  }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < kMaxChains; ++i) cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking);
+  for (int i = 0; i <= kMaxChains; ++i) cudaEventCreateWithFlags(&h->chain_ev[i], cudaEventDisableTiming);
   *out = h;
   return B200T5_OK;
 }
@@ -365,6 +453,10 @@ extern "C" int b200t5_destroy(b200t5_handle h) {
   h->plan.reset();
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->exec_stream) cudaStreamDestroy(h->exec_stream);
+  for (int i = 0; i < kMaxChains; ++i)
+    if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]);
+  for (int i = 0; i <= kMaxChains; ++i)
+    if (h->chain_ev[i]) cudaEventDestroy(h->chain_ev[i]);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -628,9 +720,22 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_xn, pl->xn.p, M, d, 128);
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
   TMAP(h, &pl->tm_hff, pl->hff.p, M, F, 128);
-  TMAP(h, &pl->tm_dxn, pl->dxn.p, B, d, 128);
-  TMAP(h, &pl->tm_dctx, pl->dctx.p, B, I, 128);
-  TMAP(h, &pl->tm_dh, pl->dh.p, B, F, 128);
+  {
+    // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
+    int nc = B >= 128 ? 4 : (B >= 64 ? 2 : 1);
+    if (h->chains_override > 0) nc = h->chains_override;
+    if (nc > kMaxChains) nc = kMaxChains;
+    if (nc > B) nc = B;
+    pl->n_chains = nc;
+    for (int i = 0; i < nc; ++i) {
+      Plan::Chain& ch = pl->chains[i];
+      ch.b0 = static_cast<int>(static_cast<long long>(B) * i / nc);
+      ch.nb = static_cast<int>(static_cast<long long>(B) * (i + 1) / nc) - ch.b0;
+      TMAP(h, &ch.tm_dxn, pl->dxn.as<bf16>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
+      TMAP(h, &ch.tm_dctx, pl->dctx.as<bf16>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
+      TMAP(h, &ch.tm_dh, pl->dh.as<bf16>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
+    }
+  }
   h->plan = std::move(pl);
   return B200T5_OK;
 }
@@ -683,7 +788,7 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     }
     CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln1.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
     {
-      EpiGeglu::Params ep{p.hff.as<bf16>(), F, h->pow_mode};
+      EpiGeglu::Params ep{p.hff.as<bf16>(), F, h->gelu_lut};
       CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
     }
     {
@@ -704,73 +809,108 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
 }
 
 // ================================================================== one decode step
+// One chain = rows [b0, b0+nb) of the batch through all decoder layers, the lm_head and the
+// greedy bookkeeping. Rows are independent, so chains only share read-only state (weights, the
+// step counter) and write disjoint row ranges of the same buffers.
 // logits_out == nullptr: fused arg-max + bookkeeping; otherwise fp32 logits are written to
 // logits_out (row stride ldl) and no token is chosen (teacher forcing).
-static int run_decode_step(b200t5_ctx* h, cudaStream_t s, float* logits_out, int ldl, long long eos, long long pad,
-                           int min_new) {
+static int run_decode_chain(b200t5_ctx* h, cudaStream_t s, const Plan::Chain& ch, float* logits_out, int ldl,
+                            long long eos, long long pad, int min_new) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
   const int B = p.B, S = p.S, d = c.d, I = c.I, F = c.F, H = c.H, T = p.Tmax;
+  const int b0 = ch.b0, nb = ch.nb;
   DecodeState* st = p.state.as<DecodeState>();
   const int* step = &st->step;
   const size_t self_layer = static_cast<size_t>(2) * B * I * T;
   const size_t cross_layer = static_cast<size_t>(2) * B * I * S;
   const int wi_tiles = (F + 31) / 32;
+  const bool pdl = h->use_pdl;  // programmatic dependent launch: prologues overlap the previous kernel's tail
+  bf16* dx = p.dx.as<bf16>() + static_cast<size_t>(b0) * d;
+  bf16* dxn = p.dxn.as<bf16>() + static_cast<size_t>(b0) * d;
+  bf16* dq = p.dq.as<bf16>() + static_cast<size_t>(b0) * I;
+  bf16* dctx = p.dctx.as<bf16>() + static_cast<size_t>(b0) * I;
+  bf16* dh = p.dh.as<bf16>() + static_cast<size_t>(b0) * F;
   for (int l = 0; l < c.Ld; ++l) {
     DecLayerW& w = h->dec[l];
-    bf16* skv = p.self_kv.as<bf16>() + l * self_layer;
-    bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
-    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln0.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    // [kv][B][H][T|S][64]: a row offset of b0 is a pointer offset inside each kv plane
+    bf16* skv = p.self_kv.as<bf16>() + l * self_layer + static_cast<size_t>(b0) * I * T;
+    bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer + static_cast<size_t>(b0) * I * S;
+    CU_OK(h, run_rmsnorm(h, dx, w.ln0.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
     {
-      EpiQkvDecode::Params ep{p.dq.as<bf16>(), skv, step, B, H, T};
-      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_qkv, B, 3 * I, d, G_QKVDEC64, 1), &ep, s));
+      EpiQkvDecode::Params ep{dq, skv, step, B, H, T};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_qkv, nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
     }
-    attn_decode_kernel<true><<<B * H, kAttnDecThreads, T * sizeof(float), s>>>(
-        p.dq.as<bf16>(), skv, skv + static_cast<size_t>(B) * I * T, p.dctx.as<bf16>(), H, T, nullptr, nullptr, step,
-        p.dec_bias.as<float>());
+    CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
+                           dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, dq, skv,
+                           skv + static_cast<size_t>(B) * I * T, dctx, nb * H, H, T, step, p.dec_bias.as<float>()));
     h->launches++;
     {
-      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
-      CU_OK(h, run_gemm(h, mk(p.tm_dctx, w.tm_o, B, d, I, G_RES32, 1), &ep, s));
+      EpiResidual::Params ep{dx, dx, d};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dctx, w.tm_o, nb, d, I, G_RES32, 1), &ep, s, pdl));
     }
-    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln1.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, dx, w.ln1.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
     {
-      EpiStore::Params ep{p.dq.as<bf16>(), I};
-      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_cq, B, I, d, G_STORE32, 1), &ep, s));
+      EpiStore::Params ep{dq, I};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_cq, nb, I, d, G_STORE32, 1), &ep, s, pdl));
     }
-    attn_decode_kernel<false><<<B * H, kAttnDecThreads, S * sizeof(float), s>>>(
-        p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(B) * I * S, p.dctx.as<bf16>(), H, S, p.extent.as<int>(),
-        p.key_ok.as<unsigned char>(), nullptr, nullptr);
+    CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
+                           dq, ckv, ckv + static_cast<size_t>(B) * I * S, dctx, H, S, p.extent.as<int>() + b0,
+                           p.key_ok.as<unsigned char>() + static_cast<size_t>(b0) * S, nullptr, nullptr));
     h->launches++;
     {
-      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
-      CU_OK(h, run_gemm(h, mk(p.tm_dctx, w.tm_co, B, d, I, G_RES32, 1), &ep, s));
+      EpiResidual::Params ep{dx, dx, d};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dctx, w.tm_co, nb, d, I, G_RES32, 1), &ep, s, pdl));
     }
-    CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), w.ln2.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, dx, w.ln2.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
     {
-      EpiGeglu::Params ep{p.dh.as<bf16>(), F, h->pow_mode};
-      CU_OK(h, run_gemm(h, mk(p.tm_dxn, w.tm_wi, B, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s));
+      EpiGeglu::Params ep{dh, F, h->gelu_lut};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_wi, nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
     }
     {
-      EpiResidual::Params ep{p.dx.as<bf16>(), p.dx.as<bf16>(), d};
-      CU_OK(h, run_gemm(h, mk(p.tm_dh, w.tm_ffo, B, d, F, G_RES32, 1), &ep, s));
+      EpiResidual::Params ep{dx, dx, d};
+      CU_OK(h, run_gemm(h, mk(ch.tm_dh, w.tm_ffo, nb, d, F, G_RES32, 1), &ep, s, pdl));
     }
   }
-  CU_OK(h, run_rmsnorm(h, p.dx.as<bf16>(), h->dec_final_ln.as<bf16>(), p.dxn.as<bf16>(), B, d, c.eps, s));
+  CU_OK(h, run_rmsnorm(h, dx, h->dec_final_ln.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
   if (logits_out) {
-    EpiStoreF32::Params ep{logits_out, ldl};
-    CU_OK(h, run_gemm(h, mk(p.tm_dxn, h->tm_lm, B, c.V, d, G_LOGITS128, 1), &ep, s));
+    EpiStoreF32::Params ep{logits_out + static_cast<size_t>(b0) * ldl, ldl};
+    CU_OK(h, run_gemm(h, mk(ch.tm_dxn, h->tm_lm, nb, c.V, d, G_LOGITS128, 1), &ep, s, pdl));
   } else {
-    EpiArgmax::Params ep{p.pval.as<float>(), p.pidx.as<int>(), p.n_vtiles, step, static_cast<int>(eos), min_new};
-    CU_OK(h, run_gemm(h, mk(p.tm_dxn, h->tm_lm, B, c.V, d, G_ARGMAX128, 1), &ep, s));
-    finalize_step_kernel<<<B, 128, 0, s>>>(p.pval.as<float>(), p.pidx.as<int>(), p.n_vtiles, st, p.unfinished.as<int>(),
-                                           p.out_ids.as<long long>(), p.out_len.as<int>(), T + 1, eos, pad,
-                                           h->shared.as<bf16>(), p.dx.as<bf16>(), d);
+    float* pval = p.pval.as<float>() + static_cast<size_t>(b0) * p.n_vtiles;
+    int* pidx = p.pidx.as<int>() + static_cast<size_t>(b0) * p.n_vtiles;
+    EpiArgmax::Params ep{pval, pidx, p.n_vtiles, step, static_cast<int>(eos), min_new};
+    CU_OK(h, run_gemm(h, mk(ch.tm_dxn, h->tm_lm, nb, c.V, d, G_ARGMAX128, 1), &ep, s, pdl));
+    CU_OK(h, launch_kernel(finalize_step_kernel, dim3(nb), dim3(128), 0, s, pdl, pval, pidx, p.n_vtiles, st,
+                           p.unfinished.as<int>() + b0, p.out_ids.as<long long>() + static_cast<size_t>(b0) * (T + 1),
+                           p.out_len.as<int>() + b0, T + 1, eos, pad, h->shared.as<bf16>(), dx, d));
     h->launches++;
   }
-  advance_step_kernel<<<1, 1, 0, s>>>(st);
+  return B200T5_OK;
+}
+
+// All chains of one step. `fork` runs them concurrently on the chain streams (used while
+// capturing the step graph); otherwise they run back to back on `s`.
+static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logits_out, int ldl, long long eos,
+                           long long pad, int min_new) {
+  Plan& p = *h->plan;
+  if (fork && p.n_chains > 1) {
+    CU_OK(h, cudaEventRecord(h->chain_ev[0], s));
+    for (int i = 1; i < p.n_chains; ++i) CU_OK(h, cudaStreamWaitEvent(h->chain_streams[i], h->chain_ev[0], 0));
+    for (int i = 0; i < p.n_chains; ++i) {
+      cudaStream_t cs = i == 0 ? s : h->chain_streams[i];
+      TRY(run_decode_chain(h, cs, p.chains[i], logits_out, ldl, eos, pad, min_new));
+      if (i > 0) {
+        CU_OK(h, cudaEventRecord(h->chain_ev[i], cs));
+        CU_OK(h, cudaStreamWaitEvent(s, h->chain_ev[i], 0));
+      }
+    }
+  } else {
+    for (int i = 0; i < p.n_chains; ++i) TRY(run_decode_chain(h, s, p.chains[i], logits_out, ldl, eos, pad, min_new));
+  }
+  // joins every chain; not PDL-launched so that it sees all of them complete
+  CU_OK(h, launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, s, false, p.state.as<DecodeState>()));
   h->launches++;
-  CU_OK(h, cudaGetLastError());
   return B200T5_OK;
 }
 
@@ -788,7 +928,7 @@ static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new
   }
   const int64_t before = h->launches;
   CU_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int rc = run_decode_step(h, h->cap_stream, nullptr, 0, eos, pad, min_new);
+  int rc = run_decode_step(h, h->cap_stream, true, nullptr, 0, eos, pad, min_new);
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &p.graph);
   p.graph_nodes = static_cast<int>(h->launches - before);
   h->launches = before;
@@ -999,7 +1139,7 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
   for (int t = 0; t < T; ++t) {
     CU_OK(h, cudaMemcpy2DAsync(col.p, 8, reinterpret_cast<const long long*>(decoder_input_ids) + t, static_cast<size_t>(T) * 8, 8, B, cudaMemcpyDeviceToDevice, s));
     force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
-    TRY(run_decode_step(h, s, logits + static_cast<size_t>(t) * c.V, T * c.V, c.eos, c.pad, 0));
+    TRY(run_decode_step(h, s, false, logits + static_cast<size_t>(t) * c.V, T * c.V, c.eos, c.pad, 0));
   }
   CU_OK(h, cudaStreamSynchronize(s));
   return B200T5_OK;
@@ -1037,7 +1177,10 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
     if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_RES256, 0), &ep, s);
     else if (bn == 32) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_RES32, 1), &ep, s);
   } else if (mode == 2) {
-    EpiGeglu::Params ep{Cb, N / 2, pow_mode};
+    GeluLut lut;
+    int lrc = ensure_gelu_lut(nullptr, pow_mode, &lut);
+    if (lrc != B200T5_OK) return lrc;
+    EpiGeglu::Params ep{Cb, N / 2, lut};
     if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_GEGLU256, 0), &ep, s);
     else if (bn == 64) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_GEGLU64, 1), &ep, s);
   } else if (mode == 3) {
@@ -1066,9 +1209,10 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
     DevBuf st;
     if (st.alloc(sizeof(DecodeState)) != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "alloc");
     set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
-    attn_decode_kernel<true><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
-        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,
-        Tk, nullptr, nullptr, &st.as<DecodeState>()->step, dist_bias);
+    self_attn_decode_warp_kernel<<<(B * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta, kSelfWarpsPerCta * 32,
+                                   kSelfWarpsPerCta * Tk * sizeof(float), s>>>(
+        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx),
+        B * H, H, Tk, &st.as<DecodeState>()->step, dist_bias);
     cudaStreamSynchronize(s);
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
@@ -1098,8 +1242,11 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
 extern "C" int b200t5_test_geglu(int device, const void* gate, const void* up, void* out, int64_t n, int pow_mode, void* stream) {
   const int sms = hook_device(device);
   if (sms < 0) return sms;
+  GeluLut lut;
+  int lrc = ensure_gelu_lut(nullptr, 0, &lut);
+  if (lrc != B200T5_OK) return lrc;
   geglu_elementwise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(gate), static_cast<const bf16*>(up), static_cast<bf16*>(out), n, pow_mode);
+      static_cast<const bf16*>(gate), static_cast<const bf16*>(up), static_cast<bf16*>(out), n, pow_mode, lut);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "geglu: %s", cudaGetErrorString(e));
   return B200T5_OK;

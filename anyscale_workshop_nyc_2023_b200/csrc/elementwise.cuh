@@ -27,6 +27,8 @@ __global__ void embed_rows_kernel(const long long* __restrict__ ids, const __nv_
 template <int kMaxVec>  // uint4 vectors per lane: d <= kMaxVec * 256
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = lane_id();
@@ -134,6 +136,8 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
                                      long long* __restrict__ out_ids, int* __restrict__ out_len, int out_ld,
                                      long long eos_tok, long long pad_tok, const __nv_bfloat16* __restrict__ E,
                                      __nv_bfloat16* __restrict__ x, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int t = st->step;
   float best = -INFINITY;
@@ -189,7 +193,11 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void advance_step_kernel(DecodeState* st) { st->step += 1; }
+__global__ void advance_step_kernel(DecodeState* st) {
+  pdl_launch_dependents();
+  pdl_wait();
+  st->step += 1;
+}
 
 // teacher forcing (test hook): overwrite the next decoder input with a given token
 __global__ void force_token_kernel(const long long* __restrict__ toks, const __nv_bfloat16* __restrict__ E,

@@ -20,6 +20,7 @@ namespace b200 {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 192;
+constexpr int kEpiSmemBytes = 8192;  // per-CTA scratch the epilogue functor may stage tables in
 
 template <int BN>
 struct GemmCfg {
@@ -27,10 +28,12 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // Big tiles (encoder, M = B*S) take the whole SM; the small-N decode tiles keep <= ~100 KB so that
+  // two CTAs of concurrently running decode chains can share an SM.
   static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = BN <= 64 ? ((100 * 1024) / kStageBytes) : (kStagesRaw > 8 ? 8 : kStagesRaw);
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiSmemBytes;
 };
 
 struct TileCoord {
@@ -49,7 +52,7 @@ DEVINL TileCoord tile_coord(int tile, int tiles_m, int tiles_n, int m_fastest) {
 }
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 64 ? 2 : 1))
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, int m_fastest, typename Epi::Params ep) {
   using Cfg = GemmCfg<BN>;
@@ -61,6 +64,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* epi_smem = smem + Cfg::kStages * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +73,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = tiles_m * tiles_n;
   const int kblocks = (K + kBK - 1) / kBK;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -88,10 +93,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
+  if (threadIdx.x >= 64) Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64);  // constant tables only
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -161,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       const int m = tc.m_tile * kBM + q * 32 + lane;
-      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N);
+      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -199,8 +206,9 @@ struct EpiStore {
     __nv_bfloat16* C;
     int ldc;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -223,8 +231,9 @@ struct EpiResidual {
     const __nv_bfloat16* R;
     int ld;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -254,13 +263,11 @@ struct EpiResidual {
   }
 };
 
-// gelu_new is evaluated exactly as HF eager evaluates it on bf16 tensors: every
-// elementwise op rounds its result to bf16 (transformers/activations.py:59-66;
-// SURVEY Appendix A.5). torch.pow(x, 3.0) on a bf16 CUDA tensor is x*x*x in bf16
-// arithmetic (two roundings, pow_mode 0); pow_mode 1 keeps the single-rounding variant
-// selectable so the exhaustive GPU test can pin whichever the installed torch does.
-// value of bf16(gelu_new(x) * lin) before the final rounding (pack_bf16x2 rounds it)
-DEVINL float geglu_bf16(float x, float lin, int pow_mode) {
+// gelu_new exactly as HF eager evaluates it on bf16 tensors: every elementwise op rounds its
+// result to bf16 (transformers/activations.py:59-66). torch.pow(x, 3.0) on
+// a bf16 tensor is x*x*x in bf16 arithmetic (two roundings, pow_mode 0; verified exhaustively
+// against torch on the GPU); pow_mode 1 keeps the single-rounding variant selectable.
+DEVINL float gelu_new_bf16_exact(float x, int pow_mode) {
   const float half_x = bf16_round(0.5f * x);
   const float x3 = pow_mode == 0 ? bf16_round(bf16_round(x * x) * x) : bf16_round(x * x * x);
   const float t1 = bf16_round(0.044715f * x3);
@@ -268,7 +275,30 @@ DEVINL float geglu_bf16(float x, float lin, int pow_mode) {
   const float t3 = bf16_round(0.7978845608028654f * t2);
   const float t4 = bf16_round(tanhf(t3));
   const float t5 = bf16_round(1.0f + t4);
-  return bf16_round(half_x * t5) * lin;
+  return bf16_round(half_x * t5);
+}
+
+// The input of gelu_new is itself a bf16 value, so the function has only 65536 possible
+// arguments: it is tabulated once per device with the exact arithmetic above. Only magnitudes in
+// [lo, hi) need the table (a few thousand entries, staged in shared memory by the epilogue);
+// below lo the result is bf16(0.5*x) and above hi it is x (positive) or -0 (negative), which the
+// host verifies entry by entry when it derives lo/hi from the full table (b200t5.cu).
+struct GeluLut {
+  const uint16_t* table;  // device: [2][hi - lo] bf16 bits, sign-major
+  int lo, hi;             // magnitude bit patterns (bf16 bits & 0x7fff)
+};
+
+DEVINL float gelu_from_lut(float x, const uint16_t* lut, int lo, int hi) {
+  const uint32_t bits = __float_as_uint(x) >> 16;
+  const int mag = static_cast<int>(bits & 0x7FFFu);
+  const int neg = static_cast<int>(bits >> 15);
+  if (mag < lo) return bf16_round(0.5f * x);  // tanh term rounds away: gelu_new(x) == bf16(0.5*x)
+  if (mag >= hi) {
+    if (mag > 0x7F80) return x;                     // NaN propagates
+    if (!neg) return x;                             // tanh saturated: 0.5x * 2
+    return mag == 0x7F80 ? __int_as_float(0x7FC00000) : -0.0f;  // 0.5x * (1 + -1): -inf*0 = NaN, else -0
+  }
+  return __uint_as_float(static_cast<uint32_t>(lut[neg * (hi - lo) + (mag - lo)]) << 16);
 }
 
 // ---- GeGLU: tile columns [0,BN/2) are wi_0 (gate) features, [BN/2,BN) the matching
@@ -278,11 +308,18 @@ struct EpiGeglu {
   struct Params {
     __nv_bfloat16* out;  // [M, F]
     int F;
-    int pow_mode;  // 0: x3 = bf16(bf16(x*x)*x)   1: x3 = bf16(x*x*x)   (set from the measured torch behaviour)
+    GeluLut lut;
   };
+  static DEVINL void prologue(const Params& p, uint8_t* epi_smem, int tid) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(epi_smem);
+    const int n = 2 * (p.lut.hi - p.lut.lo);
+    for (int i = tid; i < n; i += 128) dst[i] = p.lut.table[i];
+  }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem) {
     constexpr int HALF = BN / 2;
+    const uint16_t* lut = reinterpret_cast<const uint16_t*>(epi_smem);
+    const int lo = p.lut.lo, hi = p.lut.hi;
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
       uint32_t g[32], u[32];
@@ -299,7 +336,7 @@ struct EpiGeglu {
           for (int e = 0; e < 2; ++e) {
             const float x = bf16_round(__uint_as_float(g[2 * i + e]));
             const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
-            r[e] = geglu_bf16(x, lin, p.pow_mode);
+            r[e] = gelu_from_lut(x, lut, lo, hi) * lin;
           }
           o[i] = pack_bf16x2(r[0], r[1]);
         }
@@ -317,8 +354,9 @@ struct EpiCrossKV {
     __nv_bfloat16* arena;
     int B, H, S;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
     const int b = m / p.S, s = m - b * p.S;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -351,8 +389,9 @@ struct EpiQkvDecode {
     const int* step;       // device scalar: current decode position t
     int B, H, Tmax;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
     const int I = p.H * 64;
     const int t = *p.step;
 #pragma unroll 1
@@ -392,8 +431,9 @@ struct EpiArgmax {
     const int* step;
     int eos, min_new;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
     float best = -INFINITY;
     int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
     const bool block_eos = *p.step < p.min_new;
@@ -427,8 +467,9 @@ struct EpiStoreF32 {
     float* C;
     int ldc;
   };
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -453,15 +494,31 @@ cudaError_t prepare_gemm() {
                               GemmCfg<BN>::kSmemBytes);
 }
 
+// Launch with (optionally) the programmatic-stream-serialization attribute (PDL).
+template <class... KArgs, class... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                          Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int BN, class Epi>
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int m_fastest,
-                        const typename Epi::Params& ep, int num_sms, cudaStream_t stream) {
+                        const typename Epi::Params& ep, int num_sms, cudaStream_t stream, bool pdl = false) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tn_kernel<BN, Epi>;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, m_fastest, ep);
-  return cudaGetLastError();
+  return launch_kernel(gemm_bf16_tn_kernel<BN, Epi>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, pdl, tmA,
+                       tmB, M, N, K, m_fastest, ep);
 }
 
 }  // namespace b200

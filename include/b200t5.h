@@ -143,7 +143,8 @@ int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, 
                             const float* dist_bias, void* stream);
 int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, const float* rel_bias, const uint8_t* key_ok,
                              const int32_t* extent, int B, int S, int H, void* stream);
-/* out[i] = bf16(gelu_new(gate[i]) * up[i]) evaluated by the GeGLU epilogue arithmetic. */
+/* out[i] = bf16(gelu_new(gate[i]) * up[i]). mode 0: the GeGLU epilogue's path (exhaustive gelu table);
+ * mode 2: the op-by-op bf16 arithmetic the table is built from; mode 1: same with single-rounded pow. */
 int b200t5_test_geglu(int device, const void* gate, const void* up, void* out, int64_t n, int pow_mode,
                       void* stream);
 
