@@ -1,0 +1,288 @@
+// Encoder self-attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), S <= 512.
+//
+// T5Attention.forward (modeling_t5.py:253-344) for one (batch row b, head h, 128-query tile):
+//   scores = bf16(Q K^T)                      tcgen05.mma, fp32 accumulators in TMEM (128 x 512)
+//   scores = bf16(scores + bias[h, j-i])      bias = relative-position buckets + key-padding mask
+//   p      = bf16(softmax_fp32(scores))       exact two-pass softmax (row max, row sum, then p)
+//   out    = bf16(p V)                        tcgen05.mma, A = p staged in smem, B = V (MN-major)
+// The score tile never leaves the SM: S lives in TMEM, is rewritten in place with the rounded,
+// biased scores, and is read back twice more (sum, then p) - HF's exact rounding contract
+//  without materialising [B,H,S,S] in HBM.
+//
+// Warp roles (32 + 512 threads): warp 0 = TMEM owner + TMA + MMA issue (one elected thread);
+// warps 1..16 = softmax/epilogue: warp W owns TMEM lanes 32*(W%4).. (= query rows) and, of every
+// 128-key chunk, the 32 keys selected by (W-1)/4 (four warps per scheduler hide the MUFU/TMEM latency). P is staged per 128-key chunk through a
+// double-buffered 32 KB smem tile in the canonical 128-B-swizzled K-major layout (the same
+// layout TMA writes), so the P.V MMA of chunk c overlaps the exp/normalise work of chunk c+1.
+//
+// Shared memory: Q 16 KB | K 4 x 16 KB (reused for P once Q K^T has been issued) | V 4 x 16 KB.
+// TMEM: 512 columns = the S tile; O (64 columns) aliases S[:, 0:64) after chunk 0 was consumed.
+#pragma once
+#include "attention_decode.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kEncTcParts = 4;                        // column parts per 128-key chunk (warps per lane quarter)
+constexpr int kEncTcCompute = 128 * kEncTcParts;     // softmax/epilogue threads
+constexpr int kEncTcThreads = 32 + kEncTcCompute;
+constexpr int kEncTcQ = 128;      // queries per CTA
+constexpr int kEncTcChunk = 128;  // keys per chunk
+constexpr int kEncTcMaxS = 512;
+
+DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+      " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct EncTcSmem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = 16384;               // 4 x 16 KB, later 2 x 32 KB P buffers
+  static constexpr int kV = kK + 65536;          // 4 x 16 KB
+  static constexpr int kBars = kV + 65536;       // mbarriers + tmem slot + stats
+  static constexpr int kStat = kBars + 128;      // float[2][parts][128]: max, sum per column part
+  static constexpr int kBias = kStat + 2 * kEncTcParts * 128 * 4;  // float[S + 128]
+  static size_t bytes(int S) { return static_cast<size_t>(kBias) + (S + 128) * 4 + S + 16 + 1024; }
+};
+
+__global__ void __launch_bounds__(kEncTcThreads, 1)
+encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] bf16, box 64 x 128
+                       __nv_bfloat16* __restrict__ ctx,            // [B*S, I]
+                       const float* __restrict__ rel_bias,         // [H][2S-1], index j - i + S - 1
+                       const unsigned char* __restrict__ key_ok,   // [B][S]
+                       const int* __restrict__ extent,             // [B]
+                       int S, int H) {
+  extern __shared__ uint8_t enc_tc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(enc_tc_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + EncTcSmem::kQ;
+  uint8_t* sK = smem + EncTcSmem::kK;
+  uint8_t* sV = smem + EncTcSmem::kV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EncTcSmem::kBars);
+  uint64_t* bar_load = bars;       // TMA bytes landed
+  uint64_t* bar_s = bars + 1;      // S = Q K^T complete
+  uint64_t* bar_pfull = bars + 2;  // [2] P chunk staged (256 arrivals)
+  uint64_t* bar_pfree = bars + 4;  // [2] P.V MMA of that buffer complete
+  uint64_t* bar_o = bars + 6;      // all P.V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sStat = reinterpret_cast<float*>(smem + EncTcSmem::kStat);
+  float* sBias = reinterpret_cast<float*>(smem + EncTcSmem::kBias);
+  unsigned char* sOk = reinterpret_cast<unsigned char*>(sBias + S + 128);
+  int* sHoles = reinterpret_cast<int*>(bars + 10);
+  if (threadIdx.x == 0) *sHoles = 0;
+  __syncthreads();
+
+  const int I = H * 64;
+  const int bh = blockIdx.y;
+  const int b = bh / H, h = bh - b * H;
+  const int i0 = blockIdx.x * kEncTcQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ext = extent[b];
+  // rows at or beyond the last attended position are padding: nothing downstream reads them
+  if (i0 >= ext) return;
+  const int nchunks = (ext + kEncTcChunk - 1) / kEncTcChunk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(&bar_pfull[0], kEncTcCompute);
+      mbar_init(&bar_pfull[1], kEncTcCompute);
+      mbar_init(&bar_pfree[0], 1);
+      mbar_init(&bar_pfree[1], 1);
+      mbar_init(bar_o, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else {
+    // bias slice for this query tile: x = j - i_local + 127  <->  rel index j - i + S - 1
+    const int t = threadIdx.x - 32;
+    const int lo = S - 1 - i0 - 127;
+    for (int x = t; x < S + 127; x += kEncTcCompute) {
+      const int idx = lo + x;
+      sBias[x] = (idx >= 0 && idx < 2 * S - 1) ? rel_bias[static_cast<size_t>(h) * (2 * S - 1) + idx] : 0.f;
+    }
+    int holes = 0;
+    for (int x = t; x < S; x += kEncTcCompute) {
+      const unsigned char ok = key_ok[static_cast<size_t>(b) * S + x];
+      sOk[x] = ok;
+      holes |= (x < ext && !ok) ? 1 : 0;
+    }
+    if (holes) *sHoles = 1;  // rare: a non-prefix attention mask
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- loads: Q tile, K and V chunks of this (b,h)
+      const int row0 = b * S;
+      mbar_arrive_expect_tx(bar_load, 16384u * (1 + 2 * nchunks));
+      tma_load_2d(sQ, &tmQKV, bar_load, h * 64, row0 + i0);
+      for (int c = 0; c < nchunks; ++c) {
+        tma_load_2d(sK + c * 16384, &tmQKV, bar_load, I + h * 64, row0 + c * kEncTcChunk);
+        tma_load_2d(sV + c * 16384, &tmQKV, bar_load, 2 * I + h * 64, row0 + c * kEncTcChunk);
+      }
+      mbar_wait(bar_load, 0);
+      tc_fence_after_sync();
+      // ---------------- S[:, 128c : 128c+128] = Q K_c^T
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint64_t dq = make_desc_sw128_kmajor(smem_u32(sQ));
+      for (int c = 0; c < nchunks; ++c) {
+        const uint64_t dk = make_desc_sw128_kmajor(smem_u32(sK + c * 16384));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem_base + c * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      // ---------------- O += P_c V_c as the softmax warps hand chunks over
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&bar_pfull[buf], (c >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t pbase = smem_u32(sK + buf * 32768);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t dp = make_desc_sw128_kmajor(pbase + (kk >> 2) * 16384) + 2 * (kk & 3);
+          const uint64_t dv = make_desc_sw128_mnmajor(smem_u32(sV + c * 16384 + kk * 2048), 1024, 1024);
+          umma_bf16_ss(tmem_base, dp, dv, idesc_o, (c | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_pfree[buf]);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    // ================================================================ softmax / epilogue warps
+    const int q = warp & 3;
+    const int part = (warp - 1) >> 2;  // which 32 keys of every 128-key chunk
+    const int il = q * 32 + lane;      // local query row
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    constexpr int P = kEncTcParts;
+    mbar_wait(bar_s, 0);
+    tc_fence_after_sync();
+
+    // ---- pass A: rounded + biased + masked scores written back in place; row max
+    const bool holes = *sHoles != 0;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int jb = c * kEncTcChunk + part * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(trow + jb, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int j = jb + t;
+        float s = bf16_round(__uint_as_float(v[t]));
+        if (j < ext) {
+          s = bf16_round(s + sBias[j - il + 127]);
+          if (holes && !sOk[j]) s = kBf16Min;
+        } else {
+          s = -INFINITY;
+        }
+        mx = fmaxf(mx, s);
+        v[t] = __float_as_uint(s);
+      }
+      tmem_st_32x32(trow + jb, v);
+    }
+    tmem_st_wait();
+    sStat[part * 128 + il] = mx;
+    named_bar_sync(1, kEncTcCompute);
+#pragma unroll
+    for (int k = 0; k < P; ++k) mx = fmaxf(mx, sStat[k * 128 + il]);
+
+    // ---- pass B: e = exp(s - max) kept in place; row sum
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int jb = c * kEncTcChunk + part * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(trow + jb, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float e = expf(__uint_as_float(v[t]) - mx);
+        sum += e;
+        v[t] = __float_as_uint(e);
+      }
+      tmem_st_32x32(trow + jb, v);  // pass C only has to normalise
+    }
+    tmem_st_wait();
+    sStat[(P + part) * 128 + il] = sum;
+    named_bar_sync(1, kEncTcCompute);
+    sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < P; ++k) sum += sStat[(P + k) * 128 + il];  // fixed order: deterministic
+    // p = exp(s - max) * (1 / sum): torch divides; the two differ by at most one fp32 ulp before the
+    // rounding to bf16, i.e. in ~1e-5 of the elements by one bf16 ulp (far below the accumulation-order
+    // noise between any two implementations), and the reciprocal removes a ~10-instruction IEEE divide
+    // from the inner loop.
+    const float inv_sum = 1.0f / sum;
+
+    // ---- pass C: p = bf16(e * (1/sum)) staged per chunk for the P.V MMA
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      const int jb = c * kEncTcChunk + part * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(trow + jb, v);
+      tmem_ld_wait();
+      uint32_t pk[16];  // 32 keys of this thread's row, packed bf16x2
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        pk[t] = pack_bf16x2(__uint_as_float(v[2 * t]) * inv_sum, __uint_as_float(v[2 * t + 1]) * inv_sum);
+      if (c >= 2) mbar_wait(&bar_pfree[buf], ((c - 2) >> 1) & 1);
+      // (chunks 0/1: K's smem is free once bar_s completed, i.e. all Q K^T MMAs are done)
+      // keys part*32.. of the chunk = sub-tile part/2 (64 keys each), 16-B groups (part&1)*4 .. +3 of the row
+      uint8_t* tile = sK + buf * 32768 + (part >> 1) * 16384 + il * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int gg = (part & 1) * 4 + g;
+        *reinterpret_cast<uint4*>(tile + ((gg ^ (il & 7)) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_pfull[buf]);
+    }
+
+    // ---- epilogue: O (TMEM cols 0..63) -> bf16 -> ctx[b*S + i, h*64 + d]; 16 columns per warp
+    mbar_wait(bar_o, 0);
+    tc_fence_after_sync();
+    {
+      uint32_t o[16];
+      tmem_ld_32x16(trow + part * 16, o);
+      tmem_ld_wait();
+      const int i = i0 + il;
+      if (i < S) {
+        uint32_t pkd[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pkd[t] = pack_bf16x2(__uint_as_float(o[2 * t]), __uint_as_float(o[2 * t + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + i) * I + h * 64 + part * 16);
+        dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
+        dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace b200

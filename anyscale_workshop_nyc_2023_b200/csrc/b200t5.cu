@@ -22,6 +22,7 @@
 #include "../../include/b200t5.h"
 #include "attention_decode.cuh"
 #include "attention_encoder.cuh"
+#include "attention_encoder_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 
@@ -181,7 +182,7 @@ struct Plan {
   DevBuf state, unfinished, out_ids, out_len, ids_dev, mask_dev;
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
-  CUtensorMap tm_xn, tm_ctx, tm_hff;
+  CUtensorMap tm_xn, tm_ctx, tm_hff, tm_qkv_attn;
   // decode chains: the batch is cut into independent row ranges that run concurrently (one
   // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
   struct Chain {
@@ -232,6 +233,7 @@ struct b200t5_ctx {
   bool ev_valid = false;
   int pow_mode = 0;
   bool use_pdl = true;
+  bool enc_attn_tc = true;
   GeluLut gelu_lut{nullptr, 0, 0};
   int chains_override = 0;
   cudaStream_t chain_streams[kMaxChains] = {};
@@ -338,6 +340,9 @@ static cudaError_t init_kernel_attrs() {
   if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSelfWarpsPerCta * 4096 * 4)) != cudaSuccess)
     return e;
+  if ((e = cudaFuncSetAttribute(encoder_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(EncTcSmem::bytes(kEncTcMaxS)))) != cudaSuccess)
+    return e;
   return cudaFuncSetAttribute(encoder_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
 
@@ -418,6 +423,8 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   h->pow_mode = pm ? atoi(pm) : 0;
   const char* pdl_env = getenv("B200T5_PDL");
   h->use_pdl = pdl_env ? atoi(pdl_env) != 0 : true;
+  const char* ea_env = getenv("B200T5_ENC_ATTN");
+  h->enc_attn_tc = !(ea_env && strcmp(ea_env, "mma") == 0);
   const char* ch_env = getenv("B200T5_CHAINS");
   h->chains_override = ch_env ? atoi(ch_env) : 0;
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -720,6 +727,8 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_xn, pl->xn.p, M, d, 128);
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
   TMAP(h, &pl->tm_hff, pl->hff.p, M, F, 128);
+  TMAP(h, &pl->tm_qkv_attn, pl->qkv.p, M, 3 * I, 128);
+  CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
     // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
     int nc = B >= 128 ? 4 : (B >= 64 ? 2 : 1);
@@ -778,8 +787,13 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
       EpiStore::Params ep{p.qkv.as<bf16>(), 3 * I};
       CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
     }
-    encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
-        p.qkv.as<bf16>(), p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+    if (h->enc_attn_tc && S <= kEncTcMaxS) {
+      encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
+          p.tm_qkv_attn, p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+    } else {
+      encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
+          p.qkv.as<bf16>(), p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+    }
     h->launches++;
     CU_OK(h, cudaGetLastError());
     {
@@ -1225,9 +1239,20 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
 }
 
 extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, const float* rel_bias,
-                                        const uint8_t* key_ok, const int32_t* extent, int B, int S, int H, void* stream) {
+                                        const uint8_t* key_ok, const int32_t* extent, int B, int S, int H, int impl,
+                                        void* stream) {
   const int sms = hook_device(device);
   if (sms < 0) return sms;
+  if (impl == 1) {
+    if (S > kEncTcMaxS) return fail(nullptr, B200T5_EINVAL, "tcgen05 encoder attention supports S <= %d", kEncTcMaxS);
+    CUtensorMap tm;
+    if (!make_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, static_cast<uint64_t>(3) * H * 64, 128)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+    encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), static_cast<cudaStream_t>(stream)>>>(
+        tm, static_cast<bf16*>(ctx), rel_bias, key_ok, extent, S, H);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn_tc: %s", cudaGetErrorString(e2));
+    return B200T5_OK;
+  }
   const size_t smem = encoder_attn_smem_bytes(S);
   cudaError_t e = smem <= 96 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
   if (e == cudaSuccess) {

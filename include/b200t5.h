@@ -141,8 +141,9 @@ int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M
 int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx, int B,
                             int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
                             const float* dist_bias, void* stream);
+/* impl 0: mma.sync kernel (any S); impl 1: tcgen05/TMEM kernel (S <= 512). Query rows >= extent[b] are not written. */
 int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, const float* rel_bias, const uint8_t* key_ok,
-                             const int32_t* extent, int B, int S, int H, void* stream);
+                             const int32_t* extent, int B, int S, int H, int impl, void* stream);
 /* out[i] = bf16(gelu_new(gate[i]) * up[i]). mode 0: the GeGLU epilogue's path (exhaustive gelu table);
  * mode 2: the op-by-op bf16 arithmetic the table is built from; mode 1: same with single-rounded pow. */
 int b200t5_test_geglu(int device, const void* gate, const void* up, void* out, int64_t n, int pow_mode,
