@@ -381,7 +381,7 @@ static int ensure_gelu_lut(b200t5_ctx* h, int pow_mode, GeluLut* out) {
   while (hi > lo && t[hi - 1] == static_cast<uint16_t>(hi - 1) && t[0x8000 | (hi - 1)] == 0x8000) --hi;
   const int n = hi - lo;
   if (n < 0 || 2 * n * 2 > kEpiSmemBytes) return fail(h, B200T5_ECUDA, "gelu table window [%#x,%#x) does not fit the epilogue scratch", lo, hi);
-  std::vector<uint16_t> compact(static_cast<size_t>(2) * (n > 0 ? n : 1));
+  std::vector<uint16_t> compact(((static_cast<size_t>(2) * (n > 0 ? n : 1) + 7) / 8) * 8 + 8, 0);
   for (int i = 0; i < n; ++i) {
     compact[i] = t[lo + i];
     compact[n + i] = t[0x8000 | (lo + i)];

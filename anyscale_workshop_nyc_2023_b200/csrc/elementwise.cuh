@@ -28,11 +28,19 @@ template <int kMaxVec>  // uint4 vectors per lane: d <= kMaxVec * 256
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
   pdl_launch_dependents();
-  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
   const int lane = lane_id();
   const int nvec = d >> 3;
+  // the norm weights never depend on the previous kernel: fetch them before waiting for it
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4 wv[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) wv[i] = wr[idx];
+  }
+  pdl_wait();
+  if (row >= M) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
   uint4 v[kMaxVec];
   float ss = 0.f;
@@ -53,15 +61,13 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float inv = rsqrtf(ss * (1.0f / static_cast<float>(d)) + eps);
-  const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * d);
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      const uint4 wv = wr[idx];
       const uint32_t xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+      const uint32_t ws[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

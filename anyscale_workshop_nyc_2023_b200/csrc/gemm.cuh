@@ -93,16 +93,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
-  if (threadIdx.x >= 64) Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64);  // constant tables only
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here
+  // PDL: everything above overlapped the previous kernel's tail. Each role waits for the previous
+  // kernel (griddepcontrol.wait) only right before it first touches memory that kernel may have
+  // written; the weights (B operand) never depend on it and are prefetched into L2 before the wait.
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (static_cast<int>(blockIdx.x) < num_tiles) {
+        const TileCoord tc0 = tile_coord(blockIdx.x, tiles_m, tiles_n, m_fastest);
+        for (int kb = 0; kb < kblocks; ++kb) tma_prefetch_l2_2d(&tmB, kb * kBK, tc0.n_tile * BN);
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -162,13 +168,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     int as = 0;
     uint32_t aphase = 0;
+    Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64);  // constant tables; overlaps the main loop
+    pdl_wait();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, m_fastest);
+      const int m = tc.m_tile * kBM + q * 32 + lane;
+      typename Epi::template Pre<BN> pre;
+      pre.load(ep, m, m < M, tc.n_tile, N);  // operands of the epilogue that do not need the accumulator
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      const int m = tc.m_tile * kBM + q * 32 + lane;
-      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem);
+      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem, pre);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -208,7 +218,12 @@ struct EpiStore {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -232,8 +247,24 @@ struct EpiResidual {
     int ld;
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  // The residual operand does not depend on the accumulator: for the small decode tiles it is
+  // fetched while the main loop is still running (one row x BN columns per thread).
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    static constexpr bool kOn = BN <= 64;
+    uint4 r[kOn ? BN / 8 : 1];
+    DEVINL void load(const Params& p, int m, bool m_ok, int n_tile, int N) {
+      if constexpr (kOn) {
+        const int n0 = n_tile * BN;
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.R + static_cast<size_t>(m) * p.ld + n0);
+#pragma unroll
+        for (int g = 0; g < BN / 8; ++g) r[g] = (m_ok && n0 + g * 8 + 8 <= N) ? r4[g] : make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -247,7 +278,9 @@ struct EpiResidual {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (n0 + g * 8 + 8 <= N) {
-            const uint4 r = r4[g];
+            uint4 r;
+            if constexpr (Pre<BN>::kOn) r = pre.r[c * 4 + g];
+            else r = r4[g];
             const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -311,12 +344,20 @@ struct EpiGeglu {
     GeluLut lut;
   };
   static DEVINL void prologue(const Params& p, uint8_t* epi_smem, int tid) {
-    uint16_t* dst = reinterpret_cast<uint16_t*>(epi_smem);
-    const int n = 2 * (p.lut.hi - p.lut.lo);
-    for (int i = tid; i < n; i += 128) dst[i] = p.lut.table[i];
+    // stage the gelu table (a few KB) with 16-byte loads; only the 4 epilogue warps take part
+    const int nvec = (2 * (p.lut.hi - p.lut.lo) * 2 + 15) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(p.lut.table);
+    uint4* dst = reinterpret_cast<uint4*>(epi_smem);
+    for (int i = tid; i < nvec; i += 128) dst[i] = src[i];
+    asm volatile("bar.sync 2, 128;" ::: "memory");
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem,
+                         const Pre<BN>&) {
     constexpr int HALF = BN / 2;
     const uint16_t* lut = reinterpret_cast<const uint16_t*>(epi_smem);
     const int lo = p.lut.lo, hi = p.lut.hi;
@@ -356,7 +397,12 @@ struct EpiCrossKV {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
     const int b = m / p.S, s = m - b * p.S;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -391,7 +437,12 @@ struct EpiQkvDecode {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
     const int I = p.H * 64;
     const int t = *p.step;
 #pragma unroll 1
@@ -433,7 +484,12 @@ struct EpiArgmax {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
     float best = -INFINITY;
     int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
     const bool block_eos = *p.step < p.min_new;
@@ -469,7 +525,12 @@ struct EpiStoreF32 {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  struct Pre {
+    DEVINL void load(const Params&, int, bool, int, int) {}
+  };
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
+                         const Pre<BN>& pre) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];

@@ -240,3 +240,42 @@ def test_flan_t5_small_vs_hf_gpu(models):
     # the CUDA path must track the same-dtype GPU anchor at least twice as closely as two
     # stock bf16 runs of the dependency (GPU vs CPU) track each other
     assert err.mean() <= 0.5 * floor.mean() and err.max() <= 1.5 * floor.max()
+
+
+def test_batch_predictor_api_single_gpu(models):
+    """Notebook flow (:875-934) on the GPU through the shim: from_checkpoint -> predict -> to_pandas."""
+    from anyscale_workshop_nyc_2023_b200 import rayshim
+    from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir, make_batch_predictor
+
+    spec = SPECS["tiny"]
+    ckpt = checkpoint_dir("tiny", seed=1)
+    ids, mask = synthetic_token_batch(10, 24, spec.vocab_size, seed=31, lengths="uniform")
+    ds = rayshim.data.from_numpy({"input_ids": ids, "attention_mask": mask, "labels": ids.copy()})
+    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.bfloat16)
+    out = bp.predict(ds, batch_size=4, num_gpus_per_worker=1, max_scoring_workers=1, max_new_tokens=8).to_pandas()
+    assert len(out) == 10 and list(out.columns) == ["generated_output"]
+    model, _ = models("tiny", 1)
+    from transformers import T5Tokenizer
+
+    tok = T5Tokenizer.from_pretrained(str(ckpt))
+    want = []
+    for lo in range(0, 10, 4):
+        g = model.generate(input_ids=torch.from_numpy(ids[lo:lo + 4]), attention_mask=torch.from_numpy(mask[lo:lo + 4]), max_new_tokens=8)
+        want += tok.batch_decode(g, skip_special_tokens=True)
+    assert out["generated_output"].tolist() == want
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_batch_predictor_pool_two_gpus():
+    """One scoring process per GPU, blocks dealt round-robin, results back in input order."""
+    from anyscale_workshop_nyc_2023_b200 import rayshim
+    from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir, make_batch_predictor
+
+    spec = SPECS["tiny"]
+    ckpt = checkpoint_dir("tiny", seed=1)
+    ids, mask = synthetic_token_batch(24, 24, spec.vocab_size, seed=32, lengths="uniform")
+    ds = rayshim.data.from_numpy({"input_ids": ids, "attention_mask": mask, "labels": ids.copy()})
+    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.bfloat16)
+    one = bp.predict(ds, batch_size=4, num_gpus_per_worker=1, max_scoring_workers=1, max_new_tokens=8).to_pandas()
+    two = bp.predict(ds, batch_size=4, num_gpus_per_worker=1, max_new_tokens=8).to_pandas()
+    assert one["generated_output"].tolist() == two["generated_output"].tolist()
