@@ -234,6 +234,8 @@ struct b200t5_ctx {
   int pow_mode = 0;
   bool use_pdl = true;
   bool enc_attn_tc = true;
+  bool serialize_xattn = false;  // measured slower on B200 (300 vs 261 ms/batch): kept as an env knob only
+  std::vector<cudaEvent_t> xattn_ev;
   GeluLut gelu_lut{nullptr, 0, 0};
   int chains_override = 0;
   cudaStream_t chain_streams[kMaxChains] = {};
@@ -425,6 +427,8 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   h->use_pdl = pdl_env ? atoi(pdl_env) != 0 : true;
   const char* ea_env = getenv("B200T5_ENC_ATTN");
   h->enc_attn_tc = !(ea_env && strcmp(ea_env, "mma") == 0);
+  const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
+  if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   const char* ch_env = getenv("B200T5_CHAINS");
   h->chains_override = ch_env ? atoi(ch_env) : 0;
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -464,6 +468,8 @@ extern "C" int b200t5_destroy(b200t5_handle h) {
     if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]);
   for (int i = 0; i <= kMaxChains; ++i)
     if (h->chain_ev[i]) cudaEventDestroy(h->chain_ev[i]);
+  for (cudaEvent_t e : h->xattn_ev)
+    if (e) cudaEventDestroy(e);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -826,101 +832,175 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
 // One chain = rows [b0, b0+nb) of the batch through all decoder layers, the lm_head and the
 // greedy bookkeeping. Rows are independent, so chains only share read-only state (weights, the
 // step counter) and write disjoint row ranges of the same buffers.
-// logits_out == nullptr: fused arg-max + bookkeeping; otherwise fp32 logits are written to
-// logits_out (row stride ldl) and no token is chosen (teacher forcing).
-static int run_decode_chain(b200t5_ctx* h, cudaStream_t s, const Plan::Chain& ch, float* logits_out, int ldl,
-                            long long eos, long long pad, int min_new) {
+struct ChainView {
+  int b0, nb;
+  bf16 *dx, *dxn, *dq, *dctx, *dh;
+  const Plan::Chain* ch;
+};
+static ChainView chain_view(b200t5_ctx* h, const Plan::Chain& ch) {
+  Plan& p = *h->plan;
+  const Cfg& c = h->c;
+  ChainView v;
+  v.b0 = ch.b0;
+  v.nb = ch.nb;
+  v.dx = p.dx.as<bf16>() + static_cast<size_t>(ch.b0) * c.d;
+  v.dxn = p.dxn.as<bf16>() + static_cast<size_t>(ch.b0) * c.d;
+  v.dq = p.dq.as<bf16>() + static_cast<size_t>(ch.b0) * c.I;
+  v.dctx = p.dctx.as<bf16>() + static_cast<size_t>(ch.b0) * c.I;
+  v.dh = p.dh.as<bf16>() + static_cast<size_t>(ch.b0) * c.F;
+  v.ch = &ch;
+  return v;
+}
+
+// layer l, up to and including the cross-attention query projection
+static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
-  const int B = p.B, S = p.S, d = c.d, I = c.I, F = c.F, H = c.H, T = p.Tmax;
-  const int b0 = ch.b0, nb = ch.nb;
-  DecodeState* st = p.state.as<DecodeState>();
-  const int* step = &st->step;
-  const size_t self_layer = static_cast<size_t>(2) * B * I * T;
-  const size_t cross_layer = static_cast<size_t>(2) * B * I * S;
-  const int wi_tiles = (F + 31) / 32;
-  const bool pdl = h->use_pdl;  // programmatic dependent launch: prologues overlap the previous kernel's tail
-  bf16* dx = p.dx.as<bf16>() + static_cast<size_t>(b0) * d;
-  bf16* dxn = p.dxn.as<bf16>() + static_cast<size_t>(b0) * d;
-  bf16* dq = p.dq.as<bf16>() + static_cast<size_t>(b0) * I;
-  bf16* dctx = p.dctx.as<bf16>() + static_cast<size_t>(b0) * I;
-  bf16* dh = p.dh.as<bf16>() + static_cast<size_t>(b0) * F;
-  for (int l = 0; l < c.Ld; ++l) {
-    DecLayerW& w = h->dec[l];
-    // [kv][B][H][T|S][64]: a row offset of b0 is a pointer offset inside each kv plane
-    bf16* skv = p.self_kv.as<bf16>() + l * self_layer + static_cast<size_t>(b0) * I * T;
-    bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer + static_cast<size_t>(b0) * I * S;
-    CU_OK(h, run_rmsnorm(h, dx, w.ln0.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
-    {
-      EpiQkvDecode::Params ep{dq, skv, step, B, H, T};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_qkv, nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
-    }
-    CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
-                           dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, dq, skv,
-                           skv + static_cast<size_t>(B) * I * T, dctx, nb * H, H, T, step, p.dec_bias.as<float>()));
-    h->launches++;
-    {
-      EpiResidual::Params ep{dx, dx, d};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dctx, w.tm_o, nb, d, I, G_RES32, 1), &ep, s, pdl));
-    }
-    CU_OK(h, run_rmsnorm(h, dx, w.ln1.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
-    {
-      EpiStore::Params ep{dq, I};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_cq, nb, I, d, G_STORE32, 1), &ep, s, pdl));
-    }
-    CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
-                           dq, ckv, ckv + static_cast<size_t>(B) * I * S, dctx, H, S, p.extent.as<int>() + b0,
-                           p.key_ok.as<unsigned char>() + static_cast<size_t>(b0) * S, nullptr, nullptr));
-    h->launches++;
-    {
-      EpiResidual::Params ep{dx, dx, d};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dctx, w.tm_co, nb, d, I, G_RES32, 1), &ep, s, pdl));
-    }
-    CU_OK(h, run_rmsnorm(h, dx, w.ln2.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
-    {
-      EpiGeglu::Params ep{dh, F, h->gelu_lut};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dxn, w.tm_wi, nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
-    }
-    {
-      EpiResidual::Params ep{dx, dx, d};
-      CU_OK(h, run_gemm(h, mk(ch.tm_dh, w.tm_ffo, nb, d, F, G_RES32, 1), &ep, s, pdl));
-    }
+  const int B = p.B, d = c.d, I = c.I, H = c.H, T = p.Tmax;
+  const bool pdl = h->use_pdl;
+  const int* step = &p.state.as<DecodeState>()->step;
+  DecLayerW& w = h->dec[l];
+  // [kv][B][H][T][64]: a row offset of b0 is a pointer offset inside each kv plane
+  bf16* skv = p.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  {
+    EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
-  CU_OK(h, run_rmsnorm(h, dx, h->dec_final_ln.as<bf16>(), dxn, nb, d, c.eps, s, pdl));
+  CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
+                         dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
+                         skv + static_cast<size_t>(B) * I * T, v.dctx, v.nb * H, H, T, step, p.dec_bias.as<float>()));
+  h->launches++;
+  {
+    EpiResidual::Params ep{v.dx, v.dx, d};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
+  }
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  {
+    EpiStore::Params ep{v.dq, I};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
+  }
+  return B200T5_OK;
+}
+
+// layer l, cross-attention over the encoder keys (the HBM-streaming kernel)
+static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l, bool pdl) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  const int B = p.B, S = p.S, I = c.I, H = c.H;
+  bf16* ckv = p.cross_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
+  CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
+                         v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
+                         p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr));
+  h->launches++;
+  return B200T5_OK;
+}
+
+// layer l, after the cross-attention: output projection and the feed-forward block
+static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l) {
+  const Cfg& c = h->c;
+  const int d = c.d, I = c.I, F = c.F;
+  const bool pdl = h->use_pdl;
+  const int wi_tiles = (F + 31) / 32;
+  DecLayerW& w = h->dec[l];
+  {
+    EpiResidual::Params ep{v.dx, v.dx, d};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
+  }
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  {
+    EpiGeglu::Params ep{v.dh, F, h->gelu_lut};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
+  }
+  {
+    EpiResidual::Params ep{v.dx, v.dx, d};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dh, w.tm_ffo, v.nb, d, F, G_RES32, 1), &ep, s, pdl));
+  }
+  return B200T5_OK;
+}
+
+// final norm, lm_head and either the fused arg-max + greedy bookkeeping or fp32 logits (teacher forcing)
+static int chain_head(b200t5_ctx* h, cudaStream_t s, const ChainView& v, float* logits_out, int ldl, long long eos,
+                      long long pad, int min_new) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  const int d = c.d, T = p.Tmax;
+  const bool pdl = h->use_pdl;
+  DecodeState* st = p.state.as<DecodeState>();
+  CU_OK(h, run_rmsnorm(h, v.dx, h->dec_final_ln.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   if (logits_out) {
-    EpiStoreF32::Params ep{logits_out + static_cast<size_t>(b0) * ldl, ldl};
-    CU_OK(h, run_gemm(h, mk(ch.tm_dxn, h->tm_lm, nb, c.V, d, G_LOGITS128, 1), &ep, s, pdl));
+    EpiStoreF32::Params ep{logits_out + static_cast<size_t>(v.b0) * ldl, ldl};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, h->tm_lm, v.nb, c.V, d, G_LOGITS128, 1), &ep, s, pdl));
   } else {
-    float* pval = p.pval.as<float>() + static_cast<size_t>(b0) * p.n_vtiles;
-    int* pidx = p.pidx.as<int>() + static_cast<size_t>(b0) * p.n_vtiles;
-    EpiArgmax::Params ep{pval, pidx, p.n_vtiles, step, static_cast<int>(eos), min_new};
-    CU_OK(h, run_gemm(h, mk(ch.tm_dxn, h->tm_lm, nb, c.V, d, G_ARGMAX128, 1), &ep, s, pdl));
-    CU_OK(h, launch_kernel(finalize_step_kernel, dim3(nb), dim3(128), 0, s, pdl, pval, pidx, p.n_vtiles, st,
-                           p.unfinished.as<int>() + b0, p.out_ids.as<long long>() + static_cast<size_t>(b0) * (T + 1),
-                           p.out_len.as<int>() + b0, T + 1, eos, pad, h->shared.as<bf16>(), dx, d));
+    float* pval = p.pval.as<float>() + static_cast<size_t>(v.b0) * p.n_vtiles;
+    int* pidx = p.pidx.as<int>() + static_cast<size_t>(v.b0) * p.n_vtiles;
+    EpiArgmax::Params ep{pval, pidx, p.n_vtiles, &st->step, static_cast<int>(eos), min_new};
+    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, h->tm_lm, v.nb, c.V, d, G_ARGMAX128, 1), &ep, s, pdl));
+    CU_OK(h, launch_kernel(finalize_step_kernel, dim3(v.nb), dim3(128), 0, s, pdl, pval, pidx, p.n_vtiles, st,
+                           p.unfinished.as<int>() + v.b0, p.out_ids.as<long long>() + static_cast<size_t>(v.b0) * (T + 1),
+                           p.out_len.as<int>() + v.b0, T + 1, eos, pad, h->shared.as<bf16>(), v.dx, d));
     h->launches++;
   }
   return B200T5_OK;
 }
 
-// All chains of one step. `fork` runs them concurrently on the chain streams (used while
-// capturing the step graph); otherwise they run back to back on `s`.
+static cudaEvent_t xattn_event(b200t5_ctx* h, size_t k) {
+  while (h->xattn_ev.size() <= k) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    h->xattn_ev.push_back(e);
+  }
+  return h->xattn_ev[k];
+}
+
+// All chains of one step. `fork` (used while capturing the step graph) runs the chains on their
+// own streams and, in addition, threads ONE dependency through every cross-attention kernel in
+// round-robin order (layer-major, chain-minor). Without it the chains run in lock-step: all of
+// them stream KV at the same moment (sharing HBM four ways) and all of them sit in their
+// latency-bound GEMM phases at the same moment (HBM idle). With it at most one chain streams KV at
+// a time at full bandwidth while the other chains' GEMM phases fill the gaps - a software pipeline
+// across chains that needs no kernel changes, only graph edges.
 static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logits_out, int ldl, long long eos,
                            long long pad, int min_new) {
   Plan& p = *h->plan;
-  if (fork && p.n_chains > 1) {
+  const Cfg& c = h->c;
+  const int nc = p.n_chains;
+  ChainView v[kMaxChains];
+  for (int i = 0; i < nc; ++i) v[i] = chain_view(h, p.chains[i]);
+  if (fork && nc > 1) {
+    cudaStream_t cs[kMaxChains];
+    cs[0] = s;
+    for (int i = 1; i < nc; ++i) cs[i] = h->chain_streams[i];
     CU_OK(h, cudaEventRecord(h->chain_ev[0], s));
-    for (int i = 1; i < p.n_chains; ++i) CU_OK(h, cudaStreamWaitEvent(h->chain_streams[i], h->chain_ev[0], 0));
-    for (int i = 0; i < p.n_chains; ++i) {
-      cudaStream_t cs = i == 0 ? s : h->chain_streams[i];
-      TRY(run_decode_chain(h, cs, p.chains[i], logits_out, ldl, eos, pad, min_new));
+    for (int i = 1; i < nc; ++i) CU_OK(h, cudaStreamWaitEvent(cs[i], h->chain_ev[0], 0));
+    size_t k = 0;
+    for (int l = 0; l < c.Ld; ++l) {
+      for (int i = 0; i < nc; ++i) {
+        TRY(chain_layer_pre(h, cs[i], v[i], l));
+        if (h->serialize_xattn && k > 0) CU_OK(h, cudaStreamWaitEvent(cs[i], xattn_event(h, k - 1), 0));
+        // after an event wait the kernel has two predecessors: launch it without the PDL attribute
+        TRY(chain_layer_cross(h, cs[i], v[i], l, h->use_pdl && !(h->serialize_xattn && k > 0)));
+        if (h->serialize_xattn) CU_OK(h, cudaEventRecord(xattn_event(h, k), cs[i]));
+        ++k;
+        TRY(chain_layer_post(h, cs[i], v[i], l));
+      }
+    }
+    for (int i = 0; i < nc; ++i) {
+      TRY(chain_head(h, cs[i], v[i], logits_out, ldl, eos, pad, min_new));
       if (i > 0) {
-        CU_OK(h, cudaEventRecord(h->chain_ev[i], cs));
+        CU_OK(h, cudaEventRecord(h->chain_ev[i], cs[i]));
         CU_OK(h, cudaStreamWaitEvent(s, h->chain_ev[i], 0));
       }
     }
   } else {
-    for (int i = 0; i < p.n_chains; ++i) TRY(run_decode_chain(h, s, p.chains[i], logits_out, ldl, eos, pad, min_new));
+    for (int i = 0; i < nc; ++i) {
+      for (int l = 0; l < c.Ld; ++l) {
+        TRY(chain_layer_pre(h, s, v[i], l));
+        TRY(chain_layer_cross(h, s, v[i], l, h->use_pdl));
+        TRY(chain_layer_post(h, s, v[i], l));
+      }
+      TRY(chain_head(h, s, v[i], logits_out, ldl, eos, pad, min_new));
+    }
   }
   // joins every chain; not PDL-launched so that it sees all of them complete
   CU_OK(h, launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, s, false, p.state.as<DecodeState>()));
