@@ -25,6 +25,7 @@
 #include "attention_encoder_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm_splitk.cuh"
 
 using namespace b200;
 typedef __nv_bfloat16 bf16;
@@ -162,8 +163,9 @@ struct EncLayerW {
   CUtensorMap tm_qkv, tm_o, tm_wi, tm_ffo;
 };
 struct DecLayerW {
-  DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved for BN=64
+  DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved per N-tile of the decode wi GEMM
   CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
+  int wi_rows = 0;
 };
 
 constexpr int kMaxChains = 8;
@@ -237,6 +239,15 @@ struct b200t5_ctx {
   bool serialize_xattn = false;  // measured slower on B200 (300 vs 261 ms/batch): kept as an env knob only
   std::vector<cudaEvent_t> xattn_ev;
   GeluLut gelu_lut{nullptr, 0, 0};
+  // decode GEMMs: cluster split-K tiles (gemm_splitk.cuh). {BN, wanted split} per product;
+  // B200T5_SK=0 selects the persistent kernel instead, B200T5_SK="bn,s,bn,s,bn,s,bn,s" overrides
+  // (order: qkv, attention projections o/cq/co, wi, ffo).
+  struct SkChoice {
+    int bn, split;
+  };
+  int small_prio = 0;  // B200T5_PRIO: launch priority of the latency-bound decode kernels (see launch_priority())
+  bool sk_on = true;
+  SkChoice sk_qkv{64, 2}, sk_proj{64, 4}, sk_wi{128, 2}, sk_ffo{64, 4};  // best of the B200 sweep (tools/sweep_decode.sh)
   int chains_override = 0;
   cudaStream_t chain_streams[kMaxChains] = {};
   cudaEvent_t chain_ev[kMaxChains + 1] = {};
@@ -321,6 +332,17 @@ static cudaError_t run_gemm(b200t5_ctx* h, const GemmOp& g, const void* ep, cuda
   return cudaErrorInvalidValue;
 }
 
+// split-K cluster GEMM (decode): Epi chosen by the caller, BN/split from the handle's choice
+template <class Epi>
+static cudaError_t run_gemm_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, const CUtensorMap& tmA,
+                               const CUtensorMap& tmB, int M, int N, int K, const typename Epi::Params& ep,
+                               cudaStream_t s, bool pdl) {
+  h->launches++;
+  const int split = splitk_factor(K, ch.split);
+  if (ch.bn == 128) return launch_gemm_splitk<128, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl);
+  return launch_gemm_splitk<64, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl);
+}
+
 static cudaError_t run_rmsnorm(b200t5_ctx* h, const bf16* x, const bf16* w, bf16* y, int M, int d, float eps,
                                cudaStream_t s, bool pdl = false) {
   if (h) h->launches++;
@@ -339,6 +361,11 @@ static cudaError_t init_kernel_attrs() {
   PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
+#define PREPSK(BN, EPI) \
+  if ((e = prepare_gemm_splitk<BN, EPI>()) != cudaSuccess) return e;
+  PREPSK(64, EpiStore) PREPSK(128, EpiStore) PREPSK(64, EpiResidual) PREPSK(128, EpiResidual)
+  PREPSK(64, EpiQkvDecode) PREPSK(128, EpiQkvDecode) PREPSK(64, EpiGeglu) PREPSK(128, EpiGeglu)
+#undef PREPSK
   if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSelfWarpsPerCta * 4096 * 4)) != cudaSuccess)
     return e;
@@ -429,6 +456,19 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   h->enc_attn_tc = !(ea_env && strcmp(ea_env, "mma") == 0);
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
+  if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* sk_env = getenv("B200T5_SK")) {
+    int v[8];
+    const int n = sscanf(sk_env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
+    if (n == 1 && v[0] == 0) h->sk_on = false;
+    if (n == 8) {
+      b200t5_ctx::SkChoice* dst[4] = {&h->sk_qkv, &h->sk_proj, &h->sk_wi, &h->sk_ffo};
+      for (int i = 0; i < 4; ++i) {
+        dst[i]->bn = v[2 * i] == 128 ? 128 : 64;
+        dst[i]->split = v[2 * i + 1] >= 8 ? 8 : (v[2 * i + 1] >= 4 ? 4 : (v[2 * i + 1] >= 2 ? 2 : 1));
+      }
+    }
+  }
   const char* ch_env = getenv("B200T5_CHAINS");
   h->chains_override = ch_env ? atoi(ch_env) : 0;
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -657,15 +697,19 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     const bf16* wi1 = wi0 ? take(h, key("layer.2.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
     if (!wi1) return rc;
     int wi_rows = 0;
-    TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, 64, &wi_rows));
+    // TMA box rows = the N-tile of the kernel that will read the weight (split-K or persistent)
+    const int bn_qkv = h->sk_on ? h->sk_qkv.bn : 64, bn_proj = h->sk_on ? h->sk_proj.bn : 32;
+    const int bn_wi = h->sk_on ? h->sk_wi.bn : 64, bn_ffo = h->sk_on ? h->sk_ffo.bn : 32;
+    TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, bn_wi, &wi_rows));
+    w.wi_rows = wi_rows;
     if (!(p = take(h, key("layer.2.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
     TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
-    TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, 64);
-    TMAP(h, &w.tm_o, w.wo.p, d, I, 32);
-    TMAP(h, &w.tm_cq, w.wcq.p, I, d, 32);
-    TMAP(h, &w.tm_co, w.wco.p, d, I, 32);
-    TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, 64);
-    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, 32);
+    TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, bn_qkv);
+    TMAP(h, &w.tm_o, w.wo.p, d, I, bn_proj);
+    TMAP(h, &w.tm_cq, w.wcq.p, I, d, bn_proj);
+    TMAP(h, &w.tm_co, w.wco.p, d, I, bn_proj);
+    TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, bn_wi);
+    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, bn_ffo);
   }
   TMAP(h, &h->tm_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 256);
 
@@ -737,7 +781,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
     // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
-    int nc = B >= 128 ? 4 : (B >= 64 ? 2 : 1);
+    int nc = B >= 128 ? 2 : 1;
     if (h->chains_override > 0) nc = h->chains_override;
     if (nc > kMaxChains) nc = kMaxChains;
     if (nc > B) nc = B;
@@ -865,7 +909,8 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
   CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
                          dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
@@ -873,12 +918,14 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   h->launches++;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
   CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiStore::Params ep{v.dq, I};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
 }
@@ -889,6 +936,11 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
   Plan& p = *h->plan;
   const int B = p.B, S = p.S, I = c.I, H = c.H;
   bf16* ckv = p.cross_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
+  struct PrioGuard {
+    int saved;
+    PrioGuard() : saved(launch_priority()) { launch_priority() = 0; }
+    ~PrioGuard() { launch_priority() = saved; }
+  } guard;
   CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
                          v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
                          p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr));
@@ -905,16 +957,19 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
   DecLayerW& w = h->dec[l];
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
   CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiGeglu::Params ep{v.dh, F, h->gelu_lut};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
   }
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
-    CU_OK(h, run_gemm(h, mk(v.ch->tm_dh, w.tm_ffo, v.nb, d, F, G_RES32, 1), &ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_ffo, v.ch->tm_dh, w.tm_ffo, v.nb, d, F, ep, s, pdl));
+    else CU_OK(h, run_gemm(h, mk(v.ch->tm_dh, w.tm_ffo, v.nb, d, F, G_RES32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
 }
@@ -967,6 +1022,10 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
   const int nc = p.n_chains;
   ChainView v[kMaxChains];
   for (int i = 0; i < nc; ++i) v[i] = chain_view(h, p.chains[i]);
+  struct StepPrio {
+    StepPrio(int pr) { launch_priority() = pr; }
+    ~StepPrio() { launch_priority() = 0; }
+  } step_prio(h->small_prio);
   if (fork && nc > 1) {
     cudaStream_t cs[kMaxChains];
     cs[0] = s;
@@ -1282,6 +1341,46 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
     if (bn == 128) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_LOGITS128, 1), &ep, s);
   }
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm(bn=%d, mode=%d): %s", bn, mode, cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
+extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn,
+                                       int split, int mode, int pow_mode, void* aux, int Tmax, int step, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
+  if ((bn != 64 && bn != 128) || (split != 1 && split != 2 && split != 4 && split != 8))
+    return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bn in {64,128}, split in {1,2,4,8}");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+  b200t5_ctx dummy;
+  dummy.num_sms = sms;
+  b200t5_ctx::SkChoice ch{bn, split};
+  cudaError_t e = cudaErrorInvalidValue;
+  bf16* Cb = static_cast<bf16*>(C);
+  DevBuf st;
+  if (mode == 0) {
+    EpiStore::Params ep{Cb, N};
+    e = run_gemm_sk<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
+  } else if (mode == 1) {
+    EpiResidual::Params ep{Cb, Cb, N};
+    e = run_gemm_sk<EpiResidual>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
+  } else if (mode == 2) {
+    GeluLut lut;
+    int lrc = ensure_gelu_lut(nullptr, pow_mode, &lut);
+    if (lrc != B200T5_OK) return lrc;
+    EpiGeglu::Params ep{Cb, N / 2, lut};
+    e = run_gemm_sk<EpiGeglu>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
+  } else if (mode == 4) {
+    if (!aux || N % 192 || Tmax <= step) return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bad QKV arguments");
+    if (st.alloc(sizeof(DecodeState)) != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "alloc");
+    set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
+    EpiQkvDecode::Params ep{Cb, static_cast<bf16*>(aux), &st.as<DecodeState>()->step, M, N / 192, Tmax};
+    e = run_gemm_sk<EpiQkvDecode>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm_splitk(bn=%d, split=%d, mode=%d): %s", bn, split, mode, cudaGetErrorString(e));
   return B200T5_OK;
 }
 

@@ -173,12 +173,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, m_fastest);
       const int m = tc.m_tile * kBM + q * 32 + lane;
-      typename Epi::template Pre<BN> pre;
-      pre.load(ep, m, m < M, tc.n_tile, N);  // operands of the epilogue that do not need the accumulator
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem, pre);
+      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -194,7 +192,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ======================================================================== epilogues
-// acc[32]: 32 consecutive fp32 accumulator columns of this thread's row.
+// Every functor works on CHUNKS: 32 consecutive fp32 accumulator columns of one output row
+// (acc[] holds their bit patterns). `chunk_pre` fetches whatever the chunk needs that does not
+// depend on the accumulator (so callers can issue it early); `chunk` applies the T5 rounding
+// contract and writes HBM. Paired functors (GeGLU) consume two chunks: gate and up.
+// The persistent kernel above feeds chunks straight from TMEM (`run`); the split-K kernel
+// (gemm_splitk.cuh) feeds them from the cluster-reduced partial sums.
 
 DEVINL void round_pack_32(const uint32_t (&acc)[32], uint32_t (&out)[16]) {
 #pragma unroll
@@ -210,32 +213,50 @@ DEVINL void store_row_chunk(__nv_bfloat16* dst, const uint32_t (&p)[16], int n0,
   }
 }
 
+struct NoPre {};
+
+// Drives an unpaired functor over the BN columns of this thread's TMEM row, fetching the
+// pre-operands of chunk c+1 before chunk c is processed.
+template <int BN, class Epi>
+DEVINL void run_chunks_from_tmem(const typename Epi::Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N,
+                                 const uint8_t* epi_smem) {
+  typename Epi::ChunkPre pre[2];
+  if (m_ok) Epi::chunk_pre(p, m, n_tile * BN, N, pre[0]);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; c += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (c + u < BN / 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + (c + u) * 32, acc);
+        const int n0 = n_tile * BN + (c + u) * 32;
+        if (m_ok && c + u + 1 < BN / 32 && n0 + 32 < N) Epi::chunk_pre(p, m, n0 + 32, N, pre[(u + 1) & 1]);
+        tmem_ld_wait();
+        if (m_ok && n0 < N) Epi::chunk(p, acc, m, n0, N, epi_smem, pre[u & 1]);
+      }
+    }
+  }
+}
+
 // ---- plain store: C = bf16(acc)
 struct EpiStore {
   struct Params {
     __nv_bfloat16* C;
     int ldc;
   };
+  static constexpr bool kPaired = false;
+  typedef NoPre ChunkPre;
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
+  static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
+                           const ChunkPre&) {
+    uint32_t o[16];
+    round_pack_32(acc, o);
+    store_row_chunk(p.C + static_cast<size_t>(m) * p.ldc + n0, o, n0, N);
+  }
   template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + c * 32;
-      if (m_ok && n0 < N) {
-        uint32_t o[16];
-        round_pack_32(acc, o);
-        store_row_chunk(p.C + static_cast<size_t>(m) * p.ldc + n0, o, n0, N);
-      }
-    }
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
+    run_chunks_from_tmem<BN, EpiStore>(p, taddr, m, m_ok, n_tile, N, es);
   }
 };
 
@@ -246,53 +267,36 @@ struct EpiResidual {
     const __nv_bfloat16* R;
     int ld;
   };
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
-  // The residual operand does not depend on the accumulator: for the small decode tiles it is
-  // fetched while the main loop is still running (one row x BN columns per thread).
-  template <int BN>
-  struct Pre {
-    static constexpr bool kOn = BN <= 64;
-    uint4 r[kOn ? BN / 8 : 1];
-    DEVINL void load(const Params& p, int m, bool m_ok, int n_tile, int N) {
-      if constexpr (kOn) {
-        const int n0 = n_tile * BN;
-        const uint4* r4 = reinterpret_cast<const uint4*>(p.R + static_cast<size_t>(m) * p.ld + n0);
-#pragma unroll
-        for (int g = 0; g < BN / 8; ++g) r[g] = (m_ok && n0 + g * 8 + 8 <= N) ? r4[g] : make_uint4(0, 0, 0, 0);
-      }
-    }
+  static constexpr bool kPaired = false;
+  struct ChunkPre {
+    uint4 r[4];
   };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + c * 32;
-      if (m_ok && n0 < N) {
-        const size_t off = static_cast<size_t>(m) * p.ld + n0;
-        const uint4* r4 = reinterpret_cast<const uint4*>(p.R + off);
-        uint32_t o[16];
+  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  // The residual operand does not depend on the accumulator: it is fetched while the main loop /
+  // the previous chunk is still in flight.
+  static DEVINL void chunk_pre(const Params& p, int m, int n0, int N, ChunkPre& pre) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.R + static_cast<size_t>(m) * p.ld + n0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (n0 + g * 8 + 8 <= N) {
-            uint4 r;
-            if constexpr (Pre<BN>::kOn) r = pre.r[c * 4 + g];
-            else r = r4[g];
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    for (int g = 0; g < 4; ++g) pre.r[g] = (n0 + g * 8 + 8 <= N) ? r4[g] : make_uint4(0, 0, 0, 0);
+  }
+  static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
+                           const ChunkPre& pre) {
+    uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]));
-              const float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]));
-              o[g * 4 + j] = pack_bf16x2(bf16_lo(rw[j]) + y0, bf16_hi(rw[j]) + y1);
-            }
-          }
-        }
-        store_row_chunk(p.C + off, o, n0, N);
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t rw[4] = {pre.r[g].x, pre.r[g].y, pre.r[g].z, pre.r[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]));
+        const float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]));
+        o[g * 4 + j] = pack_bf16x2(bf16_lo(rw[j]) + y0, bf16_hi(rw[j]) + y1);
       }
     }
+    store_row_chunk(p.C + static_cast<size_t>(m) * p.ld + n0, o, n0, N);
+  }
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
+    run_chunks_from_tmem<BN, EpiResidual>(p, taddr, m, m_ok, n_tile, N, es);
   }
 };
 
@@ -343,24 +347,39 @@ struct EpiGeglu {
     int F;
     GeluLut lut;
   };
-  static DEVINL void prologue(const Params& p, uint8_t* epi_smem, int tid) {
-    // stage the gelu table (a few KB) with 16-byte loads; only the 4 epilogue warps take part
+  static constexpr bool kPaired = true;
+  typedef NoPre ChunkPre;
+  // stage the gelu table (a few KB) with 16-byte loads; `nthreads` epilogue threads take part
+  // (named barrier 2 is reserved for them)
+  static DEVINL void prologue(const Params& p, uint8_t* epi_smem, int tid, int nthreads = 128) {
     const int nvec = (2 * (p.lut.hi - p.lut.lo) * 2 + 15) / 16;
     const uint4* src = reinterpret_cast<const uint4*>(p.lut.table);
     uint4* dst = reinterpret_cast<uint4*>(epi_smem);
-    for (int i = tid; i < nvec; i += 128) dst[i] = src[i];
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    for (int i = tid; i < nvec; i += nthreads) dst[i] = src[i];
+    asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory");
   }
-  template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem,
-                         const Pre<BN>&) {
-    constexpr int HALF = BN / 2;
+  // g/u: gate and up accumulators of features [f0, f0+32)
+  static DEVINL void chunk2(const Params& p, const uint32_t (&g)[32], const uint32_t (&u)[32], int m, int f0,
+                            const uint8_t* epi_smem) {
     const uint16_t* lut = reinterpret_cast<const uint16_t*>(epi_smem);
     const int lo = p.lut.lo, hi = p.lut.hi;
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float r[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float x = bf16_round(__uint_as_float(g[2 * i + e]));
+        const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
+        r[e] = gelu_from_lut(x, lut, lo, hi) * lin;
+      }
+      o[i] = pack_bf16x2(r[0], r[1]);
+    }
+    store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
+  }
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem) {
+    constexpr int HALF = BN / 2;
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
       uint32_t g[32], u[32];
@@ -368,21 +387,7 @@ struct EpiGeglu {
       tmem_ld_32x32(taddr + HALF + c * 32, u);
       tmem_ld_wait();
       const int f0 = n_tile * HALF + c * 32;
-      if (m_ok && f0 < p.F) {
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float r[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float x = bf16_round(__uint_as_float(g[2 * i + e]));
-            const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
-            r[e] = gelu_from_lut(x, lut, lo, hi) * lin;
-          }
-          o[i] = pack_bf16x2(r[0], r[1]);
-        }
-        store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
-      }
+      if (m_ok && f0 < p.F) chunk2(p, g, u, m, f0, epi_smem);
     }
   }
 };
@@ -395,33 +400,25 @@ struct EpiCrossKV {
     __nv_bfloat16* arena;
     int B, H, S;
   };
+  static constexpr bool kPaired = false;
+  typedef NoPre ChunkPre;
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
-  template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
+  static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
+  static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
+                           const ChunkPre&) {
     const int b = m / p.S, s = m - b * p.S;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + c * 32;
-      if (m_ok && n0 < N) {
-        const int hd = p.H * 64;
-        const int lkv = n0 / hd;
-        const int rem = n0 - lkv * hd;
-        const int h = rem >> 6, d0 = rem & 63;
-        uint32_t o[16];
-        round_pack_32(acc, o);
-        __nv_bfloat16* dst =
-            p.arena + ((((static_cast<size_t>(lkv) * p.B + b) * p.H + h) * p.S + s) << 6) + d0;
-        store_row_chunk(dst, o, n0, N);
-      }
-    }
+    const int hd = p.H * 64;
+    const int lkv = n0 / hd;
+    const int rem = n0 - lkv * hd;
+    const int h = rem >> 6, d0 = rem & 63;
+    uint32_t o[16];
+    round_pack_32(acc, o);
+    __nv_bfloat16* dst = p.arena + ((((static_cast<size_t>(lkv) * p.B + b) * p.H + h) * p.S + s) << 6) + d0;
+    store_row_chunk(dst, o, n0, N);
+  }
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
+    run_chunks_from_tmem<BN, EpiCrossKV>(p, taddr, m, m_ok, n_tile, N, es);
   }
 };
 
@@ -435,38 +432,31 @@ struct EpiQkvDecode {
     const int* step;       // device scalar: current decode position t
     int B, H, Tmax;
   };
+  static constexpr bool kPaired = false;
+  typedef NoPre ChunkPre;
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
-  template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
+  static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
+  static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
+                           const ChunkPre&) {
     const int I = p.H * 64;
-    const int t = *p.step;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + c * 32;
-      if (m_ok && n0 < N) {
-        uint32_t o[16];
-        round_pack_32(acc, o);
-        __nv_bfloat16* dst;
-        if (n0 < I) {
-          dst = p.q + static_cast<size_t>(m) * I + n0;
-        } else {
-          const int r = n0 - I;
-          const int kv = r / I;
-          const int rem = r - kv * I;
-          const int h = rem >> 6, d0 = rem & 63;
-          dst = p.cache + ((((static_cast<size_t>(kv) * p.B + m) * p.H + h) * p.Tmax + t) << 6) + d0;
-        }
-        store_row_chunk(dst, o, n0, N);
-      }
+    uint32_t o[16];
+    round_pack_32(acc, o);
+    __nv_bfloat16* dst;
+    if (n0 < I) {
+      dst = p.q + static_cast<size_t>(m) * I + n0;
+    } else {
+      const int t = *p.step;
+      const int r = n0 - I;
+      const int kv = r / I;
+      const int rem = r - kv * I;
+      const int h = rem >> 6, d0 = rem & 63;
+      dst = p.cache + ((((static_cast<size_t>(kv) * p.B + m) * p.H + h) * p.Tmax + t) << 6) + d0;
     }
+    store_row_chunk(dst, o, n0, N);
+  }
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
+    run_chunks_from_tmem<BN, EpiQkvDecode>(p, taddr, m, m_ok, n_tile, N, es);
   }
 };
 
@@ -484,12 +474,7 @@ struct EpiArgmax {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
     float best = -INFINITY;
     int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
     const bool block_eos = *p.step < p.min_new;
@@ -525,12 +510,7 @@ struct EpiStoreF32 {
   };
   static DEVINL void prologue(const Params&, uint8_t*, int) {}
   template <int BN>
-  struct Pre {
-    DEVINL void load(const Params&, int, bool, int, int) {}
-  };
-  template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*,
-                         const Pre<BN>& pre) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -555,6 +535,15 @@ cudaError_t prepare_gemm() {
                               GemmCfg<BN>::kSmemBytes);
 }
 
+// Scheduling priority attached to every kernel launched through launch_kernel / launch_gemm_splitk
+// (0 = default). The decode step raises it for the short latency-bound kernels so that, when
+// row-chains run concurrently, their CTAs are placed ahead of the queued CTAs of another chain's
+// HBM-streaming cross-attention kernel instead of behind them.
+inline int& launch_priority() {
+  static thread_local int prio = 0;
+  return prio;
+}
+
 // Launch with (optionally) the programmatic-stream-serialization attribute (PDL).
 template <class... KArgs, class... Args>
 cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
@@ -564,11 +553,20 @@ cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (launch_priority() != 0) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = launch_priority();
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -136,6 +136,12 @@ int b200t5_relative_bucket(int relative_position, int bidirectional, int num_buc
  * 2 GeGLU (W rows interleaved per bn/2, C is [M,N/2]), 3 fp32 output (C is float*). bn in {32,64,128,256}. */
 int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
                      int pow_mode, void* stream);
+/* Same contract through the cluster split-K kernel the decode step uses (csrc/gemm_splitk.cuh):
+ * bn in {64,128}; split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
+ * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C), 2 GeGLU, 4 decoder QKV: C is the q
+ * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written. */
+int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int split,
+                            int mode, int pow_mode, void* aux, int Tmax, int step, void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);
 /* self != 0: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk]. */
 int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx, int B,

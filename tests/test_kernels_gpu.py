@@ -134,6 +134,95 @@ def test_gemm_geglu(lib, M, F, K, bn):
     assert (out == ref).float().mean().item() > 0.98
 
 
+SK_SHAPES = [
+    # M, N, K, bn, split   (the decode-step products of FLAN-T5-base/small/large and ragged edges)
+    (256, 768, 768, 64, 4), (256, 768, 2048, 64, 4), (256, 768, 2048, 64, 8), (256, 2304, 768, 128, 4),
+    (64, 768, 768, 64, 4), (8, 512, 384, 64, 4), (8, 512, 384, 64, 8), (130, 1024, 2816, 64, 4),
+    (256, 1000, 512, 128, 2), (200, 136, 64, 64, 4), (256, 768, 768, 64, 1), (100, 264, 1024, 128, 8),
+]
+
+
+@pytest.mark.parametrize("M,N,K,bn,split", SK_SHAPES)
+def test_gemm_splitk_store(lib, M, N, K, bn, split):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + split)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    Cout = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(Cout), M, N, K, bn, split, 0, 0, None, 0, 0, None))
+    torch.cuda.synchronize()
+    ref32 = A.float() @ W.float().T
+    assert torch.isfinite(Cout.float()).all()
+    # fp32 partial sums added in rank order, one rounding to bf16: within 1 bf16 ulp of the fp32 reference
+    ok = ulp_close(Cout, ref32.bfloat16(), 1.0) | ((Cout.float() - ref32).abs() <= 1e-3)
+    assert ok.all(), f"max err {(Cout.float() - ref32).abs().max().item()}"
+    assert (Cout == ref32.bfloat16()).float().mean().item() > 0.995
+    # deterministic: the reduction order is fixed
+    C2 = torch.empty_like(Cout)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(C2), M, N, K, bn, split, 0, 0, None, 0, 0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(Cout, C2)
+
+
+@pytest.mark.parametrize("M,N,K,bn,split", [(256, 768, 768, 64, 4), (256, 768, 2048, 64, 8), (130, 264, 128, 128, 2), (37, 512, 1024, 64, 4)])
+def test_gemm_splitk_residual(lib, M, N, K, bn, split):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.2).bfloat16()
+    R = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    Cio = R.clone()
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(Cio), M, N, K, bn, split, 1, 0, None, 0, 0, None))
+    torch.cuda.synchronize()
+    y = (A.float() @ W.float().T).bfloat16()
+    ref = (R.float() + y.float()).bfloat16()
+    tol = 2.0 ** -7 * (y.float().abs() + ref.float().abs()) + 1e-3
+    assert ((Cio.float() - ref.float()).abs() <= tol).all()
+    assert (Cio == ref).float().mean().item() > 0.99
+
+
+@pytest.mark.parametrize("M,F,K,bn,split", [(256, 2048, 768, 128, 2), (256, 2048, 768, 64, 4), (64, 1024, 512, 128, 4), (100, 2816, 1024, 64, 2)])
+def test_gemm_splitk_geglu(lib, M, F, K, bn, split):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W0 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
+    W1 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
+    half = bn // 2
+    assert F % half == 0
+    ntiles = F // half
+    Wi = torch.zeros(ntiles * bn, K, device="cuda", dtype=torch.bfloat16)
+    Wi.view(ntiles, 2, half, K)[:, 0] = W0.view(ntiles, half, K)
+    Wi.view(ntiles, 2, half, K)[:, 1] = W1.view(ntiles, half, K)
+    out = torch.full((M, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(Wi), P(out), M, 2 * F, K, bn, split, 2, 0, None, 0, 0, None))
+    torch.cuda.synchronize()
+    gate = (A.float() @ W0.float().T).bfloat16()
+    lin = (A.float() @ W1.float().T).bfloat16()
+    ref = hf_gelu_new(gate) * lin
+    assert torch.isfinite(out.float()).all()
+    close = ulp_close(out, ref, 2.0) | ((out.float() - ref.float()).abs() < 1e-6)
+    assert close.float().mean().item() > 0.999
+    assert (out == ref).float().mean().item() > 0.98
+
+
+@pytest.mark.parametrize("B,H,K,bn,split,Tmax,step", [(256, 12, 768, 128, 4, 16, 5), (8, 6, 512, 64, 4, 8, 0), (70, 16, 1024, 128, 2, 4, 3)])
+def test_gemm_splitk_qkv_append(lib, B, H, K, bn, split, Tmax, step):
+    """q -> [B, I]; k/v rows appended in place at cache[kv][b][h][step] (replaces cache_utils.py:119-120)."""
+    I = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B + H)
+    A = (torch.randn(B, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(3 * I, K, device="cuda", generator=g) * 0.3).bfloat16()
+    q = torch.full((B, I), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cache = torch.zeros(2, B, H, Tmax, 64, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(q), B, 3 * I, K, bn, split, 4, 0, P(cache), Tmax, step, None))
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().T).bfloat16()
+    rq, rk, rv = ref[:, :I], ref[:, I:2 * I].view(B, H, 64), ref[:, 2 * I:].view(B, H, 64)
+    assert (ulp_close(q, rq, 1.0) | ((q.float() - rq.float()).abs() <= 1e-3)).all()
+    assert (ulp_close(cache[0, :, :, step], rk, 1.0) | ((cache[0, :, :, step].float() - rk.float()).abs() <= 1e-3)).all()
+    assert (ulp_close(cache[1, :, :, step], rv, 1.0) | ((cache[1, :, :, step].float() - rv.float()).abs() <= 1e-3)).all()
+    other = [t for t in range(Tmax) if t != step]
+    assert (cache[:, :, :, other] == 0).all()  # no other cache row is touched
+
+
 def test_gemm_logits_f32(lib):
     M, N, K = 256, 1000, 512
     g = torch.Generator(device="cuda").manual_seed(9)
