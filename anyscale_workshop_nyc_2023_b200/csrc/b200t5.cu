@@ -26,6 +26,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm_splitk.cuh"
+#include "decode_mega.cuh"
 
 using namespace b200;
 typedef __nv_bfloat16 bf16;
@@ -166,6 +167,9 @@ struct DecLayerW {
   DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved per N-tile of the decode wi GEMM
   CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
   int wi_rows = 0;
+  DevBuf mega_wi_own;  // wi interleaved for the persistent kernel's tile when it differs from `wi`
+  void* mega_wi = nullptr;
+  int mega_wi_rows = 0, mega_wi_bn = 0;
 };
 
 constexpr int kMaxChains = 8;
@@ -193,6 +197,10 @@ struct Plan {
   };
   int n_chains = 1;
   Chain chains[kMaxChains];
+  // persistent decode kernel (decode_mega.cuh): device-resident tensor maps, layer table, split-K workspace
+  bool mega_ok = false;
+  DevBuf mega_maps, mega_layers, mega_ws, mega_bar, mega_prof;
+  MegaParams mega{};
   // decode-step graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -245,6 +253,11 @@ struct b200t5_ctx {
   struct SkChoice {
     int bn, split;
   };
+  // Persistent decode kernel (decode_mega.cuh). Bit-identical to the step graph but, as measured on B200
+  // (profiles/mega_phases_r1.md), not yet faster: it is opt-in. B200T5_MEGA=1 enables it,
+  // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
+  bool mega_on = false;
+  int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
   int small_prio = 0;  // B200T5_PRIO: launch priority of the latency-bound decode kernels (see launch_priority())
   bool sk_on = true;
   SkChoice sk_qkv{64, 2}, sk_proj{64, 4}, sk_wi{128, 2}, sk_ffo{64, 4};  // best of the B200 sweep (tools/sweep_decode.sh)
@@ -366,6 +379,8 @@ static cudaError_t init_kernel_attrs() {
   PREPSK(64, EpiStore) PREPSK(128, EpiStore) PREPSK(64, EpiResidual) PREPSK(128, EpiResidual)
   PREPSK(64, EpiQkvDecode) PREPSK(128, EpiQkvDecode) PREPSK(64, EpiGeglu) PREPSK(128, EpiGeglu)
 #undef PREPSK
+  if ((e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmemBytes)) != cudaSuccess)
+    return e;
   if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSelfWarpsPerCta * 4096 * 4)) != cudaSuccess)
     return e;
@@ -457,6 +472,18 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* mg_env = getenv("B200T5_MEGA")) {
+    int v[7];
+    const int n = sscanf(mg_env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+    if (n == 1) h->mega_on = v[0] != 0;
+    if (n == 7) {
+      auto bn_ok = [](int b) { return b == 32 || b == 64 || b == 128; };
+      if (bn_ok(v[0]) && bn_ok(v[1]) && bn_ok(v[3]) && (v[4] == 64 || v[4] == 128) && bn_ok(v[5]) && v[2] >= 1 && v[6] >= 1) {
+        for (int i = 0; i < 7; ++i) h->mega_cfg[i] = v[i];
+        h->mega_on = true;
+      }
+    }
+  }
   if (const char* sk_env = getenv("B200T5_SK")) {
     int v[8];
     const int n = sscanf(sk_env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
@@ -702,6 +729,17 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     const int bn_wi = h->sk_on ? h->sk_wi.bn : 64, bn_ffo = h->sk_on ? h->sk_ffo.bn : 32;
     TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, bn_wi, &wi_rows));
     w.wi_rows = wi_rows;
+    if (h->mega_on) {
+      const int mbn = h->mega_cfg[4];
+      if (mbn == bn_wi) {
+        w.mega_wi = w.wi.p;
+        w.mega_wi_rows = wi_rows;
+      } else {
+        TRY(interleave_geglu(h, wi0, wi1, w.mega_wi_own, F, d, mbn, &w.mega_wi_rows));
+        w.mega_wi = w.mega_wi_own.p;
+      }
+      w.mega_wi_bn = mbn;
+    }
     if (!(p = take(h, key("layer.2.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
     TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
     TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, bn_qkv);
@@ -716,6 +754,115 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
   h->raw.clear();
   h->raw_shape.clear();
   h->finalized = true;
+  return B200T5_OK;
+}
+
+
+// ================================================================== persistent decode kernel: host side
+// Largest k-split not above `want` that leaves every slice at least one 64-wide k-block.
+static int mega_ksplit(int K, int want) {
+  const int kblocks = (K + kBK - 1) / kBK;
+  for (int s = want < kblocks ? want : kblocks; s > 1; --s) {
+    const int per = (kblocks + s - 1) / s;
+    if ((s - 1) * per < kblocks) return s;
+  }
+  return 1;
+}
+
+static int build_mega(b200t5_ctx* h, Plan& pl) {
+  pl.mega_ok = false;
+  if (!h->mega_on) return B200T5_OK;
+  const Cfg& c = h->c;
+  const int B = pl.B, S = pl.S, T = pl.Tmax, d = c.d, I = c.I, F = c.F;
+  // shared-memory scratch of the attention phases
+  if (static_cast<size_t>(kMegaWarps) * T * 4 > kMegaScratchBytes ||
+      static_cast<size_t>(kMegaGroups) * (S + 4 * 64 + 8) * 4 > kMegaScratchBytes)
+    return B200T5_OK;  // too long for the resident kernel: the step graph handles it
+  int occ = 0;
+  CU_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_mega_kernel, kMegaThreads, kMegaSmemBytes));
+  int coop = 0;
+  CU_OK(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+  if (occ < 1 || !coop) return B200T5_OK;
+  const int bn_qkv = h->mega_cfg[0], bn_proj = h->mega_cfg[1], bn_cq = h->mega_cfg[3], bn_wi = h->mega_cfg[4], bn_ffo = h->mega_cfg[5];
+  const int ks_proj = mega_ksplit(I, h->mega_cfg[2]), ks_ffo = mega_ksplit(F, h->mega_cfg[6]);
+  const int nmaps = 6 * c.Ld + 4;
+  std::vector<CUtensorMap> maps(nmaps);
+  std::vector<MegaLayer> layers(c.Ld);
+  CU_OK(h, pl.mega_maps.alloc(sizeof(CUtensorMap) * nmaps));
+  CU_OK(h, pl.mega_layers.alloc(sizeof(MegaLayer) * c.Ld));
+  const int ks_max = ks_proj > ks_ffo ? ks_proj : ks_ffo;
+  CU_OK(h, pl.mega_ws.alloc(static_cast<size_t>(ks_max) * B * d * 4));
+  CU_OK(h, pl.mega_bar.alloc(256));
+  const CUtensorMap* dmaps = pl.mega_maps.as<CUtensorMap>();
+  for (int l = 0; l < c.Ld; ++l) {
+    DecLayerW& w = h->dec[l];
+    if (w.mega_wi_bn != bn_wi) return fail(h, B200T5_ESTATE, "decoder wi weights were not packed for the persistent kernel (bn_wi=%d)", bn_wi);
+    CUtensorMap* m = &maps[6 * l];
+    TMAP(h, &m[0], w.wqkv.p, 3 * I, d, bn_qkv);
+    TMAP(h, &m[1], w.wo.p, d, I, bn_proj);
+    TMAP(h, &m[2], w.wcq.p, I, d, bn_cq);
+    TMAP(h, &m[3], w.wco.p, d, I, bn_proj);
+    TMAP(h, &m[4], w.mega_wi, w.mega_wi_rows, d, bn_wi);
+    TMAP(h, &m[5], w.wff_o.p, d, F, bn_ffo);
+    MegaLayer& L = layers[l];
+    L.tm_qkv = dmaps + 6 * l;
+    L.tm_o = dmaps + 6 * l + 1;
+    L.tm_cq = dmaps + 6 * l + 2;
+    L.tm_co = dmaps + 6 * l + 3;
+    L.tm_wi = dmaps + 6 * l + 4;
+    L.tm_ffo = dmaps + 6 * l + 5;
+    L.ln0 = w.ln0.as<bf16>();
+    L.ln1 = w.ln1.as<bf16>();
+    L.ln2 = w.ln2.as<bf16>();
+    L.self_kv = pl.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T);
+    L.cross_kv = pl.cross_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * S);
+    L.wi_rows = w.mega_wi_rows;
+  }
+  CUtensorMap* a = &maps[6 * c.Ld];
+  TMAP(h, &a[0], pl.dxn.p, B, d, 128);
+  TMAP(h, &a[1], pl.dctx.p, B, I, 128);
+  TMAP(h, &a[2], pl.dh.p, B, F, 128);
+  TMAP(h, &a[3], h->lm_head.p, c.V, d, 128);
+  CU_OK(h, cudaMemcpy(pl.mega_maps.p, maps.data(), sizeof(CUtensorMap) * nmaps, cudaMemcpyHostToDevice));
+  CU_OK(h, cudaMemcpy(pl.mega_layers.p, layers.data(), sizeof(MegaLayer) * c.Ld, cudaMemcpyHostToDevice));
+  MegaParams& P = pl.mega;
+  P.B = B; P.S = S; P.T = T; P.d = d; P.I = I; P.F = F; P.H = c.H; P.V = c.V; P.Ld = c.Ld;
+  P.eps = c.eps;
+  P.dx = pl.dx.as<bf16>(); P.dxn = pl.dxn.as<bf16>(); P.dq = pl.dq.as<bf16>(); P.dctx = pl.dctx.as<bf16>(); P.dh = pl.dh.as<bf16>();
+  P.ws = pl.mega_ws.as<float>();
+  P.tm_dxn = dmaps + 6 * c.Ld; P.tm_dctx = dmaps + 6 * c.Ld + 1; P.tm_dh = dmaps + 6 * c.Ld + 2; P.tm_lm = dmaps + 6 * c.Ld + 3;
+  P.layers = pl.mega_layers.as<MegaLayer>();
+  P.final_ln = h->dec_final_ln.as<bf16>(); P.E = h->shared.as<bf16>();
+  P.extent = pl.extent.as<int>(); P.key_ok = pl.key_ok.as<unsigned char>(); P.dec_bias = pl.dec_bias.as<float>();
+  P.st = pl.state.as<DecodeState>(); P.unfinished = pl.unfinished.as<int>(); P.out_ids = pl.out_ids.as<long long>();
+  P.out_len = pl.out_len.as<int>(); P.pval = pl.pval.as<float>(); P.pidx = pl.pidx.as<int>(); P.n_vtiles = pl.n_vtiles;
+  P.lut = h->gelu_lut;
+  P.bar = pl.mega_bar.as<unsigned int>();
+  P.prof = nullptr;
+  P.prof_step = -1;
+  if (const char* pe = getenv("B200T5_MEGA_PROF")) {  // diagnostic: phase timeline of one step (tools/mega_phases.py)
+    CU_OK(h, pl.mega_prof.alloc(4096 * 8));
+    CU_OK(h, cudaMemset(pl.mega_prof.p, 0, 4096 * 8));
+    P.prof = pl.mega_prof.as<long long>();
+    P.prof_step = atoi(pe);
+  }
+  P.bn_qkv = bn_qkv; P.bn_proj = bn_proj; P.ks_proj = ks_proj; P.bn_cq = bn_cq; P.bn_wi = bn_wi; P.bn_ffo = bn_ffo;
+  P.ks_ffo = ks_ffo; P.bn_lm = 128;
+  pl.mega_ok = true;
+  return B200T5_OK;
+}
+
+static int launch_mega(b200t5_ctx* h, cudaStream_t s, long long eos, long long pad, int min_new, int nsteps) {
+  Plan& p = *h->plan;
+  p.mega.eos = eos;
+  p.mega.pad = pad;
+  p.mega.min_new = min_new;
+  p.mega.nsteps = nsteps;
+  CU_OK(h, cudaMemsetAsync(p.mega_bar.p, 0, 256, s));
+  void* args[1] = {&p.mega};
+  CU_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_mega_kernel), dim3(h->num_sms), dim3(kMegaThreads), args,
+                                       kMegaSmemBytes, s));
+  h->launches++;
   return B200T5_OK;
 }
 
@@ -795,6 +942,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
       TMAP(h, &ch.tm_dh, pl->dh.as<bf16>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
     }
   }
+  TRY(build_mega(h, *pl));
   h->plan = std::move(pl);
   return B200T5_OK;
 }
@@ -1133,7 +1281,8 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   const int poll = gp->poll_interval > 0 ? gp->poll_interval : 8;
   TRY(ensure_plan(h, B, S, T));
   Plan& p = *h->plan;
-  TRY(ensure_graph(h, eos, pad, min_new));
+  const bool mega = p.mega_ok;
+  if (!mega) TRY(ensure_graph(h, eos, pad, min_new));
   h->launches = 0;
   CU_OK(h, cudaEventRecord(h->ev[0], s));
   TRY(run_encoder(h, ids, mask, s));
@@ -1144,7 +1293,22 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   CU_OK(h, cudaGetLastError());
   CU_OK(h, cudaEventRecord(h->ev[1], s));
   int steps = 0;
-  for (int t = 0; t < T; ++t) {
+  if (mega) {
+    // the whole greedy loop, EOS early exit included, is one resident kernel
+    TRY(launch_mega(h, s, eos, pad, min_new, T));
+    CU_OK(h, cudaMemcpyAsync(p.h_state, p.state.p, sizeof(DecodeState), cudaMemcpyDeviceToHost, s));
+    steps = -1;  // read back from the device state in get_stats
+    if (p.mega.prof) {
+      std::vector<long long> st(4096);
+      CU_OK(h, cudaStreamSynchronize(s));
+      CU_OK(h, cudaMemcpy(st.data(), p.mega_prof.p, 4096 * 8, cudaMemcpyDeviceToHost));
+      // pairs (before barrier, after barrier): phase k runs from after[k-1] to before[k]
+      fprintf(stderr, "MEGA_PROF step %d (SM clocks of CTA 0):", p.mega.prof_step);
+      for (int i = 0; i < 4096 && st[i]; ++i) fprintf(stderr, " %lld", st[i] - st[0]);
+      fprintf(stderr, "\n");
+    }
+  }
+  for (int t = 0; t < T && !mega; ++t) {
     CU_OK(h, cudaGraphLaunch(p.gexec, s));
     h->launches += p.graph_nodes;
     ++steps;
@@ -1210,6 +1374,7 @@ extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
   CU_OK(h, cudaEventSynchronize(h->ev[2]));
   CU_OK(h, cudaEventElapsedTime(&out->encoder_ms, h->ev[0], h->ev[1]));
   CU_OK(h, cudaEventElapsedTime(&out->decode_ms, h->ev[1], h->ev[2]));
+  if (h->last_steps < 0) h->last_steps = h->plan->h_state->step;  // persistent kernel: steps were counted on the device
   out->decode_steps = h->last_steps;
   out->kernel_launches = h->launches;
   fill_stats_model(h, h->last_steps);

@@ -1,0 +1,829 @@
+// The whole greedy decode loop as ONE persistent cooperative kernel.
+//
+// Why: a decode step of FLAN-T5-base is ~135 dependent kernels whose useful work is a few
+// microseconds each (M = batch rows GEMMs, per-row norms, single-query attention). Launched one
+// by one - even inside a CUDA graph with programmatic dependent launch - every kernel costs
+// 5-10 us of launch, fill and drain, so the step takes ~1.6 ms while its HBM traffic needs 0.87 ms
+// (profiles/decode_trace_r1.md). Here one CTA per SM stays resident for the whole generate()
+// call; the ops of a step become PHASES separated by a grid-wide barrier (one atomic + one
+// polled load, ~0.5 us), pipelines/barriers/TMEM are set up once, and nothing returns to the
+// host until every row has finished (the EOS early exit is decided on the device).
+//
+// Phases of one decoder layer (reference: T5Block.forward, transformers modeling_t5.py:411-498):
+//   G_qkv   xn  -> q, K/V appended to the self cache      tcgen05 tiles, direct epilogue
+//   A_self  single-query attention over t+1 cached keys    one warp per (row, head)
+//   G_o     ctx -> fp32 split-K partials                   tcgen05 tiles
+//   E       x += bf16(sum partials); xn = RMSNorm(x)       one warp per row
+//   G_cq    xn  -> q                                        direct epilogue
+//   A_cross single-query attention over the encoder keys   4 warps per (row, head); HBM streaming
+//   G_co, E, G_wi (GeGLU epilogue), G_ffo, E               as above
+// then the lm_head tiles with the fused arg-max epilogue and the greedy bookkeeping (HF
+// GenerationMixin._sample, generation/utils.py:2762-2805), which also gathers the next token's
+// embedding and applies the first RMSNorm of the next step.
+//
+// GEMM phases reuse the warp roles of gemm.cuh inside the resident CTA: thread 0 = TMA producer,
+// warp 1 lane 0 = tcgen05.mma issuer, warps 4..7 = epilogue (TMEM lane quarters); the smem ring,
+// its mbarriers and the two TMEM accumulators persist across phases. The rounding contract is
+// the shared chunk functors of gemm.cuh; split-K partial sums are added in a fixed order, so the
+// output is run-to-run deterministic.
+#pragma once
+#include "attention_decode.cuh"
+#include "attention_encoder.cuh"  // cp_async_commit / cp_async_wait
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace b200 {
+
+constexpr int kMegaThreads = 384;
+constexpr int kMegaWarps = kMegaThreads / 32;
+constexpr int kMegaStages = 4;
+constexpr int kMegaBnMax = 128;
+constexpr int kMegaStageBytes = kBM * kBK * 2 + kMegaBnMax * kBK * 2;  // 32 KB
+constexpr int kMegaAccCols = 128;                                      // two accumulators -> 256 TMEM columns
+constexpr int kMegaGroups = 3;                                         // cross-attention: 4-warp groups per CTA
+constexpr int kMegaScratchBytes = 48 * 1024;                           // scores / gelu table (phases are disjoint)
+constexpr int kMegaSmemBytes = kMegaStages * kMegaStageBytes + 1024 /*align*/ + 512 /*barriers*/ + kMegaScratchBytes;
+
+struct MegaLayer {
+  const CUtensorMap *tm_qkv, *tm_o, *tm_cq, *tm_co, *tm_wi, *tm_ffo;  // device-resident tensor maps
+  const __nv_bfloat16 *ln0, *ln1, *ln2;
+  __nv_bfloat16* self_kv;         // [2][B][H][T][64]
+  const __nv_bfloat16* cross_kv;  // [2][B][H][S][64]
+  int wi_rows;                    // padded N of the interleaved wi weight
+};
+
+struct MegaParams {
+  int B, S, T, d, I, F, H, V, Ld;
+  float eps;
+  __nv_bfloat16 *dx, *dxn, *dq, *dctx, *dh;
+  float* ws;  // [ks][B][d] fp32 split-K partials
+  const CUtensorMap *tm_dxn, *tm_dctx, *tm_dh, *tm_lm;
+  const MegaLayer* layers;
+  const __nv_bfloat16 *final_ln, *E;
+  const int* extent;
+  const unsigned char* key_ok;
+  const float* dec_bias;
+  DecodeState* st;
+  int* unfinished;
+  long long* out_ids;
+  int* out_len;
+  float* pval;
+  int* pidx;
+  int n_vtiles;
+  long long eos, pad;
+  int min_new, nsteps;
+  GeluLut lut;
+  unsigned int* bar;  // grid barrier counter, zeroed by the host before the launch
+  long long* prof;    // optional: SM-clock stamps of CTA 0 at every phase boundary of step `prof_step`
+  int prof_step;
+  int bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo, bn_lm;
+};
+
+enum MegaEpi { ME_PARTIAL = 0, ME_QKV = 1, ME_STORE = 2, ME_GEGLU = 3, ME_ARGMAX = 4 };
+
+struct MegaShared {
+  uint8_t* ring;
+  uint64_t *full, *empty, *tfull, *tempty;
+  uint32_t* tmem_slot;
+  int* s_step;
+  uint8_t* scratch;
+};
+
+struct MegaPipe {
+  int stage = 0;
+  uint32_t phase = 0;
+  int as = 0;
+  uint32_t aphase = 0;
+};
+
+DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of the (cooperative) grid: one release-add and a polled acquire-load by thread 0
+// (SASS: RED.STRONG.GPU, LDG.STRONG.GPU + CCTL.IVALL - the acquire also drops this SM's stale L1
+// lines, so the other threads' plain loads after the bar.sync see the peers' writes). Thread 0 is
+// also the TMA producer: the proxy fence orders the peers' generic-proxy global writes, and this
+// CTA's generic-proxy use of the shared-memory ring, before its next async-proxy (TMA) accesses.
+DEVINL void grid_sync(unsigned int* bar, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned int spins = 0;
+    uint64_t t0 = 0;
+    while (ld_acquire_u32(bar) < target) {
+      if ((++spins & 0xFFFu) == 0) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) __trap();  // a protocol bug traps instead of hanging the GPU
+      }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- GEMM phase
+// D[M,N] = A[M,K] W[N,K]^T as 128 x bn tiles, K cut in `ksplit` slices; jobs round-robin over CTAs.
+struct MegaGemm {
+  const CUtensorMap *tmA, *tmB;
+  int M, N, K, bn, ksplit, epi;
+  // epilogue operands
+  EpiQkvDecode::Params qkv;
+  EpiStore::Params store;
+  EpiGeglu::Params geglu;
+  EpiArgmax::Params amax;
+  float* ws;
+  int ws_ld;  // row stride of ws (= N)
+};
+
+__device__ __noinline__ void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_base, const MegaGemm& g) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + kBM - 1) / kBM;
+  const int tiles_n = (g.N + g.bn - 1) / g.bn;
+  const int kblocks = (g.K + kBK - 1) / kBK;
+  const int kb_per = (kblocks + g.ksplit - 1) / g.ksplit;
+  const int njobs = tiles_m * tiles_n * g.ksplit;
+  const uint32_t stage_tx = static_cast<uint32_t>(kBM * kBK * 2 + g.bn * kBK * 2);
+
+  if (threadIdx.x == 0) {
+    // ------------------------------------------------------------ TMA producer
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      const int ks = job % g.ksplit, t = job / g.ksplit;
+      const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+      const int kb0 = ks * kb_per;
+      const int kb1 = kb0 + kb_per < kblocks ? kb0 + kb_per : kblocks;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&sh.empty[ps.stage], ps.phase ^ 1u);
+        uint8_t* sA = sh.ring + ps.stage * kMegaStageBytes;
+        mbar_arrive_expect_tx(&sh.full[ps.stage], stage_tx);
+        tma_load_2d(sA, g.tmA, &sh.full[ps.stage], kb * kBK, m_tile * kBM);
+        tma_load_2d(sA + kBM * kBK * 2, g.tmB, &sh.full[ps.stage], kb * kBK, n_tile * g.bn);
+        if (++ps.stage == kMegaStages) {
+          ps.stage = 0;
+          ps.phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, 0, 0);
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int ks = job % g.ksplit;
+        const int kb0 = ks * kb_per;
+        const int kb1 = kb0 + kb_per < kblocks ? kb0 + kb_per : kblocks;
+        mbar_wait(&sh.tempty[ps.as], ps.aphase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ps.as * kMegaAccCols);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&sh.full[ps.stage], ps.phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sh.ring + ps.stage * kMegaStageBytes);
+          const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
+          const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + kBM * kBK * 2);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&sh.empty[ps.stage]);
+          if (++ps.stage == kMegaStages) {
+            ps.stage = 0;
+            ps.phase ^= 1u;
+          }
+        }
+        umma_commit(&sh.tfull[ps.as]);
+        ps.as ^= 1;
+        if (ps.as == 0) ps.aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    if (g.epi == ME_GEGLU) EpiGeglu::prologue(g.geglu, sh.scratch, static_cast<int>(threadIdx.x) - 128, 128);
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      const int ks = job % g.ksplit, t = job / g.ksplit;
+      const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+      const int m = m_tile * kBM + q * 32 + lane;
+      const bool m_ok = m < g.M;
+      mbar_wait(&sh.tfull[ps.as], ps.aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ps.as * kMegaAccCols);
+      if (g.epi == ME_GEGLU) {
+        const int half = g.bn >> 1;
+        for (int c = 0; c < half / 32; ++c) {
+          uint32_t gt[32], up[32];
+          tmem_ld_32x32(taddr + c * 32, gt);
+          tmem_ld_32x32(taddr + half + c * 32, up);
+          tmem_ld_wait();
+          const int f0 = n_tile * half + c * 32;
+          if (m_ok && f0 < g.geglu.F) EpiGeglu::chunk2(g.geglu, gt, up, m, f0, sh.scratch);
+        }
+      } else if (g.epi == ME_ARGMAX) {
+        float best = -INFINITY;
+        int bidx = n_tile * g.bn;
+        const bool block_eos = *g.amax.step < g.amax.min_new;
+        for (int c = 0; c < g.bn / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          const int n0 = n_tile * g.bn + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            float v = bf16_round(__uint_as_float(acc[j]));
+            if (n >= g.N || (block_eos && n == g.amax.eos)) v = -INFINITY;
+            if (v > best) {
+              best = v;
+              bidx = n;
+            }
+          }
+        }
+        if (m_ok) {
+          g.amax.pval[static_cast<size_t>(m) * g.amax.n_tiles + n_tile] = best;
+          g.amax.pidx[static_cast<size_t>(m) * g.amax.n_tiles + n_tile] = bidx;
+        }
+      } else {
+        for (int c = 0; c < g.bn / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          const int n0 = n_tile * g.bn + c * 32;
+          if (m_ok && n0 < g.N) {
+            if (g.epi == ME_PARTIAL) {
+              float4* dst = reinterpret_cast<float4*>(g.ws + (static_cast<size_t>(ks) * g.M + m) * g.ws_ld + n0);
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                if (n0 + 4 * v + 4 <= g.N)
+                  dst[v] = make_float4(__uint_as_float(acc[4 * v]), __uint_as_float(acc[4 * v + 1]),
+                                       __uint_as_float(acc[4 * v + 2]), __uint_as_float(acc[4 * v + 3]));
+            } else if (g.epi == ME_QKV) {
+              EpiQkvDecode::chunk(g.qkv, acc, m, n0, g.N, nullptr, NoPre());
+            } else {
+              EpiStore::chunk(g.store, acc, m, n0, g.N, nullptr, NoPre());
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.tempty[ps.as]);
+      ps.as ^= 1;
+      if (ps.as == 0) ps.aphase ^= 1u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- E phase: residual + RMSNorm
+// x[row] = bf16(x[row] + bf16(sum_ks ws[ks][row]))   (modeling_t5.py:375,406,149; skipped when ksplit == 0)
+// xn[row] = T5LayerNorm(x[row]) * w                   (modeling_t5.py:55-68)
+// The phase is pure latency (256 rows x 1.5 KB): a row is spread over W = ceil(d/256) warps so
+// that every lane owns ONE 16-byte vector and all of its loads (x, the ksplit partials, w) are
+// issued back to back - one L2 round trip instead of ksplit * d/256 dependent ones.
+
+__device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* ws, int ksplit, const __nv_bfloat16* w, __nv_bfloat16* xn,
+                               int rows, int d, float eps, float* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = d >> 3;
+  int W = (nvec + 31) >> 5;          // warps per row
+  if (W > kMegaWarps) W = kMegaWarps;  // wider rows: lanes loop over vectors
+  const int groups = kMegaWarps / W;
+  const int grp = warp / W, wl = warp - grp * W;  // warps beyond groups*W idle
+  const int gl = wl * 32 + lane;                  // lane index inside the row group
+  float* red = scratch + grp * 16;                // per-group partial sums of squares
+  const bool active = grp < groups;
+  const int passes = (rows + gridDim.x * groups - 1) / (gridDim.x * groups);
+  for (int ps = 0; ps < passes; ++ps) {
+    const int row = (ps * gridDim.x + blockIdx.x) * groups + grp;
+    const bool row_ok = active && row < rows;
+    float ss = 0.f;
+    if (row_ok) {
+      for (int idx = gl; idx < nvec; idx += W * 32) {
+        uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * d) + idx;
+        const uint4 v = *xr;
+        uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+        if (ksplit > 0) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = 0.f;
+          for (int k0 = 0; k0 < ksplit; k0 += 4) {  // 4 partials (8 loads) in flight per batch
+            float4 pa[4], pb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k0 + u < ksplit) {
+                const float4* p4 = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(k0 + u) * rows + row) * d + idx * 8);
+                pa[u] = p4[0];
+                pb[u] = p4[1];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k0 + u < ksplit) {
+                y[0] += pa[u].x; y[1] += pa[u].y; y[2] += pa[u].z; y[3] += pa[u].w;
+                y[4] += pb[u].x; y[5] += pb[u].y; y[6] += pb[u].z; y[7] += pb[u].w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            xs[j] = pack_bf16x2(bf16_lo(xs[j]) + bf16_round(y[2 * j]), bf16_hi(xs[j]) + bf16_round(y[2 * j + 1]));
+          *xr = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(xs[j]), b = bf16_hi(xs[j]);
+          ss = fmaf(a, a, ss);
+          ss = fmaf(b, b, ss);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (active && lane == 0) red[wl] = ss;
+    __syncthreads();  // uniform: every thread of the CTA runs the same number of passes
+    if (row_ok) {
+      float tot = 0.f;
+      for (int i = 0; i < W; ++i) tot += red[i];  // fixed order
+      const float inv = rsqrtf(tot * (1.0f / static_cast<float>(d)) + eps);
+      for (int idx = gl; idx < nvec; idx += W * 32) {
+        const uint4 v = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d)[idx];
+        const uint4 wv = reinterpret_cast<const uint4*>(w)[idx];
+        const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t wsv[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_round(bf16_lo(xs[j]) * inv);
+          const float b = bf16_round(bf16_hi(xs[j]) * inv);
+          o[j] = pack_bf16x2(bf16_lo(wsv[j]) * a, bf16_hi(wsv[j]) * b);
+        }
+        reinterpret_cast<uint4*>(xn + static_cast<size_t>(row) * d)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();  // red[] is reused by the next pass
+  }
+}
+
+// ---------------------------------------------------------------- self-attention phase
+// One warp per (row, head); same arithmetic and rounding points as self_attn_decode_warp_kernel.
+__device__ __noinline__ void mega_self_attn_phase(const __nv_bfloat16* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc,
+                                 __nv_bfloat16* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
+                                 float* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sc = scratch + warp * Tk;
+  const int ks = lane >> 3, dg = lane & 7;
+  const int nkeys = t + 1;
+  constexpr int U = 4;
+  for (int bh = blockIdx.x * kMegaWarps + warp; bh < BH; bh += gridDim.x * kMegaWarps) {
+    const int h = bh % H;
+    const size_t slab = static_cast<size_t>(bh) * Tk * 64;
+    const __nv_bfloat16* Kp = Kc + slab + dg * 8;
+    const __nv_bfloat16* Vp = Vc + slab + dg * 8;
+    float qf[8];
+    {
+      const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
+      qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
+      qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+    }
+    for (int jb = 0; jb < nkeys; jb += 4 * U) {
+      uint4 kv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jb + ks + 4 * u;
+        kv[u] = j < nkeys ? *reinterpret_cast<const uint4*>(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jb + ks + 4 * u;
+        float s = dot8(kv[u], qf);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (dg == 0 && j < nkeys) sc[j] = bf16_round(bf16_round(s) + dist_bias[h * Tk + (t - j)]);
+      }
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < nkeys; j += 32) {
+      const float e = expf(sc[j] - mx);
+      sc[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int j = lane; j < nkeys; j += 32) sc[j] = bf16_round(sc[j] / sum);
+    __syncwarp();
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int jb = 0; jb < nkeys; jb += 4 * U) {
+      uint4 vv[U];
+      float p[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jb + ks + 4 * u;
+        const bool ok = j < nkeys;
+        vv[u] = ok ? *reinterpret_cast<const uint4*>(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+        p[u] = ok ? sc[j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[0] = fmaf(p[u], bf16_lo(vv[u].x), acc[0]);
+        acc[1] = fmaf(p[u], bf16_hi(vv[u].x), acc[1]);
+        acc[2] = fmaf(p[u], bf16_lo(vv[u].y), acc[2]);
+        acc[3] = fmaf(p[u], bf16_hi(vv[u].y), acc[3]);
+        acc[4] = fmaf(p[u], bf16_lo(vv[u].z), acc[4]);
+        acc[5] = fmaf(p[u], bf16_hi(vv[u].z), acc[5]);
+        acc[6] = fmaf(p[u], bf16_lo(vv[u].w), acc[6]);
+        acc[7] = fmaf(p[u], bf16_hi(vv[u].w), acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (ks == 0) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]);
+      o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]);
+      o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(bh) * 64 + dg * 8) = o;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- cross-attention phase
+// A group of 4 warps per (row, head), kMegaGroups groups per CTA; the arithmetic is
+// attn_decode_kernel<false>'s (exact two-pass softmax, K and V each streamed once).
+//
+// The phase is the HBM roofline of the step, and with one resident CTA per SM the bytes in
+// flight must come from depth, not from occupancy: every thread streams ITS OWN 16-byte pieces
+// (the same (key, segment) mapping it consumes) through a private ring of kXaDepth cp.async
+// slots in shared memory - kXaDepth * 384 * 16 B = 96 KB in flight per SM, no registers held,
+// no inter-thread synchronisation for the ring. The request stream runs ahead across the
+// K -> softmax -> V -> next (row, head) boundaries (V and the next item's K do not depend on the
+// scores), so the memory pipe never drains inside the phase.
+constexpr int kXaDepth = 16;
+static_assert(kXaDepth * kMegaThreads * 16 <= kMegaStages * kMegaStageBytes, "the request ring reuses the (idle) GEMM ring");
+
+DEVINL void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 4) : "memory"); }
+DEVINL void cp_async16_evict_first(uint32_t smem_dst, const void* gsrc, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
+}
+
+struct XaStream {  // per-thread request stream over this group's items: K pieces then V pieces of each item
+  int bh, e, n;    // current item, entry inside the item (0..2n), pieces per operand
+  const __nv_bfloat16 *Kp, *Vp;
+};
+
+DEVINL void xa_open_item(XaStream& st, int bh, int BH, int H, int Tk, const int* extent, const __nv_bfloat16* Kc,
+                         const __nv_bfloat16* Vc, int dg) {
+  st.bh = bh;
+  st.e = 0;
+  if (bh < BH) {
+    const int nkeys = extent[bh / H];
+    st.n = (nkeys + 15) >> 4;
+    const size_t slab = static_cast<size_t>(bh) * Tk * 64;
+    st.Kp = Kc + slab + dg * 8;
+    st.Vp = Vc + slab + dg * 8;
+  } else {
+    st.n = 0;
+  }
+}
+
+__device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc,
+                                  __nv_bfloat16* ctx, int BH, int H, int Tk, const int* extent,
+                                  const unsigned char* key_ok, float* scratch, uint8_t* ring) {
+  const int group = threadIdx.x >> 7;  // 0..kMegaGroups-1
+  const int gt = threadIdx.x & 127;
+  const int warp = gt >> 5, lane = gt & 31;
+  const int ks = lane >> 3, dg = lane & 7;
+  float* s_scores = scratch + group * (Tk + 4 * 64 + 8);
+  float* s_red = s_scores + Tk;    // [4][64]
+  float* s_stat = s_red + 4 * 64;  // [8]
+  const uint32_t my_ring = smem_u32(ring) + threadIdx.x * 16u;  // slot s of this thread: + s * kMegaThreads * 16
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const int stride = gridDim.x * kMegaGroups;
+  const int j_base = warp * 4 + ks;  // this thread's first key; its pieces are keys j_base + 16 u
+
+  // request stream: issue one piece (or an empty group) per call
+  XaStream rq;
+  xa_open_item(rq, blockIdx.x * kMegaGroups + group, BH, H, Tk, extent, Kc, Vc, dg);
+  unsigned int seq_issue = 0;
+  auto issue_one = [&]() {
+    while (rq.bh < BH && rq.e >= 2 * rq.n) xa_open_item(rq, rq.bh + stride, BH, H, Tk, extent, Kc, Vc, dg);
+    if (rq.bh < BH) {
+      const bool isv = rq.e >= rq.n;
+      const int u = isv ? rq.e - rq.n : rq.e;
+      const int j = j_base + 16 * u;
+      const int nkeys = extent[rq.bh / H];
+      if (j < nkeys)
+        cp_async16_evict_first(my_ring + (seq_issue % kXaDepth) * (kMegaThreads * 16u),
+                               (isv ? rq.Vp : rq.Kp) + static_cast<size_t>(j) * 64, policy);
+      ++rq.e;
+    }
+    cp_async_commit();
+    ++seq_issue;
+  };
+#pragma unroll 1
+  for (int i = 0; i < kXaDepth; ++i) issue_one();
+
+  unsigned int seq_use = 0;
+  for (int bh = blockIdx.x * kMegaGroups + group; bh < BH; bh += stride) {
+    const int b = bh / H;
+    const int nkeys = extent[b];
+    const int n = (nkeys + 15) >> 4;
+    float qf[8];
+    {
+      const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
+      qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
+      qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+    }
+    // ---- scores
+    for (int u = 0; u < n; ++u) {
+      cp_async_wait<kXaDepth - 1>();
+      const int j = j_base + 16 * u;
+      uint4 kv = make_uint4(0, 0, 0, 0);
+      if (j < nkeys) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kv.x), "=r"(kv.y), "=r"(kv.z), "=r"(kv.w) : "r"(my_ring + (seq_use % kXaDepth) * (kMegaThreads * 16u)));
+      ++seq_use;
+      issue_one();  // refill the slot just consumed (same thread: program order suffices)
+      float sc = dot8(kv, qf);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (dg == 0 && j < nkeys) {
+        sc = bf16_round(sc);
+        if (!key_ok[static_cast<size_t>(b) * Tk + j]) sc = kBf16Min;
+        s_scores[j] = sc;
+      }
+    }
+    group_sync(group);
+    float mx = -INFINITY;
+    for (int j = gt; j < nkeys; j += 128) mx = fmaxf(mx, s_scores[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_stat[warp] = mx;
+    group_sync(group);
+    mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
+    float sum = 0.f;
+    for (int j = gt; j < nkeys; j += 128) {
+      const float e = expf(s_scores[j] - mx);
+      s_scores[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_stat[4 + warp] = sum;
+    group_sync(group);
+    sum = (s_stat[4] + s_stat[5]) + (s_stat[6] + s_stat[7]);
+    for (int j = gt; j < nkeys; j += 128) s_scores[j] = bf16_round(s_scores[j] / sum);
+    group_sync(group);
+    // ---- out = P . V
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int u = 0; u < n; ++u) {
+      cp_async_wait<kXaDepth - 1>();
+      const int j = j_base + 16 * u;
+      uint4 vv = make_uint4(0, 0, 0, 0);
+      float pj = 0.f;
+      if (j < nkeys) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w) : "r"(my_ring + (seq_use % kXaDepth) * (kMegaThreads * 16u)));
+        pj = s_scores[j];
+      }
+      ++seq_use;
+      issue_one();
+      acc[0] = fmaf(pj, bf16_lo(vv.x), acc[0]);
+      acc[1] = fmaf(pj, bf16_hi(vv.x), acc[1]);
+      acc[2] = fmaf(pj, bf16_lo(vv.y), acc[2]);
+      acc[3] = fmaf(pj, bf16_hi(vv.y), acc[3]);
+      acc[4] = fmaf(pj, bf16_lo(vv.z), acc[4]);
+      acc[5] = fmaf(pj, bf16_hi(vv.z), acc[5]);
+      acc[6] = fmaf(pj, bf16_lo(vv.w), acc[6]);
+      acc[7] = fmaf(pj, bf16_hi(vv.w), acc[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (ks == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_red[warp * 64 + dg * 8 + e] = acc[e];
+    }
+    group_sync(group);
+    if (gt < 32) {
+      const int d0 = gt * 2;
+      const float o0 = (s_red[d0] + s_red[64 + d0]) + (s_red[128 + d0] + s_red[192 + d0]);
+      const float o1 = (s_red[d0 + 1] + s_red[64 + d0 + 1]) + (s_red[128 + d0 + 1] + s_red[192 + d0 + 1]);
+      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(bh) * 64 + d0) = pack_bf16x2(o0, o1);
+    }
+    group_sync(group);  // s_scores / s_red are reused by the next item
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------- greedy bookkeeping phase
+// One warp per row: reduce the per-tile arg-max partials (lowest index wins ties), apply HF's
+// pad/EOS logic (generation/utils.py:2793-2805), gather the next token's embedding into x and
+// apply the first RMSNorm of the next step.
+__device__ __noinline__ void mega_finalize_phase(const MegaParams& P, int t) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d, nvec = d >> 3;
+  for (int b = blockIdx.x * kMegaWarps + warp; b < P.B; b += gridDim.x * kMegaWarps) {
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int i = lane; i < P.n_vtiles; i += 32) {
+      const float v = P.pval[static_cast<size_t>(b) * P.n_vtiles + i];
+      const int ix = P.pidx[static_cast<size_t>(b) * P.n_vtiles + i];
+      if (v > best || (v == best && ix < bidx)) {
+        best = v;
+        bidx = ix;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) {
+        best = ov;
+        bidx = oi;
+      }
+    }
+    long long tok = 0;
+    if (lane == 0) {
+      const int unf = P.unfinished[b];
+      tok = unf ? static_cast<long long>(bidx) : P.pad;
+      P.out_ids[static_cast<size_t>(b) * (P.T + 1) + t + 1] = tok;
+      if (unf) {
+        P.out_len[b] = t + 1;
+        if (tok == P.eos) {
+          P.unfinished[b] = 0;
+          atomicAdd(&P.st->finished_rows, 1);
+        }
+      }
+    }
+    tok = __shfl_sync(0xffffffffu, tok, 0);
+    const uint4* src = reinterpret_cast<const uint4*>(P.E + static_cast<size_t>(tok) * d);
+    uint4* dst = reinterpret_cast<uint4*>(P.dx + static_cast<size_t>(b) * d);
+    for (int i = lane; i < nvec; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
+}
+
+// ================================================================== the kernel
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __grid_constant__ MegaParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  MegaShared sh;
+  sh.ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMegaStages * kMegaStageBytes);
+  sh.full = bars;
+  sh.empty = bars + kMegaStages;
+  sh.tfull = bars + 2 * kMegaStages;
+  sh.tempty = sh.tfull + 2;
+  sh.tmem_slot = reinterpret_cast<uint32_t*>(sh.tempty + 2);
+  sh.s_step = reinterpret_cast<int*>(sh.tmem_slot + 1);
+  sh.scratch = smem + kMegaStages * kMegaStageBytes + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kMegaStages; ++i) {
+        mbar_init(&sh.full[i], 1);
+        mbar_init(&sh.empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sh.tfull[i], 1);
+        mbar_init(&sh.tempty[i], 4);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc<2 * kMegaAccCols>(sh.tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *sh.tmem_slot;
+
+  MegaPipe ps;
+  unsigned int bar_target = 0;
+  int prof_n = 0;
+  int prof_t = -1;
+#define GSYNC()                                                                                  \
+  do {                                                                                           \
+    const bool _pr = P.prof != nullptr && prof_t == P.prof_step && blockIdx.x == 0 && threadIdx.x == 0; \
+    if (_pr) P.prof[prof_n++] = clock64();                                                       \
+    grid_sync(P.bar, bar_target);                                                                \
+    if (_pr) P.prof[prof_n++] = clock64();                                                       \
+  } while (0)
+  const int B = P.B, d = P.d, I = P.I, F = P.F, H = P.H;
+  float* fscratch = reinterpret_cast<float*>(sh.scratch);
+
+  // first RMSNorm of the first step (x = embedding of decoder_start, set by decode_init_kernel)
+  mega_resnorm_phase(P.dx, nullptr, 0, P.layers[0].ln0, P.dxn, B, d, P.eps, fscratch);
+  GSYNC();
+
+  for (int t = 0; t < P.nsteps; ++t) {
+    if (threadIdx.x == 0) *sh.s_step = t;
+    prof_t = t;
+    __syncthreads();
+    for (int l = 0; l < P.Ld; ++l) {
+      const MegaLayer& L = P.layers[l];
+      const size_t self_plane = static_cast<size_t>(B) * I * P.T;
+      const size_t cross_plane = static_cast<size_t>(B) * I * P.S;
+      // ---- self-attention block
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dxn; g.tmB = L.tm_qkv; g.M = B; g.N = 3 * I; g.K = d; g.bn = P.bn_qkv; g.ksplit = 1; g.epi = ME_QKV;
+        g.qkv = EpiQkvDecode::Params{P.dq, L.self_kv, sh.s_step, B, H, P.T};
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      mega_self_attn_phase(P.dq, L.self_kv, L.self_kv + self_plane, P.dctx, B * H, H, P.T, t, P.dec_bias, fscratch);
+      GSYNC();
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dctx; g.tmB = L.tm_o; g.M = B; g.N = d; g.K = I; g.bn = P.bn_proj; g.ksplit = P.ks_proj; g.epi = ME_PARTIAL;
+        g.ws = P.ws; g.ws_ld = d;
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      mega_resnorm_phase(P.dx, P.ws, P.ks_proj, L.ln1, P.dxn, B, d, P.eps, fscratch);
+      GSYNC();
+      // ---- cross-attention block
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dxn; g.tmB = L.tm_cq; g.M = B; g.N = I; g.K = d; g.bn = P.bn_cq; g.ksplit = 1; g.epi = ME_STORE;
+        g.store = EpiStore::Params{P.dq, I};
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      mega_cross_attn_phase(P.dq, L.cross_kv, L.cross_kv + cross_plane, P.dctx, B * H, H, P.S, P.extent, P.key_ok, fscratch, sh.ring);
+      GSYNC();
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dctx; g.tmB = L.tm_co; g.M = B; g.N = d; g.K = I; g.bn = P.bn_proj; g.ksplit = P.ks_proj; g.epi = ME_PARTIAL;
+        g.ws = P.ws; g.ws_ld = d;
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      mega_resnorm_phase(P.dx, P.ws, P.ks_proj, L.ln2, P.dxn, B, d, P.eps, fscratch);
+      GSYNC();
+      // ---- feed-forward block
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dxn; g.tmB = L.tm_wi; g.M = B; g.N = L.wi_rows; g.K = d; g.bn = P.bn_wi; g.ksplit = 1; g.epi = ME_GEGLU;
+        g.geglu = EpiGeglu::Params{P.dh, F, P.lut};
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      {
+        MegaGemm g;
+        g.tmA = P.tm_dh; g.tmB = L.tm_ffo; g.M = B; g.N = d; g.K = F; g.bn = P.bn_ffo; g.ksplit = P.ks_ffo; g.epi = ME_PARTIAL;
+        g.ws = P.ws; g.ws_ld = d;
+        mega_gemm_phase(sh, ps, tmem_base, g);
+      }
+      GSYNC();
+      mega_resnorm_phase(P.dx, P.ws, P.ks_ffo, l + 1 < P.Ld ? P.layers[l + 1].ln0 : P.final_ln, P.dxn, B, d, P.eps, fscratch);
+      GSYNC();
+    }
+    // ---- lm_head + arg-max, then the greedy bookkeeping
+    {
+      MegaGemm g;
+      g.tmA = P.tm_dxn; g.tmB = P.tm_lm; g.M = B; g.N = P.V; g.K = d; g.bn = P.bn_lm; g.ksplit = 1; g.epi = ME_ARGMAX;
+      g.amax = EpiArgmax::Params{P.pval, P.pidx, P.n_vtiles, sh.s_step, static_cast<int>(P.eos), P.min_new};
+      mega_gemm_phase(sh, ps, tmem_base, g);
+    }
+    GSYNC();
+    mega_finalize_phase(P, t);
+    GSYNC();
+    // every row has emitted EOS: the remaining steps would only append pad tokens (already there)
+    const int finished = *reinterpret_cast<volatile int*>(&P.st->finished_rows);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.st->step = t + 1;
+    if (finished >= B) break;
+    mega_resnorm_phase(P.dx, nullptr, 0, P.layers[0].ln0, P.dxn, B, d, P.eps, fscratch);
+    GSYNC();
+  }
+
+#undef GSYNC
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<2 * kMegaAccCols>(tmem_base);
+  }
+}
+
+}  // namespace b200

@@ -279,3 +279,29 @@ def test_batch_predictor_pool_two_gpus():
     one = bp.predict(ds, batch_size=4, num_gpus_per_worker=1, max_scoring_workers=1, max_new_tokens=8).to_pandas()
     two = bp.predict(ds, batch_size=4, num_gpus_per_worker=1, max_new_tokens=8).to_pandas()
     assert one["generated_output"].tolist() == two["generated_output"].tolist()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_persistent_decode_kernel_matches_goldens(case, tmp_path, monkeypatch):
+    """The opt-in persistent decode kernel (csrc/decode_mega.cuh, B200T5_MEGA=1) against the same anchors as the
+    step-graph path: HF bf16 goldens and the oracle (margin-gated), natural EOS and forced length, and
+    run-to-run determinism (its split-K partial sums are added in a fixed order)."""
+    from anyscale_workshop_nyc_2023_b200.modeling import B200T5ForConditionalGeneration
+
+    spec_name, seed, T = CASES[case]
+    monkeypatch.setenv("B200T5_MEGA", "1")  # read when the handle is created
+    save_checkpoint(tmp_path, SPECS[spec_name], seed=seed)
+    model = B200T5ForConditionalGeneration.from_pretrained(tmp_path, device_map="auto", torch_dtype=torch.bfloat16)
+    g = np.load(GOLD / f"{case}.npz")
+    ids, mask = torch.from_numpy(g["ids"]), torch.from_numpy(g["mask"])
+    out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=T).cpu().numpy()
+    assert model.stats()["kernel_launches"] < 200, "the persistent kernel did not run (step graph fallback?)"
+    otoks, margins = oracle_for(spec_name, seed).generate(g["ids"], g["mask"], max_new_tokens=T, return_margins=True)
+    gated_o, full_o = gated_prefix_match(out, otoks, margins)
+    gated_h, full_h = gated_prefix_match(out, g["tokens_bf16"], margins)
+    print(f"{case} [persistent]: vs oracle gated={gated_o:.2f} full={full_o:.2f} | vs HF-bf16 golden gated={gated_h:.2f} full={full_h:.2f}")
+    assert gated_o == 1.0 and gated_h == 1.0
+    again = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=T).cpu().numpy()
+    assert np.array_equal(out, again)
+    forced = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=T, min_new_tokens=T).cpu().numpy()
+    assert forced.shape[1] == T + 1 and (forced[:, 1:] != 1).all()
