@@ -19,7 +19,8 @@ namespace b200 {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;      // 2 control warps + 4 epilogue warps
+constexpr int kGemmThreadsWide = 320;  // 2 control warps + 8 epilogue warps (big tiles: the epilogue is the bottleneck)
 constexpr int kEpiSmemBytes = 8192;  // per-CTA scratch the epilogue functor may stage tables in
 
 template <int BN>
@@ -51,8 +52,19 @@ DEVINL TileCoord tile_coord(int tile, int tiles_m, int tiles_n, int m_fastest) {
   return c;
 }
 
+// Epilogue warps: a warp may only touch the TMEM lane quarter 32*(warp%4), so 4 warps cover a tile's
+// 128 rows; the big tiles (BN = 256) run 8 epilogue warps - two per lane quarter, each taking half of
+// the tile's 32-column chunks - because with 4 the epilogue (not the MMA) bounds the kernel: measured
+// on B200, tensor pipe active 27 % for the GeGLU tile and 34 % for the K = 768 residual tile
+// (profiles/encoder_ncu_r1.md).
+template <int BN>
+struct EpiWarps {
+  static constexpr int kCount = BN >= 256 ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kCount;
+};
+
 template <int BN, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, (BN <= 64 ? 2 : 1))
+__global__ void __launch_bounds__(EpiWarps<BN>::kThreads, (BN <= 64 ? 2 : 1))
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, int m_fastest, typename Epi::Params ep) {
   using Cfg = GemmCfg<BN>;
@@ -86,7 +98,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], EpiWarps<BN>::kCount);
       }
       mbar_fence_init();
     }
@@ -166,9 +178,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
+    constexpr int kParts = EpiWarps<BN>::kCount / 4;  // column parts of a tile row
+    const int part = (warp - 2) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64);  // constant tables; overlaps the main loop
+    Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64, 32 * EpiWarps<BN>::kCount);  // constant tables; overlaps the main loop
     pdl_wait();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(tile, tiles_m, tiles_n, m_fastest);
@@ -176,7 +190,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem);
+      Epi::template run<BN>(ep, taddr, m, m < M, tc.n_tile, N, epi_smem, part, kParts);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -217,20 +231,23 @@ struct NoPre {};
 
 // Drives an unpaired functor over the BN columns of this thread's TMEM row, fetching the
 // pre-operands of chunk c+1 before chunk c is processed.
+// `part` of `parts`: the epilogue warp handles chunks [part*C/parts, (part+1)*C/parts) of the C = BN/32 chunks.
 template <int BN, class Epi>
 DEVINL void run_chunks_from_tmem(const typename Epi::Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N,
-                                 const uint8_t* epi_smem) {
+                                 const uint8_t* epi_smem, int part, int parts) {
+  constexpr int C = BN / 32;
+  const int c_lo = part * C / parts, c_hi = (part + 1) * C / parts;
   typename Epi::ChunkPre pre[2];
-  if (m_ok) Epi::chunk_pre(p, m, n_tile * BN, N, pre[0]);
+  if (m_ok && n_tile * BN + c_lo * 32 < N) Epi::chunk_pre(p, m, n_tile * BN + c_lo * 32, N, pre[0]);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; c += 2) {
+  for (int c = c_lo; c < c_hi; c += 2) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      if (c + u < BN / 32) {
+      if (c + u < c_hi) {
         uint32_t acc[32];
         tmem_ld_32x32(taddr + (c + u) * 32, acc);
         const int n0 = n_tile * BN + (c + u) * 32;
-        if (m_ok && c + u + 1 < BN / 32 && n0 + 32 < N) Epi::chunk_pre(p, m, n0 + 32, N, pre[(u + 1) & 1]);
+        if (m_ok && c + u + 1 < c_hi && n0 + 32 < N) Epi::chunk_pre(p, m, n0 + 32, N, pre[(u + 1) & 1]);
         tmem_ld_wait();
         if (m_ok && n0 < N) Epi::chunk(p, acc, m, n0, N, epi_smem, pre[u & 1]);
       }
@@ -246,7 +263,7 @@ struct EpiStore {
   };
   static constexpr bool kPaired = false;
   typedef NoPre ChunkPre;
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
   static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
                            const ChunkPre&) {
@@ -255,8 +272,9 @@ struct EpiStore {
     store_row_chunk(p.C + static_cast<size_t>(m) * p.ldc + n0, o, n0, N);
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
-    run_chunks_from_tmem<BN, EpiStore>(p, taddr, m, m_ok, n_tile, N, es);
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,
+                         int part, int parts) {
+    run_chunks_from_tmem<BN, EpiStore>(p, taddr, m, m_ok, n_tile, N, es, part, parts);
   }
 };
 
@@ -271,7 +289,7 @@ struct EpiResidual {
   struct ChunkPre {
     uint4 r[4];
   };
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   // The residual operand does not depend on the accumulator: it is fetched while the main loop /
   // the previous chunk is still in flight.
   static DEVINL void chunk_pre(const Params& p, int m, int n0, int N, ChunkPre& pre) {
@@ -295,8 +313,9 @@ struct EpiResidual {
     store_row_chunk(p.C + static_cast<size_t>(m) * p.ld + n0, o, n0, N);
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
-    run_chunks_from_tmem<BN, EpiResidual>(p, taddr, m, m_ok, n_tile, N, es);
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,
+                         int part, int parts) {
+    run_chunks_from_tmem<BN, EpiResidual>(p, taddr, m, m_ok, n_tile, N, es, part, parts);
   }
 };
 
@@ -324,6 +343,21 @@ struct GeluLut {
   const uint16_t* table;  // device: [2][hi - lo] bf16 bits, sign-major
   int lo, hi;             // magnitude bit patterns (bf16 bits & 0x7fff)
 };
+
+// Same function without divergent branches (the GEMM epilogue evaluates it 128 times per thread and tile):
+// the three cases are computed side by side and selected.
+DEVINL float gelu_from_lut_sel(float x, const uint16_t* lut, int lo, int n /* = hi - lo */) {
+  const uint32_t bits = __float_as_uint(x) >> 16;
+  const int mag = static_cast<int>(bits & 0x7FFFu);
+  const bool neg = (bits >> 15) != 0;
+  const int rel = mag - lo;
+  const int idx = min(max(rel, 0), n - 1) + (neg ? n : 0);
+  const float tab = __uint_as_float(static_cast<uint32_t>(lut[idx]) << 16);
+  const float half = bf16_round(0.5f * x);
+  float sat = neg ? (mag == 0x7F80 ? __int_as_float(0x7FC00000) : -0.0f) : x;
+  sat = mag > 0x7F80 ? x : sat;
+  return rel < 0 ? half : (rel >= n ? sat : tab);
+}
 
 DEVINL float gelu_from_lut(float x, const uint16_t* lut, int lo, int hi) {
   const uint32_t bits = __float_as_uint(x) >> 16;
@@ -362,7 +396,7 @@ struct EpiGeglu {
   static DEVINL void chunk2(const Params& p, const uint32_t (&g)[32], const uint32_t (&u)[32], int m, int f0,
                             const uint8_t* epi_smem) {
     const uint16_t* lut = reinterpret_cast<const uint16_t*>(epi_smem);
-    const int lo = p.lut.lo, hi = p.lut.hi;
+    const int lo = p.lut.lo, n = p.lut.hi - p.lut.lo;
     uint32_t o[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -371,17 +405,19 @@ struct EpiGeglu {
       for (int e = 0; e < 2; ++e) {
         const float x = bf16_round(__uint_as_float(g[2 * i + e]));
         const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
-        r[e] = gelu_from_lut(x, lut, lo, hi) * lin;
+        r[e] = (n > 0 ? gelu_from_lut_sel(x, lut, lo, n) : gelu_from_lut(x, lut, lo, p.lut.hi)) * lin;
       }
       o[i] = pack_bf16x2(r[0], r[1]);
     }
     store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem,
+                         int part, int parts) {
     constexpr int HALF = BN / 2;
+    constexpr int C = HALF / 32;
 #pragma unroll 1
-    for (int c = 0; c < HALF / 32; ++c) {
+    for (int c = part * C / parts; c < (part + 1) * C / parts; ++c) {
       uint32_t g[32], u[32];
       tmem_ld_32x32(taddr + c * 32, g);
       tmem_ld_32x32(taddr + HALF + c * 32, u);
@@ -402,7 +438,7 @@ struct EpiCrossKV {
   };
   static constexpr bool kPaired = false;
   typedef NoPre ChunkPre;
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
   static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
                            const ChunkPre&) {
@@ -417,8 +453,9 @@ struct EpiCrossKV {
     store_row_chunk(dst, o, n0, N);
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
-    run_chunks_from_tmem<BN, EpiCrossKV>(p, taddr, m, m_ok, n_tile, N, es);
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,
+                         int part, int parts) {
+    run_chunks_from_tmem<BN, EpiCrossKV>(p, taddr, m, m_ok, n_tile, N, es, part, parts);
   }
 };
 
@@ -434,7 +471,7 @@ struct EpiQkvDecode {
   };
   static constexpr bool kPaired = false;
   typedef NoPre ChunkPre;
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
   static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
                            const ChunkPre&) {
@@ -455,8 +492,9 @@ struct EpiQkvDecode {
     store_row_chunk(dst, o, n0, N);
   }
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es) {
-    run_chunks_from_tmem<BN, EpiQkvDecode>(p, taddr, m, m_ok, n_tile, N, es);
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,
+                         int part, int parts) {
+    run_chunks_from_tmem<BN, EpiQkvDecode>(p, taddr, m, m_ok, n_tile, N, es, part, parts);
   }
 };
 
@@ -472,9 +510,9 @@ struct EpiArgmax {
     const int* step;
     int eos, min_new;
   };
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*, int, int) {
     float best = -INFINITY;
     int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
     const bool block_eos = *p.step < p.min_new;
@@ -508,9 +546,9 @@ struct EpiStoreF32 {
     float* C;
     int ldc;
   };
-  static DEVINL void prologue(const Params&, uint8_t*, int) {}
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   template <int BN>
-  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*) {
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*, int, int) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];
@@ -576,8 +614,8 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   using Cfg = GemmCfg<BN>;
   const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  return launch_kernel(gemm_bf16_tn_kernel<BN, Epi>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, pdl, tmA,
-                       tmB, M, N, K, m_fastest, ep);
+  return launch_kernel(gemm_bf16_tn_kernel<BN, Epi>, dim3(grid), dim3(EpiWarps<BN>::kThreads), Cfg::kSmemBytes, stream, pdl,
+                       tmA, tmB, M, N, K, m_fastest, ep);
 }
 
 }  // namespace b200
