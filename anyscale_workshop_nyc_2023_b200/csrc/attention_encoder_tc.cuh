@@ -51,8 +51,11 @@ struct EncTcSmem {
   static constexpr int kV = kK + 65536;          // 4 x 16 KB
   static constexpr int kBars = kV + 65536;       // mbarriers + tmem slot + stats
   static constexpr int kStat = kBars + 128;      // float[2][parts][128]: max, sum per column part
-  static constexpr int kBias = kStat + 2 * kEncTcParts * 128 * 4;  // float[S + 128]
-  static size_t bytes(int S) { return static_cast<size_t>(kBias) + (S + 128) * 4 + S + 16 + 1024; }
+  // two packed bf16x2 bias tables, T0[k] = (bias[2k], bias[2k+1]) and T1[k] = (bias[2k+1], bias[2k+2]),
+  // (S + 128) / 2 + 16 words each (the +16 staggers T1 by half the banks)
+  static constexpr int kBias = kStat + 2 * kEncTcParts * 128 * 4;
+  __host__ __device__ static int table_words(int S) { return (S + 128) / 2 + 16; }
+  static size_t bytes(int S) { return static_cast<size_t>(kBias) + 2 * table_words(S) * 4 + S + 16 + 1024; }
 };
 
 __global__ void __launch_bounds__(kEncTcThreads, 1)
@@ -75,8 +78,9 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
   uint64_t* bar_o = bars + 6;      // all P.V complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* sStat = reinterpret_cast<float*>(smem + EncTcSmem::kStat);
-  float* sBias = reinterpret_cast<float*>(smem + EncTcSmem::kBias);
-  unsigned char* sOk = reinterpret_cast<unsigned char*>(sBias + S + 128);
+  uint32_t* sT0 = reinterpret_cast<uint32_t*>(smem + EncTcSmem::kBias);
+  uint32_t* sT1 = sT0 + EncTcSmem::table_words(S);
+  unsigned char* sOk = reinterpret_cast<unsigned char*>(sT1 + EncTcSmem::table_words(S));
   int* sHoles = reinterpret_cast<int*>(bars + 10);
   if (threadIdx.x == 0) *sHoles = 0;
   __syncthreads();
@@ -109,9 +113,15 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     // bias slice for this query tile: x = j - i_local + 127  <->  rel index j - i + S - 1
     const int t = threadIdx.x - 32;
     const int lo = S - 1 - i0 - 127;
-    for (int x = t; x < S + 127; x += kEncTcCompute) {
+    // the bias values are bf16 embedding entries widened to fp32: packing them back is lossless
+    auto bias_at = [&](int x) -> float {
       const int idx = lo + x;
-      sBias[x] = (idx >= 0 && idx < 2 * S - 1) ? rel_bias[static_cast<size_t>(h) * (2 * S - 1) + idx] : 0.f;
+      return (x < S + 127 && idx >= 0 && idx < 2 * S - 1) ? rel_bias[static_cast<size_t>(h) * (2 * S - 1) + idx] : 0.f;
+    };
+    for (int k = t; k < (S + 128) / 2; k += kEncTcCompute) {
+      const float b0 = bias_at(2 * k), b1 = bias_at(2 * k + 1), b2 = bias_at(2 * k + 2);
+      sT0[k] = pack_bf16x2(b0, b1);
+      sT1[k] = pack_bf16x2(b1, b2);
     }
     int holes = 0;
     for (int x = t; x < S; x += kEncTcCompute) {
@@ -175,49 +185,79 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     mbar_wait(bar_s, 0);
     tc_fence_after_sync();
 
-    // ---- pass A: rounded + biased + masked scores written back in place; row max
+    // ---- pass A: s = bf16(bf16(acc) + bias) (+ mask), two keys per instruction: the fp32 accumulators are
+    // packed to bf16x2 (one F2FP), the bias pair comes from the packed table, add.rn.bf16x2 rounds
+    // exactly like bf16(float(a) + float(b)) (the fp32 sum of two bf16 values is exact whenever it can
+    // affect the bf16 rounding), max.bf16x2 keeps the running row max. The packed scores are written
+    // back over the first 16 columns of the 32-column block they came from.
     const bool holes = *sHoles != 0;
-    float mx = -INFINITY;
+    const uint32_t* tab = ((127 - il) & 1) ? sT1 : sT0;
+    __nv_bfloat162 mx2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       const int jb = c * kEncTcChunk + part * 32;
       uint32_t v[32];
       tmem_ld_32x32(trow + jb, v);
+      const int k0 = (jb - il + 127) >> 1;
+      uint32_t pk[16];
       tmem_ld_wait();
+      if (jb + 32 <= ext && !holes) {
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const int j = jb + t;
-        float s = bf16_round(__uint_as_float(v[t]));
-        if (j < ext) {
-          s = bf16_round(s + sBias[j - il + 127]);
-          if (holes && !sOk[j]) s = kBf16Min;
-        } else {
-          s = -INFINITY;
+        for (int t = 0; t < 16; ++t) {
+          const uint32_t sb = pack_bf16x2(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1]));
+          const uint32_t bb = tab[k0 + t];
+          const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&sb), *reinterpret_cast<const __nv_bfloat162*>(&bb));
+          mx2 = __hmax2(mx2, r);
+          pk[t] = *reinterpret_cast<const uint32_t*>(&r);
         }
-        mx = fmaxf(mx, s);
-        v[t] = __float_as_uint(s);
+      } else {  // the chunk that contains the end of the row / a non-prefix mask: element by element
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          float r2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = jb + 2 * t + e;
+            float sc = bf16_round(__uint_as_float(v[2 * t + e]));
+            if (j < ext) {
+              const uint32_t bb = tab[k0 + t];
+              sc = bf16_round(sc + (e ? bf16_hi(bb) : bf16_lo(bb)));
+              if (holes && !sOk[j]) sc = kBf16Min;
+            } else {
+              sc = -INFINITY;
+            }
+            r2[e] = sc;
+          }
+          const __nv_bfloat162 r = __floats2bfloat162_rn(r2[0], r2[1]);  // exact: both are bf16 values
+          mx2 = __hmax2(mx2, r);
+          pk[t] = *reinterpret_cast<const uint32_t*>(&r);
+        }
       }
-      tmem_st_32x32(trow + jb, v);
+      tmem_st_32x16(trow + jb, pk);
     }
     tmem_st_wait();
+    float mx = fmaxf(__low2float(mx2), __high2float(mx2));
     sStat[part * 128 + il] = mx;
     named_bar_sync(1, kEncTcCompute);
 #pragma unroll
     for (int k = 0; k < P; ++k) mx = fmaxf(mx, sStat[k * 128 + il]);
 
-    // ---- pass B: e = exp(s - max) kept in place; row sum
+    // ---- pass B: e = exp(s - max) kept in place as fp32; row sum
     float sum = 0.f;
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       const int jb = c * kEncTcChunk + part * 32;
-      uint32_t v[32];
-      tmem_ld_32x32(trow + jb, v);
+      uint32_t pk[16];
+      tmem_ld_32x16(trow + jb, pk);
       tmem_ld_wait();
+      uint32_t v[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float e = expf(__uint_as_float(v[t]) - mx);
-        sum += e;
-        v[t] = __float_as_uint(e);
+      for (int t = 0; t < 16; ++t) {
+        const float e0 = expf(bf16_lo(pk[t]) - mx);
+        const float e1 = expf(bf16_hi(pk[t]) - mx);
+        sum += e0;
+        sum += e1;
+        v[2 * t] = __float_as_uint(e0);
+        v[2 * t + 1] = __float_as_uint(e1);
       }
       tmem_st_32x32(trow + jb, v);  // pass C only has to normalise
     }
