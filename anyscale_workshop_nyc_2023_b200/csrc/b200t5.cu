@@ -258,6 +258,8 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
+                           // (measured: decode 201.5 -> 188.3 ms per batch); B200T5_SELF=warp selects one warp per (row, head)
   int small_prio = 0;  // B200T5_PRIO: launch priority of the latency-bound decode kernels (see launch_priority())
   bool sk_on = true;
   SkChoice sk_qkv{64, 2}, sk_proj{64, 4}, sk_wi{128, 2}, sk_ffo{64, 4};  // best of the B200 sweep (tools/sweep_decode.sh)
@@ -472,6 +474,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
   if (const char* mg_env = getenv("B200T5_MEGA")) {
     int v[7];
     const int n = sscanf(mg_env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
@@ -776,7 +779,7 @@ static int build_mega(b200t5_ctx* h, Plan& pl) {
   const int B = pl.B, S = pl.S, T = pl.Tmax, d = c.d, I = c.I, F = c.F;
   // shared-memory scratch of the attention phases
   if (static_cast<size_t>(kMegaWarps) * T * 4 > kMegaScratchBytes ||
-      static_cast<size_t>(kMegaGroups) * (S + 4 * 64 + 8) * 4 > kMegaScratchBytes)
+      static_cast<size_t>(kMegaGroups) * (S + 4 * 64 + 8) * 4 > kMegaScratchBytes || d > kMegaWarps * 256)
     return B200T5_OK;  // too long for the resident kernel: the step graph handles it
   int occ = 0;
   CU_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_mega_kernel, kMegaThreads, kMegaSmemBytes));
@@ -1060,9 +1063,13 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
     if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
-  CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
-                         dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
-                         skv + static_cast<size_t>(B) * I * T, v.dctx, v.nb * H, H, T, step, p.dec_bias.as<float>()));
+  if (h->self_block)  // 4 warps per (row, head): two memory round trips whatever t is
+    CU_OK(h, launch_kernel(attn_decode_kernel<true>, dim3(v.nb * H), dim3(kAttnDecThreads), T * sizeof(float), s, pdl, v.dq, skv,
+                           skv + static_cast<size_t>(B) * I * T, v.dctx, H, T, nullptr, nullptr, step, p.dec_bias.as<float>()));
+  else
+    CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
+                           dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
+                           skv + static_cast<size_t>(B) * I * T, v.dctx, v.nb * H, H, T, step, p.dec_bias.as<float>()));
   h->launches++;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};

@@ -34,15 +34,20 @@
 
 namespace b200 {
 
-constexpr int kMegaThreads = 384;
-constexpr int kMegaWarps = kMegaThreads / 32;
-constexpr int kMegaStages = 4;
+constexpr int kMegaWarps = 12;                       // compute warps (attention, norms, GEMM MMA + epilogue roles)
+constexpr int kMegaThreads = kMegaWarps * 32 + 32;   // + one control warp: TMA / bulk-copy producer and grid-barrier master
+constexpr int kMegaMaster = kMegaWarps * 32;         // thread index of the control warp's lane 0
+constexpr int kMegaStages = 3;
 constexpr int kMegaBnMax = 128;
 constexpr int kMegaStageBytes = kBM * kBK * 2 + kMegaBnMax * kBK * 2;  // 32 KB
 constexpr int kMegaAccCols = 128;                                      // two accumulators -> 256 TMEM columns
 constexpr int kMegaGroups = 3;                                         // cross-attention: 4-warp groups per CTA
-constexpr int kMegaScratchBytes = 48 * 1024;                           // scores / gelu table (phases are disjoint)
-constexpr int kMegaSmemBytes = kMegaStages * kMegaStageBytes + 1024 /*align*/ + 512 /*barriers*/ + kMegaScratchBytes;
+constexpr int kXaSlots = 4;                                            // bulk-copy chunks in flight per group
+constexpr int kXaChunkKeys = 64;
+constexpr int kXaChunkBytes = kXaChunkKeys * 128;                      // 8 KB: 64 keys x 64 bf16
+constexpr int kMegaXaRingBytes = kMegaGroups * kXaSlots * kXaChunkBytes;  // 96 KB
+constexpr int kMegaScratchBytes = 24 * 1024;                           // scores / gelu table / norm partials (phases are disjoint)
+constexpr int kMegaSmemBytes = kMegaStages * kMegaStageBytes + kMegaXaRingBytes + 1024 /*align*/ + 512 /*barriers*/ + kMegaScratchBytes;
 
 struct MegaLayer {
   const CUtensorMap *tm_qkv, *tm_o, *tm_cq, *tm_co, *tm_wi, *tm_ffo;  // device-resident tensor maps
@@ -82,18 +87,24 @@ struct MegaParams {
 enum MegaEpi { ME_PARTIAL = 0, ME_QKV = 1, ME_STORE = 2, ME_GEGLU = 3, ME_ARGMAX = 4 };
 
 struct MegaShared {
-  uint8_t* ring;
+  uint8_t* ring;     // GEMM operand ring (TMA tensor tiles)
+  uint8_t* xa_ring;  // cross-attention K/V chunk ring (bulk copies), [group][slot][8 KB]
   uint64_t *full, *empty, *tfull, *tempty;
+  uint64_t *xa_full, *xa_empty;  // [group][slot]
   uint32_t* tmem_slot;
   int* s_step;
   uint8_t* scratch;
 };
 
+// Pipeline positions that persist across phases (every thread carries a copy; each role uses its fields).
 struct MegaPipe {
   int stage = 0;
   uint32_t phase = 0;
   int as = 0;
   uint32_t aphase = 0;
+  int pref = 0;                       // producer: k-blocks of the next GEMM phase whose weight tile is already requested
+  unsigned int xa_use = 0;            // cross-attention consumer: chunks consumed by this thread's group
+  unsigned int xa_issue[kMegaGroups] = {0, 0, 0};  // producer: chunks issued per group
 };
 
 DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -102,14 +113,14 @@ DEVINL unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-// All CTAs of the (cooperative) grid: one release-add and a polled acquire-load by thread 0
-// (SASS: RED.STRONG.GPU, LDG.STRONG.GPU + CCTL.IVALL - the acquire also drops this SM's stale L1
-// lines, so the other threads' plain loads after the bar.sync see the peers' writes). Thread 0 is
-// also the TMA producer: the proxy fence orders the peers' generic-proxy global writes, and this
+// All CTAs of the (cooperative) grid: one release-add and a polled acquire-load by the control
+// warp's lane 0 (SASS: RED.STRONG.GPU, LDG.STRONG.GPU + CCTL.IVALL - the acquire also drops this
+// SM's stale L1 lines, so the other threads' plain loads after the bar.sync see the peers' writes).
+// The same thread is the TMA producer: the proxy fence orders the peers' generic-proxy global writes, and this
 // CTA's generic-proxy use of the shared-memory ring, before its next async-proxy (TMA) accesses.
 DEVINL void grid_sync(unsigned int* bar, unsigned int& target) {
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == kMegaMaster) {
     target += gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int spins = 0;
@@ -140,7 +151,40 @@ struct MegaGemm {
   int ws_ld;  // row stride of ws (= N)
 };
 
-__device__ __noinline__ void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_base, const MegaGemm& g) {
+// Producer only: request the WEIGHT tiles of this CTA's first job of an upcoming GEMM phase. They never
+// depend on the phases in between, so their HBM latency is hidden behind those phases and the barrier;
+// the matching activation tiles are requested by mega_gemm_phase once the barrier has passed.
+DEVINL void mega_gemm_prefetch_b(const MegaShared& sh, MegaPipe& ps, const MegaGemm& g) {
+  if (threadIdx.x != kMegaMaster) return;
+  const int tiles_m = (g.M + kBM - 1) / kBM;
+  const int tiles_n = (g.N + g.bn - 1) / g.bn;
+  const int kblocks = (g.K + kBK - 1) / kBK;
+  const int kb_per = (kblocks + g.ksplit - 1) / g.ksplit;
+  const int njobs = tiles_m * tiles_n * g.ksplit;
+  ps.pref = 0;
+  const int job = blockIdx.x;
+  if (job >= njobs) return;
+  const int ks = job % g.ksplit, t = job / g.ksplit;
+  const int n_tile = t % tiles_n;
+  const int kb0 = ks * kb_per;
+  const int kb1 = kb0 + kb_per < kblocks ? kb0 + kb_per : kblocks;
+  const int n = (kb1 - kb0) < kMegaStages ? (kb1 - kb0) : kMegaStages;
+  const uint32_t stage_tx = static_cast<uint32_t>(kBM * kBK * 2 + g.bn * kBK * 2);
+  int st = ps.stage;
+  uint32_t ph = ps.phase;
+  for (int i = 0; i < n; ++i) {
+    mbar_wait(&sh.empty[st], ph ^ 1u);
+    mbar_arrive_expect_tx(&sh.full[st], stage_tx);
+    tma_load_2d(sh.ring + st * kMegaStageBytes + kBM * kBK * 2, g.tmB, &sh.full[st], (kb0 + i) * kBK, n_tile * g.bn);
+    if (++st == kMegaStages) {
+      st = 0;
+      ph ^= 1u;
+    }
+  }
+  ps.pref = n;
+}
+
+DEVINL void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_base, const MegaGemm& g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + kBM - 1) / kBM;
   const int tiles_n = (g.N + g.bn - 1) / g.bn;
@@ -149,19 +193,25 @@ __device__ __noinline__ void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps,
   const int njobs = tiles_m * tiles_n * g.ksplit;
   const uint32_t stage_tx = static_cast<uint32_t>(kBM * kBK * 2 + g.bn * kBK * 2);
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == kMegaMaster) {
     // ------------------------------------------------------------ TMA producer
+    int pref = ps.pref;  // leading k-blocks of the first job whose weight tile was requested ahead of the barrier
+    ps.pref = 0;
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
       const int ks = job % g.ksplit, t = job / g.ksplit;
       const int n_tile = t % tiles_n, m_tile = t / tiles_n;
       const int kb0 = ks * kb_per;
       const int kb1 = kb0 + kb_per < kblocks ? kb0 + kb_per : kblocks;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&sh.empty[ps.stage], ps.phase ^ 1u);
         uint8_t* sA = sh.ring + ps.stage * kMegaStageBytes;
-        mbar_arrive_expect_tx(&sh.full[ps.stage], stage_tx);
+        if (pref > 0) {
+          --pref;  // slot reserved, transaction count armed and B in flight already
+        } else {
+          mbar_wait(&sh.empty[ps.stage], ps.phase ^ 1u);
+          mbar_arrive_expect_tx(&sh.full[ps.stage], stage_tx);
+          tma_load_2d(sA + kBM * kBK * 2, g.tmB, &sh.full[ps.stage], kb * kBK, n_tile * g.bn);
+        }
         tma_load_2d(sA, g.tmA, &sh.full[ps.stage], kb * kBK, m_tile * kBM);
-        tma_load_2d(sA + kBM * kBK * 2, g.tmB, &sh.full[ps.stage], kb * kBK, n_tile * g.bn);
         if (++ps.stage == kMegaStages) {
           ps.stage = 0;
           ps.phase ^= 1u;
@@ -201,7 +251,7 @@ __device__ __noinline__ void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps,
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------ epilogue warps (threads 128..255)
     const int q = warp & 3;
     if (g.epi == ME_GEGLU) EpiGeglu::prologue(g.geglu, sh.scratch, static_cast<int>(threadIdx.x) - 128, 128);
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
@@ -286,7 +336,7 @@ __device__ __noinline__ void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps,
 
 __device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* ws, int ksplit, const __nv_bfloat16* w, __nv_bfloat16* xn,
                                int rows, int d, float eps, float* scratch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // the control warp (12) falls outside every row group
   const int nvec = d >> 3;
   int W = (nvec + 31) >> 5;          // warps per row
   if (W > kMegaWarps) W = kMegaWarps;  // wider rows: lanes loop over vectors
@@ -373,6 +423,7 @@ __device__ __noinline__ void mega_self_attn_phase(const __nv_bfloat16* q, const 
                                  __nv_bfloat16* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
                                  float* scratch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= kMegaWarps) return;  // control warp
   float* sc = scratch + warp * Tk;
   const int ks = lane >> 3, dg = lane & 7;
   const int nkeys = t + 1;
@@ -466,106 +517,115 @@ __device__ __noinline__ void mega_self_attn_phase(const __nv_bfloat16* q, const 
 // A group of 4 warps per (row, head), kMegaGroups groups per CTA; the arithmetic is
 // attn_decode_kernel<false>'s (exact two-pass softmax, K and V each streamed once).
 //
-// The phase is the HBM roofline of the step, and with one resident CTA per SM the bytes in
-// flight must come from depth, not from occupancy: every thread streams ITS OWN 16-byte pieces
-// (the same (key, segment) mapping it consumes) through a private ring of kXaDepth cp.async
-// slots in shared memory - kXaDepth * 384 * 16 B = 96 KB in flight per SM, no registers held,
-// no inter-thread synchronisation for the ring. The request stream runs ahead across the
-// K -> softmax -> V -> next (row, head) boundaries (V and the next item's K do not depend on the
-// scores), so the memory pipe never drains inside the phase.
-constexpr int kXaDepth = 16;
-static_assert(kXaDepth * kMegaThreads * 16 <= kMegaStages * kMegaStageBytes, "the request ring reuses the (idle) GEMM ring");
-
+// The phase is the HBM roofline of the step, and with one resident CTA per SM the bytes in flight
+// must come from depth, not from occupancy. The control warp streams every group's K and V slabs
+// as 8 KB bulk copies (cp.async.bulk, 64 keys x 128 B, L2 evict-first) into a ring of kXaSlots
+// chunks per group: 96 KB in flight per SM for ~one instruction per 8 KB, completion on per-slot
+// mbarriers. The request stream runs ahead across the K -> softmax -> V -> next (row, head)
+// boundaries (V and the next item's K do not depend on the scores), so the memory pipe never
+// drains inside the phase; the compute warps only read shared memory.
 DEVINL void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 4) : "memory"); }
-DEVINL void cp_async16_evict_first(uint32_t smem_dst, const void* gsrc, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(policy) : "memory");
+
+DEVINL void bulk_load_1d_evict_first(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
-struct XaStream {  // per-thread request stream over this group's items: K pieces then V pieces of each item
-  int bh, e, n;    // current item, entry inside the item (0..2n), pieces per operand
-  const __nv_bfloat16 *Kp, *Vp;
-};
-
-DEVINL void xa_open_item(XaStream& st, int bh, int BH, int H, int Tk, const int* extent, const __nv_bfloat16* Kc,
-                         const __nv_bfloat16* Vc, int dg) {
-  st.bh = bh;
-  st.e = 0;
-  if (bh < BH) {
-    const int nkeys = extent[bh / H];
-    st.n = (nkeys + 15) >> 4;
-    const size_t slab = static_cast<size_t>(bh) * Tk * 64;
-    st.Kp = Kc + slab + dg * 8;
-    st.Vp = Vc + slab + dg * 8;
-  } else {
-    st.n = 0;
+__device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPipe& ps, const __nv_bfloat16* q,
+                                                   const __nv_bfloat16* Kc, const __nv_bfloat16* Vc, __nv_bfloat16* ctx,
+                                                   int BH, int H, int Tk, const int* extent, const unsigned char* key_ok) {
+  const int stride = gridDim.x * kMegaGroups;
+  if (threadIdx.x >= kMegaWarps * 32) {
+    // ------------------------------------------------------------ bulk-copy producer (control warp, lane 0)
+    if (threadIdx.x != kMegaMaster) return;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    int bh[kMegaGroups], e[kMegaGroups], nck[kMegaGroups], nkeys[kMegaGroups];
+#pragma unroll
+    for (int g = 0; g < kMegaGroups; ++g) {
+      bh[g] = blockIdx.x * kMegaGroups + g;
+      e[g] = 0;
+      nkeys[g] = bh[g] < BH ? extent[bh[g] / H] : 0;
+      nck[g] = (nkeys[g] + kXaChunkKeys - 1) / kXaChunkKeys;
+    }
+    bool any = true;
+    while (any) {
+      any = false;
+#pragma unroll
+      for (int g = 0; g < kMegaGroups; ++g) {
+        if (bh[g] >= BH) continue;
+        any = true;
+        const bool isv = e[g] >= nck[g];
+        const int c = isv ? e[g] - nck[g] : e[g];
+        const int rows = nkeys[g] - c * kXaChunkKeys < kXaChunkKeys ? nkeys[g] - c * kXaChunkKeys : kXaChunkKeys;
+        const unsigned int seq = ps.xa_issue[g]++;
+        const int slot = seq % kXaSlots;
+        uint64_t* full = &sh.xa_full[g * kXaSlots + slot];
+        mbar_wait(&sh.xa_empty[g * kXaSlots + slot], ((seq / kXaSlots) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(full, static_cast<uint32_t>(rows) * 128u);
+        const __nv_bfloat16* src = (isv ? Vc : Kc) + (static_cast<size_t>(bh[g]) * Tk + static_cast<size_t>(c) * kXaChunkKeys) * 64;
+        bulk_load_1d_evict_first(sh.xa_ring + (g * kXaSlots + slot) * kXaChunkBytes, src, static_cast<uint32_t>(rows) * 128u, full, policy);
+        if (++e[g] == 2 * nck[g]) {
+          bh[g] += stride;
+          e[g] = 0;
+          nkeys[g] = bh[g] < BH ? extent[bh[g] / H] : 0;
+          nck[g] = (nkeys[g] + kXaChunkKeys - 1) / kXaChunkKeys;
+        }
+      }
+    }
+    return;
   }
-}
-
-__device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc,
-                                  __nv_bfloat16* ctx, int BH, int H, int Tk, const int* extent,
-                                  const unsigned char* key_ok, float* scratch, uint8_t* ring) {
-  const int group = threadIdx.x >> 7;  // 0..kMegaGroups-1
+  // ------------------------------------------------------------ compute groups
+  const int group = threadIdx.x >> 7;
   const int gt = threadIdx.x & 127;
   const int warp = gt >> 5, lane = gt & 31;
   const int ks = lane >> 3, dg = lane & 7;
-  float* s_scores = scratch + group * (Tk + 4 * 64 + 8);
+  float* s_scores = reinterpret_cast<float*>(sh.scratch) + group * (Tk + 4 * 64 + 8);
   float* s_red = s_scores + Tk;    // [4][64]
   float* s_stat = s_red + 4 * 64;  // [8]
-  const uint32_t my_ring = smem_u32(ring) + threadIdx.x * 16u;  // slot s of this thread: + s * kMegaThreads * 16
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const int stride = gridDim.x * kMegaGroups;
-  const int j_base = warp * 4 + ks;  // this thread's first key; its pieces are keys j_base + 16 u
-
-  // request stream: issue one piece (or an empty group) per call
-  XaStream rq;
-  xa_open_item(rq, blockIdx.x * kMegaGroups + group, BH, H, Tk, extent, Kc, Vc, dg);
-  unsigned int seq_issue = 0;
-  auto issue_one = [&]() {
-    while (rq.bh < BH && rq.e >= 2 * rq.n) xa_open_item(rq, rq.bh + stride, BH, H, Tk, extent, Kc, Vc, dg);
-    if (rq.bh < BH) {
-      const bool isv = rq.e >= rq.n;
-      const int u = isv ? rq.e - rq.n : rq.e;
-      const int j = j_base + 16 * u;
-      const int nkeys = extent[rq.bh / H];
-      if (j < nkeys)
-        cp_async16_evict_first(my_ring + (seq_issue % kXaDepth) * (kMegaThreads * 16u),
-                               (isv ? rq.Vp : rq.Kp) + static_cast<size_t>(j) * 64, policy);
-      ++rq.e;
-    }
-    cp_async_commit();
-    ++seq_issue;
-  };
-#pragma unroll 1
-  for (int i = 0; i < kXaDepth; ++i) issue_one();
-
-  unsigned int seq_use = 0;
+  const uint32_t ring0 = smem_u32(sh.xa_ring + group * kXaSlots * kXaChunkBytes) + (warp * 4 + ks) * 128 + dg * 16;
+  uint64_t* full0 = sh.xa_full + group * kXaSlots;
+  uint64_t* empty0 = sh.xa_empty + group * kXaSlots;
   for (int bh = blockIdx.x * kMegaGroups + group; bh < BH; bh += stride) {
     const int b = bh / H;
     const int nkeys = extent[b];
-    const int n = (nkeys + 15) >> 4;
+    const int nck = (nkeys + kXaChunkKeys - 1) / kXaChunkKeys;
     float qf[8];
     {
       const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
       qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
       qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
     }
-    // ---- scores
-    for (int u = 0; u < n; ++u) {
-      cp_async_wait<kXaDepth - 1>();
-      const int j = j_base + 16 * u;
-      uint4 kv = make_uint4(0, 0, 0, 0);
-      if (j < nkeys) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kv.x), "=r"(kv.y), "=r"(kv.z), "=r"(kv.w) : "r"(my_ring + (seq_use % kXaDepth) * (kMegaThreads * 16u)));
-      ++seq_use;
-      issue_one();  // refill the slot just consumed (same thread: program order suffices)
-      float sc = dot8(kv, qf);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-      if (dg == 0 && j < nkeys) {
-        sc = bf16_round(sc);
-        if (!key_ok[static_cast<size_t>(b) * Tk + j]) sc = kBf16Min;
-        s_scores[j] = sc;
+    // ---- scores: chunk c holds keys [64c, 64c+64); this thread reads keys 64c + 16r + 4*warp + ks, r = 0..3
+    for (int c = 0; c < nck; ++c) {
+      const unsigned int seq = ps.xa_use++;
+      const int slot = seq % kXaSlots;
+      mbar_wait(&full0[slot], (seq / kXaSlots) & 1u);
+      const uint32_t base = ring0 + slot * kXaChunkBytes;
+      uint4 kv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = c * kXaChunkKeys + r * 16 + warp * 4 + ks;
+        kv[r] = make_uint4(0, 0, 0, 0);
+        if (j < nkeys)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kv[r].x), "=r"(kv[r].y), "=r"(kv[r].z), "=r"(kv[r].w) : "r"(base + r * 16 * 128));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty0[slot]);  // this warp has copied its pieces out of the slot
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = c * kXaChunkKeys + r * 16 + warp * 4 + ks;
+        float sc = dot8(kv[r], qf);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        if (dg == 0 && j < nkeys) {
+          sc = bf16_round(sc);
+          if (!key_ok[static_cast<size_t>(b) * Tk + j]) sc = kBf16Min;
+          s_scores[j] = sc;
+        }
       }
     }
     group_sync(group);
@@ -578,9 +638,9 @@ __device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const
     mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
     float sum = 0.f;
     for (int j = gt; j < nkeys; j += 128) {
-      const float e = expf(s_scores[j] - mx);
-      s_scores[j] = e;
-      sum += e;
+      const float ev = expf(s_scores[j] - mx);
+      s_scores[j] = ev;
+      sum += ev;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -592,35 +652,46 @@ __device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const
     // ---- out = P . V
     float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int u = 0; u < n; ++u) {
-      cp_async_wait<kXaDepth - 1>();
-      const int j = j_base + 16 * u;
-      uint4 vv = make_uint4(0, 0, 0, 0);
-      float pj = 0.f;
-      if (j < nkeys) {
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vv.x), "=r"(vv.y), "=r"(vv.z), "=r"(vv.w) : "r"(my_ring + (seq_use % kXaDepth) * (kMegaThreads * 16u)));
-        pj = s_scores[j];
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int c = 0; c < nck; ++c) {
+      const unsigned int seq = ps.xa_use++;
+      const int slot = seq % kXaSlots;
+      mbar_wait(&full0[slot], (seq / kXaSlots) & 1u);
+      const uint32_t base = ring0 + slot * kXaChunkBytes;
+      uint4 vv[4];
+      float pj[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = c * kXaChunkKeys + r * 16 + warp * 4 + ks;
+        vv[r] = make_uint4(0, 0, 0, 0);
+        pj[r] = 0.f;
+        if (j < nkeys) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vv[r].x), "=r"(vv[r].y), "=r"(vv[r].z), "=r"(vv[r].w) : "r"(base + r * 16 * 128));
+          pj[r] = s_scores[j];
+        }
       }
-      ++seq_use;
-      issue_one();
-      acc[0] = fmaf(pj, bf16_lo(vv.x), acc[0]);
-      acc[1] = fmaf(pj, bf16_hi(vv.x), acc[1]);
-      acc[2] = fmaf(pj, bf16_lo(vv.y), acc[2]);
-      acc[3] = fmaf(pj, bf16_hi(vv.y), acc[3]);
-      acc[4] = fmaf(pj, bf16_lo(vv.z), acc[4]);
-      acc[5] = fmaf(pj, bf16_hi(vv.z), acc[5]);
-      acc[6] = fmaf(pj, bf16_lo(vv.w), acc[6]);
-      acc[7] = fmaf(pj, bf16_hi(vv.w), acc[7]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty0[slot]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[0] = fmaf(pj[r], bf16_lo(vv[r].x), acc[0]);
+        acc[1] = fmaf(pj[r], bf16_hi(vv[r].x), acc[1]);
+        acc[2] = fmaf(pj[r], bf16_lo(vv[r].y), acc[2]);
+        acc[3] = fmaf(pj[r], bf16_hi(vv[r].y), acc[3]);
+        acc[4] = fmaf(pj[r], bf16_lo(vv[r].z), acc[4]);
+        acc[5] = fmaf(pj[r], bf16_hi(vv[r].z), acc[5]);
+        acc[6] = fmaf(pj[r], bf16_lo(vv[r].w), acc[6]);
+        acc[7] = fmaf(pj[r], bf16_hi(vv[r].w), acc[7]);
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
     if (ks == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s_red[warp * 64 + dg * 8 + e] = acc[e];
+      for (int i = 0; i < 8; ++i) s_red[warp * 64 + dg * 8 + i] = acc[i];
     }
     group_sync(group);
     if (gt < 32) {
@@ -631,7 +702,6 @@ __device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const
     }
     group_sync(group);  // s_scores / s_red are reused by the next item
   }
-  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------- greedy bookkeeping phase
@@ -640,6 +710,7 @@ __device__ __noinline__ void mega_cross_attn_phase(const __nv_bfloat16* q, const
 // apply the first RMSNorm of the next step.
 __device__ __noinline__ void mega_finalize_phase(const MegaParams& P, int t) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= kMegaWarps) return;  // control warp
   const int d = P.d, nvec = d >> 3;
   for (int b = blockIdx.x * kMegaWarps + warp; b < P.B; b += gridDim.x * kMegaWarps) {
     float best = -INFINITY;
@@ -688,14 +759,18 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   MegaShared sh;
   sh.ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMegaStages * kMegaStageBytes);
+  sh.xa_ring = smem + kMegaStages * kMegaStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sh.xa_ring + kMegaXaRingBytes);
   sh.full = bars;
   sh.empty = bars + kMegaStages;
   sh.tfull = bars + 2 * kMegaStages;
   sh.tempty = sh.tfull + 2;
-  sh.tmem_slot = reinterpret_cast<uint32_t*>(sh.tempty + 2);
+  sh.xa_full = sh.tempty + 2;
+  sh.xa_empty = sh.xa_full + kMegaGroups * kXaSlots;
+  sh.tmem_slot = reinterpret_cast<uint32_t*>(sh.xa_empty + kMegaGroups * kXaSlots);
   sh.s_step = reinterpret_cast<int*>(sh.tmem_slot + 1);
-  sh.scratch = smem + kMegaStages * kMegaStageBytes + 512;
+  sh.scratch = reinterpret_cast<uint8_t*>(bars) + 512;
+  static_assert((2 * kMegaStages + 4 + 2 * kMegaGroups * kXaSlots) * 8 + 8 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1) {
@@ -707,6 +782,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
       for (int i = 0; i < 2; ++i) {
         mbar_init(&sh.tfull[i], 1);
         mbar_init(&sh.tempty[i], 4);
+      }
+      for (int i = 0; i < kMegaGroups * kXaSlots; ++i) {
+        mbar_init(&sh.xa_full[i], 1);
+        mbar_init(&sh.xa_empty[i], 4);  // the group's four warps
       }
       mbar_fence_init();
     }
@@ -722,17 +801,51 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
   unsigned int bar_target = 0;
   int prof_n = 0;
   int prof_t = -1;
-#define GSYNC()                                                                                  \
-  do {                                                                                           \
-    const bool _pr = P.prof != nullptr && prof_t == P.prof_step && blockIdx.x == 0 && threadIdx.x == 0; \
-    if (_pr) P.prof[prof_n++] = clock64();                                                       \
-    grid_sync(P.bar, bar_target);                                                                \
-    if (_pr) P.prof[prof_n++] = clock64();                                                       \
+#define GSYNC()                                                                                        \
+  do {                                                                                                 \
+    const bool _pr = P.prof != nullptr && prof_t == P.prof_step && blockIdx.x == 0 && threadIdx.x == kMegaMaster; \
+    __syncthreads();                                                                                   \
+    if (_pr) P.prof[prof_n++] = clock64(); /* this CTA's work of the phase is complete */            \
+    grid_sync(P.bar, bar_target);                                                                      \
+    if (_pr) P.prof[prof_n++] = clock64();                                                             \
   } while (0)
   const int B = P.B, d = P.d, I = P.I, F = P.F, H = P.H;
   float* fscratch = reinterpret_cast<float*>(sh.scratch);
 
+  // GEMM phase descriptors
+  auto g_qkv = [&](const MegaLayer& L) {
+    MegaGemm g;
+    g.tmA = P.tm_dxn; g.tmB = L.tm_qkv; g.M = B; g.N = 3 * I; g.K = d; g.bn = P.bn_qkv; g.ksplit = 1; g.epi = ME_QKV;
+    g.qkv = EpiQkvDecode::Params{P.dq, L.self_kv, sh.s_step, B, H, P.T};
+    return g;
+  };
+  auto g_part = [&](const CUtensorMap* tmA, const CUtensorMap* tmB, int K, int bn, int ksplit) {
+    MegaGemm g;
+    g.tmA = tmA; g.tmB = tmB; g.M = B; g.N = d; g.K = K; g.bn = bn; g.ksplit = ksplit; g.epi = ME_PARTIAL;
+    g.ws = P.ws; g.ws_ld = d;
+    return g;
+  };
+  auto g_cq = [&](const MegaLayer& L) {
+    MegaGemm g;
+    g.tmA = P.tm_dxn; g.tmB = L.tm_cq; g.M = B; g.N = I; g.K = d; g.bn = P.bn_cq; g.ksplit = 1; g.epi = ME_STORE;
+    g.store = EpiStore::Params{P.dq, I};
+    return g;
+  };
+  auto g_wi = [&](const MegaLayer& L) {
+    MegaGemm g;
+    g.tmA = P.tm_dxn; g.tmB = L.tm_wi; g.M = B; g.N = L.wi_rows; g.K = d; g.bn = P.bn_wi; g.ksplit = 1; g.epi = ME_GEGLU;
+    g.geglu = EpiGeglu::Params{P.dh, F, P.lut};
+    return g;
+  };
+  auto g_lm = [&]() {
+    MegaGemm g;
+    g.tmA = P.tm_dxn; g.tmB = P.tm_lm; g.M = B; g.N = P.V; g.K = d; g.bn = P.bn_lm; g.ksplit = 1; g.epi = ME_ARGMAX;
+    g.amax = EpiArgmax::Params{P.pval, P.pidx, P.n_vtiles, sh.s_step, static_cast<int>(P.eos), P.min_new};
+    return g;
+  };
+
   // first RMSNorm of the first step (x = embedding of decoder_start, set by decode_init_kernel)
+  mega_gemm_prefetch_b(sh, ps, g_qkv(P.layers[0]));
   mega_resnorm_phase(P.dx, nullptr, 0, P.layers[0].ln0, P.dxn, B, d, P.eps, fscratch);
   GSYNC();
 
@@ -745,68 +858,41 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
       const size_t self_plane = static_cast<size_t>(B) * I * P.T;
       const size_t cross_plane = static_cast<size_t>(B) * I * P.S;
       // ---- self-attention block
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dxn; g.tmB = L.tm_qkv; g.M = B; g.N = 3 * I; g.K = d; g.bn = P.bn_qkv; g.ksplit = 1; g.epi = ME_QKV;
-        g.qkv = EpiQkvDecode::Params{P.dq, L.self_kv, sh.s_step, B, H, P.T};
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_qkv(L));
+      mega_gemm_prefetch_b(sh, ps, g_part(P.tm_dctx, L.tm_o, I, P.bn_proj, P.ks_proj));
       GSYNC();
       mega_self_attn_phase(P.dq, L.self_kv, L.self_kv + self_plane, P.dctx, B * H, H, P.T, t, P.dec_bias, fscratch);
       GSYNC();
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dctx; g.tmB = L.tm_o; g.M = B; g.N = d; g.K = I; g.bn = P.bn_proj; g.ksplit = P.ks_proj; g.epi = ME_PARTIAL;
-        g.ws = P.ws; g.ws_ld = d;
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_part(P.tm_dctx, L.tm_o, I, P.bn_proj, P.ks_proj));
+      mega_gemm_prefetch_b(sh, ps, g_cq(L));
       GSYNC();
       mega_resnorm_phase(P.dx, P.ws, P.ks_proj, L.ln1, P.dxn, B, d, P.eps, fscratch);
       GSYNC();
       // ---- cross-attention block
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dxn; g.tmB = L.tm_cq; g.M = B; g.N = I; g.K = d; g.bn = P.bn_cq; g.ksplit = 1; g.epi = ME_STORE;
-        g.store = EpiStore::Params{P.dq, I};
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_cq(L));
+      mega_gemm_prefetch_b(sh, ps, g_part(P.tm_dctx, L.tm_co, I, P.bn_proj, P.ks_proj));
       GSYNC();
-      mega_cross_attn_phase(P.dq, L.cross_kv, L.cross_kv + cross_plane, P.dctx, B * H, H, P.S, P.extent, P.key_ok, fscratch, sh.ring);
+      mega_cross_attn_phase(sh, ps, P.dq, L.cross_kv, L.cross_kv + cross_plane, P.dctx, B * H, H, P.S, P.extent, P.key_ok);
       GSYNC();
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dctx; g.tmB = L.tm_co; g.M = B; g.N = d; g.K = I; g.bn = P.bn_proj; g.ksplit = P.ks_proj; g.epi = ME_PARTIAL;
-        g.ws = P.ws; g.ws_ld = d;
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_part(P.tm_dctx, L.tm_co, I, P.bn_proj, P.ks_proj));
+      mega_gemm_prefetch_b(sh, ps, g_wi(L));
       GSYNC();
       mega_resnorm_phase(P.dx, P.ws, P.ks_proj, L.ln2, P.dxn, B, d, P.eps, fscratch);
       GSYNC();
       // ---- feed-forward block
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dxn; g.tmB = L.tm_wi; g.M = B; g.N = L.wi_rows; g.K = d; g.bn = P.bn_wi; g.ksplit = 1; g.epi = ME_GEGLU;
-        g.geglu = EpiGeglu::Params{P.dh, F, P.lut};
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_wi(L));
+      mega_gemm_prefetch_b(sh, ps, g_part(P.tm_dh, L.tm_ffo, F, P.bn_ffo, P.ks_ffo));
       GSYNC();
-      {
-        MegaGemm g;
-        g.tmA = P.tm_dh; g.tmB = L.tm_ffo; g.M = B; g.N = d; g.K = F; g.bn = P.bn_ffo; g.ksplit = P.ks_ffo; g.epi = ME_PARTIAL;
-        g.ws = P.ws; g.ws_ld = d;
-        mega_gemm_phase(sh, ps, tmem_base, g);
-      }
+      mega_gemm_phase(sh, ps, tmem_base, g_part(P.tm_dh, L.tm_ffo, F, P.bn_ffo, P.ks_ffo));
+      if (l + 1 < P.Ld) mega_gemm_prefetch_b(sh, ps, g_qkv(P.layers[l + 1]));
+      else mega_gemm_prefetch_b(sh, ps, g_lm());
       GSYNC();
       mega_resnorm_phase(P.dx, P.ws, P.ks_ffo, l + 1 < P.Ld ? P.layers[l + 1].ln0 : P.final_ln, P.dxn, B, d, P.eps, fscratch);
       GSYNC();
     }
     // ---- lm_head + arg-max, then the greedy bookkeeping
-    {
-      MegaGemm g;
-      g.tmA = P.tm_dxn; g.tmB = P.tm_lm; g.M = B; g.N = P.V; g.K = d; g.bn = P.bn_lm; g.ksplit = 1; g.epi = ME_ARGMAX;
-      g.amax = EpiArgmax::Params{P.pval, P.pidx, P.n_vtiles, sh.s_step, static_cast<int>(P.eos), P.min_new};
-      mega_gemm_phase(sh, ps, tmem_base, g);
-    }
+    mega_gemm_phase(sh, ps, tmem_base, g_lm());
+    mega_gemm_prefetch_b(sh, ps, g_qkv(P.layers[0]));  // next step (harmless after the last one: never consumed)
     GSYNC();
     mega_finalize_phase(P, t);
     GSYNC();
@@ -817,8 +903,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     mega_resnorm_phase(P.dx, nullptr, 0, P.layers[0].ln0, P.dxn, B, d, P.eps, fscratch);
     GSYNC();
   }
-
 #undef GSYNC
+  // a weight tile requested for a step that never ran must land before the shared memory is released
+  if (threadIdx.x == kMegaMaster && ps.pref > 0) {
+    // complete the armed transactions with the matching activation tiles (any valid tile) and wait for them
+    const MegaGemm g = g_qkv(P.layers[0]);
+    int st = ps.stage;
+    uint32_t ph = ps.phase;
+    for (int i = 0; i < ps.pref; ++i) {
+      tma_load_2d(sh.ring + st * kMegaStageBytes, g.tmA, &sh.full[st], i * kBK, 0);
+      mbar_wait(&sh.full[st], ph);
+      if (++st == kMegaStages) {
+        st = 0;
+        ph ^= 1u;
+      }
+    }
+  }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
