@@ -17,6 +17,9 @@
 // (release/acquire) publishes the writes, and the owner sums the S partials in rank order
 // (deterministic) and feeds 32-column chunks to the same epilogue functors the persistent GEMM
 // uses (gemm.cuh), so the T5 rounding contract is shared.
+// (Measured alternative: st.async with a receiver-side mbarrier instead of the release fence +
+// cluster barrier - the fence/barrier pair is ~30 % of this kernel's stall samples - was slower,
+// 194.8 vs 188.3 ms per batch: thousands of 16-byte complete_tx updates serialise on the barrier.)
 #pragma once
 #include "gemm.cuh"
 
