@@ -77,7 +77,12 @@ def effective_cores() -> int:
 
 
 def workload_name(a):
-    return f"{a.model} batch {a.batch} {a.seq}-in/{a.new}-out greedy, lengths={a.lengths} (BASELINE configs[1])"
+    # BASELINE.json: configs[1] = FLAN-T5-base, batch 256, 512-in/128-out on one B200 (the config the metric is
+    # quoted on); configs[3] = the same shape with FLAN-T5-large (HBM-roofline report); configs[0] is the CPU case
+    tag = {"flan-t5-base": "BASELINE configs[1]", "flan-t5-large": "BASELINE configs[3] shape", "flan-t5-small": "configs[0] model at the configs[1] shape"}
+    std = a.batch == 256 and a.seq == 512 and a.new == 128 and a.lengths == "full"
+    note = tag.get(a.model, "custom") if std else "custom shape"
+    return f"{a.model} batch {a.batch} {a.seq}-in/{a.new}-out greedy, lengths={a.lengths} ({note})"
 
 
 # --------------------------------------------------------------------------- clocks sampling
@@ -295,10 +300,15 @@ def main_b200(a):
         hbm_peak, tf_peak, peak_src = float(pk["hbm_gbs"]), float(pk.get("bf16_tflops_sustained", 1458.8)), "measured (MEASURED_PEAKS.json)"
     else:
         hbm_peak, tf_peak, peak_src = 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+    # DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture: only valid for the
+    # configuration that was captured (FLAN-T5-base, B=256, S=512, full-length prompts)
     traffic = None
     tf = ROOT / "profiles" / "cross_attn_traffic.json"
-    if tf.exists():
+    if tf.exists() and a.model == "flan-t5-base" and (B, S, a.lengths) == (256, 512, "full"):
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    kv_gb = 2.0 * spec.num_decoder_layers * 2 * B * S * spec.inner_dim / 1e9
+    w_gb = 2.0 * (spec.num_decoder_layers * (6 * spec.d_model * spec.inner_dim + 3 * spec.d_model * spec.d_ff)
+                  + spec.vocab_size * spec.d_model) / 1e9
 
     if rank == 0:
         tokens = world * K * B * T
@@ -310,7 +320,8 @@ def main_b200(a):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": world * B, "prompts_per_rank_step": B,
                        "parallelism": f"dataset sharded over {world} replica(s), no collective",
-                       "l2": "inputs exceed L2 (cross-KV arena 4.8 GB, weights 0.5 GB per step vs 126 MB L2)",
+                       "l2": f"inputs exceed L2 (cross-KV arena {kv_gb:.1f} GB and {w_gb:.2f} GB of decoder weights "
+                             "are streamed every step vs 126 MB L2)",
                        "forced_length": "min_new_tokens == max_new_tokens"},
             "prompts_per_s": world * K * B / (elapsed_ms / 1e3),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * S * 8,
