@@ -36,6 +36,16 @@ DEVINL float dot8(const uint4& kv, const float (&qf)[8]) {
   return s;
 }
 
+// Weights the kernels AFTER the cross-attention will need (this layer's cross-O / wi / FF-out, the next layer's
+// QKV / O / cross-Q). Decoder weights (198 MB for base) do not survive in L2 across a step once 4.8 GB of KV
+// has streamed through, so every skinny GEMM used to start with an HBM round trip on its critical path. The
+// streaming kernel has 64 us and ~4 % of spare bandwidth: each CTA requests one slice of every buffer into L2
+// (evict-last) while the K/V stream itself is marked evict-first.
+struct L2Prefetch {
+  const void* ptr[6];
+  unsigned int bytes[6];
+};
+
 template <bool kSelf>
 __global__ void __launch_bounds__(kAttnDecThreads)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
@@ -46,13 +56,28 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
                    const int* __restrict__ extent,            // cross: [B] keys to visit
                    const unsigned char* __restrict__ key_ok,  // cross: [B][Tk] 1 = attended
                    const int* __restrict__ step,              // self: device scalar t
-                   const float* __restrict__ dist_bias) {     // self: [H][Tk] bias by distance t-j
+                   const float* __restrict__ dist_bias,       // self: [H][Tk] bias by distance t-j
+                   const L2Prefetch pf) {                     // cross: weight slices to pull into L2 (bytes 0 = none)
   extern __shared__ float s_scores[];  // Tk floats
   __shared__ float s_red[4][64];
   __shared__ float s_stat[8];
 
   pdl_launch_dependents();
+  if (!kSelf && threadIdx.x == 0) {
+    // constant data: no need to wait for the previous kernel
+    const uint64_t keep = l2_policy_evict_last();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const unsigned int per = ((pf.bytes[k] + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
+      const unsigned long long off = static_cast<unsigned long long>(blockIdx.x) * per;
+      if (off < pf.bytes[k]) {
+        const unsigned int n = pf.bytes[k] - off < per ? static_cast<unsigned int>(pf.bytes[k] - off) & ~15u : per;
+        if (n) prefetch_l2_bulk(static_cast<const char*>(pf.ptr[k]) + off, n, keep);
+      }
+    }
+  }
   pdl_wait();
+  const uint64_t stream_policy = l2_policy_evict_first();
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = lane >> 3, dg = lane & 7;
@@ -78,7 +103,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
 #pragma unroll
     for (int u = 0; u < kAttnDecUnroll; ++u) {
       const int j = j0 + 16 * u;
-      kv[u] = j < nkeys ? ldg_nc_v4(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      kv[u] = j < nkeys ? (kSelf ? ldg_nc_v4(Kp + static_cast<size_t>(j) * 64) : ldg_nc_v4_hint(Kp + static_cast<size_t>(j) * 64, stream_policy))
+                        : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < kAttnDecUnroll; ++u) {
@@ -134,7 +160,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
     for (int u = 0; u < kAttnDecUnroll; ++u) {
       const int j = j0 + 16 * u;
       const bool ok = j < nkeys;
-      vv[u] = ok ? ldg_nc_v4(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? (kSelf ? ldg_nc_v4(Vp + static_cast<size_t>(j) * 64) : ldg_nc_v4_hint(Vp + static_cast<size_t>(j) * 64, stream_policy))
+                 : make_uint4(0, 0, 0, 0);
       p[u] = ok ? s_scores[j] : 0.f;
     }
 #pragma unroll

@@ -258,6 +258,7 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool l2_prefetch = false;  // measured: no gain (189.4 vs 188.1 ms/batch), the weight fetch is not on the critical path. B200T5_L2PF=1: pull the next kernels' weights into L2 from the cross-attention kernel
   bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
                            // (measured: decode 201.5 -> 188.3 ms per batch); B200T5_SELF=warp selects one warp per (row, head)
   int small_prio = 0;  // B200T5_PRIO: launch priority of the latency-bound decode kernels (see launch_priority())
@@ -474,6 +475,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* pf_env = getenv("B200T5_L2PF")) h->l2_prefetch = atoi(pf_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
   if (const char* mg_env = getenv("B200T5_MEGA")) {
     int v[7];
@@ -1065,7 +1067,8 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   }
   if (h->self_block)  // 4 warps per (row, head): two memory round trips whatever t is
     CU_OK(h, launch_kernel(attn_decode_kernel<true>, dim3(v.nb * H), dim3(kAttnDecThreads), T * sizeof(float), s, pdl, v.dq, skv,
-                           skv + static_cast<size_t>(B) * I * T, v.dctx, H, T, nullptr, nullptr, step, p.dec_bias.as<float>()));
+                           skv + static_cast<size_t>(B) * I * T, v.dctx, H, T, nullptr, nullptr, step, p.dec_bias.as<float>(),
+                           L2Prefetch{}));
   else
     CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
                            dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
@@ -1096,9 +1099,27 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
     PrioGuard() : saved(launch_priority()) { launch_priority() = 0; }
     ~PrioGuard() { launch_priority() = saved; }
   } guard;
+  // weights of the kernels that follow (this layer's cross-O / wi / FF-out, the next layer's QKV / O / cross-Q)
+  L2Prefetch pf{};
+  if (h->l2_prefetch) {
+    const DecLayerW& w = h->dec[l];
+    auto add = [&](int k, const DevBuf& b) {
+      pf.ptr[k] = b.p;
+      pf.bytes[k] = static_cast<unsigned int>(b.bytes);
+    };
+    add(0, w.wco);
+    add(1, w.wi);
+    add(2, w.wff_o);
+    if (l + 1 < c.Ld) {
+      const DecLayerW& n = h->dec[l + 1];
+      add(3, n.wqkv);
+      add(4, n.wo);
+      add(5, n.wcq);
+    }
+  }
   CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
                          v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
-                         p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr));
+                         p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf));
   h->launches++;
   return B200T5_OK;
 }
@@ -1408,7 +1429,7 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_
       bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
       attn_decode_kernel<false><<<p.B * c.H, kAttnDecThreads, p.S * sizeof(float), s>>>(
           p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<bf16>(), c.H, p.S,
-          p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr);
+          p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr, L2Prefetch{});
     }
   };
   sweep();  // warm-up
@@ -1582,7 +1603,7 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
         static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,
-        Tk, extent, key_ok, nullptr, nullptr);
+        Tk, extent, key_ok, nullptr, nullptr, L2Prefetch{});
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "attn_decode: %s", cudaGetErrorString(e));
