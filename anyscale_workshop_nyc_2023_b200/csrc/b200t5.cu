@@ -26,6 +26,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm_splitk.cuh"
+#include "gemm_2cta.cuh"
 #include "decode_mega.cuh"
 
 using namespace b200;
@@ -162,6 +163,7 @@ struct GemmOp {
 struct EncLayerW {
   DevBuf ln0, ln1, wqkv, wo, wi, wff_o;  // wi interleaved for BN=256
   CUtensorMap tm_qkv, tm_o, tm_wi, tm_ffo;
+  CUtensorMap tm2_qkv, tm2_o, tm2_wi, tm2_ffo;  // box of 128 weight rows: each CTA of a pair stages half of a 256-wide tile
 };
 struct DecLayerW {
   DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved per N-tile of the decode wi GEMM
@@ -233,7 +235,7 @@ struct b200t5_ctx {
   std::map<std::string, std::unique_ptr<DevBuf>> raw;  // HF name -> bf16 copy (until finalize)
   std::map<std::string, std::vector<int64_t>> raw_shape;
   DevBuf shared, lm_head, enc_final_ln, dec_final_ln, enc_relbias, dec_relbias, wcrosskv;
-  CUtensorMap tm_lm, tm_crosskv;
+  CUtensorMap tm_lm, tm_crosskv, tm2_crosskv;
   std::vector<float> enc_relbias_h, dec_relbias_h;  // [nb][H] as float
   std::vector<EncLayerW> enc;
   std::vector<DecLayerW> dec;
@@ -258,6 +260,7 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool use_2cta = true;  // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
   bool l2_prefetch = false;  // measured: no gain (189.4 vs 188.1 ms/batch), the weight fetch is not on the critical path. B200T5_L2PF=1: pull the next kernels' weights into L2 from the cross-attention kernel
   bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
                            // (measured: decode 201.5 -> 188.3 ms per batch); B200T5_SELF=warp selects one warp per (row, head)
@@ -348,6 +351,14 @@ static cudaError_t run_gemm(b200t5_ctx* h, const GemmOp& g, const void* ep, cuda
   return cudaErrorInvalidValue;
 }
 
+// CTA-pair GEMM (encoder, 256 x 256 tiles)
+template <class Epi>
+static cudaError_t run_gemm_2cta(b200t5_ctx* h, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                                 const typename Epi::Params& ep, cudaStream_t s) {
+  h->launches++;
+  return launch_gemm_2cta<Epi>(tmA, tmB, M, N, K, ep, h->num_sms, s);
+}
+
 // split-K cluster GEMM (decode): Epi chosen by the caller, BN/split from the handle's choice
 template <class Epi>
 static cudaError_t run_gemm_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, const CUtensorMap& tmA,
@@ -377,6 +388,10 @@ static cudaError_t init_kernel_attrs() {
   PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
+  if ((e = prepare_gemm_2cta<EpiStore>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_2cta<EpiResidual>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_2cta<EpiGeglu>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_2cta<EpiCrossKV>()) != cudaSuccess) return e;
 #define PREPSK(BN, EPI) \
   if ((e = prepare_gemm_splitk<BN, EPI>()) != cudaSuccess) return e;
   PREPSK(64, EpiStore) PREPSK(128, EpiStore) PREPSK(64, EpiResidual) PREPSK(128, EpiResidual)
@@ -475,6 +490,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* pf_env = getenv("B200T5_L2PF")) h->l2_prefetch = atoi(pf_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
   if (const char* mg_env = getenv("B200T5_MEGA")) {
@@ -690,6 +706,10 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TMAP(h, &w.tm_o, w.wo.p, d, I, 256);
     TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, 256);
     TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, 256);
+    TMAP(h, &w.tm2_qkv, w.wqkv.p, 3 * I, d, 128);
+    TMAP(h, &w.tm2_o, w.wo.p, d, I, 128);
+    TMAP(h, &w.tm2_wi, w.wi.p, wi_rows, d, 128);
+    TMAP(h, &w.tm2_ffo, w.wff_o.p, d, F, 128);
   }
 
   CU_OK(h, h->wcrosskv.alloc(static_cast<size_t>(c.Ld) * 2 * I * d * sizeof(bf16)));
@@ -755,6 +775,7 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, bn_ffo);
   }
   TMAP(h, &h->tm_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 256);
+  TMAP(h, &h->tm2_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 128);
 
   h->raw.clear();
   h->raw_shape.clear();
@@ -988,7 +1009,8 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln0.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
     {
       EpiStore::Params ep{p.qkv.as<bf16>(), 3 * I};
-      CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
+      if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiStore>(h, p.tm_xn, w.tm2_qkv, M, 3 * I, d, ep, s));
+      else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
     }
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
       encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
@@ -1001,16 +1023,19 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     CU_OK(h, cudaGetLastError());
     {
       EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
-      CU_OK(h, run_gemm(h, mk(p.tm_ctx, w.tm_o, M, d, I, G_RES256, 0), &ep, s));
+      if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_ctx, w.tm2_o, M, d, I, ep, s));
+      else CU_OK(h, run_gemm(h, mk(p.tm_ctx, w.tm_o, M, d, I, G_RES256, 0), &ep, s));
     }
     CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln1.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
     {
       EpiGeglu::Params ep{p.hff.as<bf16>(), F, h->gelu_lut};
-      CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
+      if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiGeglu>(h, p.tm_xn, w.tm2_wi, M, wi_tiles * 256, d, ep, s));
+      else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
     }
     {
       EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
-      CU_OK(h, run_gemm(h, mk(p.tm_hff, w.tm_ffo, M, d, F, G_RES256, 0), &ep, s));
+      if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_hff, w.tm2_ffo, M, d, F, ep, s));
+      else CU_OK(h, run_gemm(h, mk(p.tm_hff, w.tm_ffo, M, d, F, G_RES256, 0), &ep, s));
     }
   }
   CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), h->enc_final_ln.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
@@ -1021,7 +1046,8 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
   EpiCrossKV::Params ep{p.cross_kv.as<bf16>(), p.B, c.H, p.S};
-  CU_OK(h, run_gemm(h, mk(p.tm_xn, h->tm_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, G_CROSSKV256, 0), &ep, s));
+  if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiCrossKV>(h, p.tm_xn, h->tm2_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, ep, s));
+  else CU_OK(h, run_gemm(h, mk(p.tm_xn, h->tm_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, G_CROSSKV256, 0), &ep, s));
   return B200T5_OK;
 }
 
@@ -1507,11 +1533,28 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
   if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+  if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn == 512 ? 128 : bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
   b200t5_ctx dummy;
   dummy.num_sms = sms;
   cudaError_t e = cudaErrorInvalidValue;
   bf16* Cb = static_cast<bf16*>(C);
+  if (bn == 512) {  // CTA-pair kernel, 256 x 256 tiles (gemm_2cta.cuh)
+    if (mode == 0) {
+      EpiStore::Params ep{Cb, N};
+      e = run_gemm_2cta<EpiStore>(&dummy, ta, tb, M, N, K, ep, s);
+    } else if (mode == 1) {
+      EpiResidual::Params ep{Cb, Cb, N};
+      e = run_gemm_2cta<EpiResidual>(&dummy, ta, tb, M, N, K, ep, s);
+    } else if (mode == 2) {
+      GeluLut lut;
+      int lrc = ensure_gelu_lut(nullptr, pow_mode, &lut);
+      if (lrc != B200T5_OK) return lrc;
+      EpiGeglu::Params ep{Cb, N / 2, lut};
+      e = run_gemm_2cta<EpiGeglu>(&dummy, ta, tb, M, N, K, ep, s);
+    }
+    if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm(pair, mode=%d): %s", mode, cudaGetErrorString(e));
+    return B200T5_OK;
+  }
   if (mode == 0) {
     EpiStore::Params ep{Cb, N};
     if (bn == 256) e = run_gemm(&dummy, mk(ta, tb, M, N, K, G_STORE256, 0), &ep, s);

@@ -133,7 +133,8 @@ int b200t5_relative_bucket(int relative_position, int bidirectional, int num_buc
 
 /* Single-kernel hooks: all pointers are device pointers, bf16 unless noted. */
 /* C[M,N] = bf16(A[M,K] W[N,K]^T) via the tcgen05 GEMM; mode 0 plain, 1 += residual R (in C),
- * 2 GeGLU (W rows interleaved per bn/2, C is [M,N/2]), 3 fp32 output (C is float*). bn in {32,64,128,256}. */
+ * 2 GeGLU (W rows interleaved per bn/2, C is [M,N/2]), 3 fp32 output (C is float*). bn in {32,64,128,256};
+ * bn = 512 selects the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles, GeGLU interleave per 128), modes 0-2. */
 int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
                      int pow_mode, void* stream);
 /* Same contract through the cluster split-K kernel the decode step uses (csrc/gemm_splitk.cuh):

@@ -36,6 +36,8 @@ def ulp_close(a, b, ulps=1.0):
     (128, 256, 64, 256), (128, 256, 128, 256), (256, 512, 768, 256), (300, 520, 264, 256),
     (4096, 2304, 768, 256), (8, 2304, 768, 64), (256, 768, 768, 32), (256, 768, 2048, 32),
     (256, 1000, 512, 128), (200, 136, 64, 64),
+    # bn = 512: CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles)
+    (256, 256, 64, 512), (512, 768, 768, 512), (4096, 2304, 768, 512), (300, 520, 264, 512), (1000, 1000, 2048, 512),
 ])
 def test_gemm_store(lib, M, N, K, bn):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -53,7 +55,8 @@ def test_gemm_store(lib, M, N, K, bn):
     assert exact > 0.995, exact
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(256, 768, 768, 32), (384, 512, 1024, 256), (130, 264, 128, 256)])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 768, 768, 32), (384, 512, 1024, 256), (130, 264, 128, 256),
+                                      (4096, 768, 2048, 512), (130, 264, 128, 512)])
 def test_gemm_residual(lib, M, N, K, bn):
     g = torch.Generator(device="cuda").manual_seed(11)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
@@ -105,23 +108,24 @@ def test_geglu_exhaustive(lib):
     assert ((out.float() == ref2.float()) | (out.view(torch.int16) == ref2.view(torch.int16))).all()
 
 
-@pytest.mark.parametrize("M,F,K,bn", [(256, 2048, 768, 64), (512, 1024, 512, 256), (100, 160, 128, 64)])
+@pytest.mark.parametrize("M,F,K,bn", [(256, 2048, 768, 64), (512, 1024, 512, 256), (100, 160, 128, 64), (4096, 2048, 768, 512)])
 def test_gemm_geglu(lib, M, F, K, bn):
     g = torch.Generator(device="cuda").manual_seed(5)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     W0 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
     W1 = (torch.randn(F, K, device="cuda", generator=g) * 0.1).bfloat16()
-    half = bn // 2
+    tile = 256 if bn == 512 else bn  # the pair kernel's tile is 256 wide
+    half = tile // 2
     ntiles = (F + half - 1) // half
-    Wi = torch.zeros(ntiles * bn, K, device="cuda", dtype=torch.bfloat16)
+    Wi = torch.zeros(ntiles * tile, K, device="cuda", dtype=torch.bfloat16)
     for j in range(ntiles):
         rows = min(half, F - j * half)
-        Wi[j * bn: j * bn + rows] = W0[j * half: j * half + rows]
-        Wi[j * bn + half: j * bn + half + rows] = W1[j * half: j * half + rows]
+        Wi[j * tile: j * tile + rows] = W0[j * half: j * half + rows]
+        Wi[j * tile + half: j * tile + half + rows] = W1[j * half: j * half + rows]
     out = torch.full((M, F), float("nan"), device="cuda", dtype=torch.bfloat16)
     # N passed = 2F so that the hook derives F = N/2; padded tile rows are zero weights
-    assert ntiles * bn == 2 * F or F % half != 0
-    _lib.check(lib.b200t5_test_gemm(DEV, P(A), P(Wi), P(out), M, 2 * F if F % half == 0 else ntiles * bn, K, bn, 2, 0, None))
+    assert ntiles * tile == 2 * F or F % half != 0
+    _lib.check(lib.b200t5_test_gemm(DEV, P(A), P(Wi), P(out), M, 2 * F if F % half == 0 else ntiles * tile, K, bn, 2, 0, None))
     torch.cuda.synchronize()
     if F % half != 0:
         pytest.skip("ragged F is exercised end-to-end only")
