@@ -8,14 +8,14 @@
 // mode each CTA stages its own 128 rows of A and only HALF of the weight tile (16 + 16 KB per
 // k-block): the operand traffic per SM drops by a third and the pipe can be kept busy.
 //
-// Roles per CTA (320 threads, as gemm.cuh): warp 0 = TMA producer, warp 1 = TMEM allocation and
-// (leader CTA only) the MMA issuer, warps 2..9 = epilogue. Barriers:
+// Roles per CTA (as gemm.cuh): warp 0 = TMA producer, warp 1 = TMEM allocation and (leader CTA
+// only) the MMA issuer, warps 2.. = epilogue (8, or 16 for GeGLU). Barriers:
 //   full[s]    leader's; armed by the leader's producer with the bytes of BOTH CTAs, completed by
 //              both CTAs' TMA loads (cp.async.bulk.tensor...cta_group::2 with the barrier address
 //              mapped into the leader CTA);
 //   empty[s]   one per CTA, released for both by tcgen05.commit...multicast::cluster (mask 0b11);
 //   tfull[a]   one per CTA (multicast commit): this CTA's 128 x 256 accumulator is complete;
-//   tempty[a]  leader's; 2 x 8 epilogue warps (the peer's arrive remotely) hand a buffer back.
+//   tempty[a]  leader's; the epilogue warps of both CTAs (the peer's arrive remotely) hand a buffer back.
 // TMEM: 512 columns per CTA (two accumulator buffers), allocated collectively with cta_group::2.
 #pragma once
 #include "gemm.cuh"
@@ -26,7 +26,12 @@ namespace b200 {
 constexpr int k2ctaBN = 256;
 constexpr int k2ctaStages = 6;
 constexpr int k2ctaStageBytes = kBM * kBK * 2 + 128 * kBK * 2;  // own A rows + own half of the weight tile: 32 KB
-constexpr int k2ctaThreads = 64 + 32 * 8;
+// epilogue warps per CTA: 8 (two per TMEM lane quarter); the GeGLU epilogue (a table lookup per output) takes 16
+template <class Epi>
+struct PairEpi {
+  static constexpr int kWarps = Epi::kPaired ? 16 : 8;
+  static constexpr int kThreads = 64 + 32 * kWarps;
+};
 constexpr int k2ctaSmemBytes = k2ctaStages * k2ctaStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiSmemBytes;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: the even CTA of the pair
 
@@ -64,7 +69,7 @@ DEVINL void tmem_dealloc_pair_512(uint32_t taddr) {
 
 // tmA: box 64 x 128 rows of A; tmB: box 64 x 128 rows of W. grid = 2 * pairs (persistent), cluster (2,1,1).
 template <class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2ctaThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairEpi<Epi>::kThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                          int K, typename Epi::Params ep) {
   constexpr int BN = k2ctaBN;
@@ -100,7 +105,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 16);  // 8 epilogue warps of each CTA of the pair
+        mbar_init(&tempty[i], 2 * PairEpi<Epi>::kWarps);  // the epilogue warps of both CTAs of the pair
       }
       mbar_fence_init();
     }
@@ -174,14 +179,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int part = (warp - 2) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64, 256);
+    Epi::prologue(ep, epi_smem, static_cast<int>(threadIdx.x) - 64, 32 * PairEpi<Epi>::kWarps);
     for (int tile = pair; tile < num_tiles; tile += npairs) {
       const int n_tile = tile % tiles_n, m_tile = tile / tiles_n;
       const int m = m_tile * 2 * kBM + rank * kBM + q * 32 + lane;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      Epi::template run<BN>(ep, taddr, m, m < M, n_tile, N, epi_smem, part, 2);
+      Epi::template run<BN>(ep, taddr, m, m < M, n_tile, N, epi_smem, part, PairEpi<Epi>::kWarps / 4);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[as]);
@@ -211,7 +216,7 @@ cudaError_t launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int
   const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + k2ctaBN - 1) / k2ctaBN);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm_bf16_tn_2cta_kernel<Epi><<<dim3(2 * pairs), dim3(k2ctaThreads), k2ctaSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_bf16_tn_2cta_kernel<Epi><<<dim3(2 * pairs), dim3(PairEpi<Epi>::kThreads), k2ctaSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
   return cudaGetLastError();
 }
 
