@@ -105,3 +105,28 @@ def test_sharding_roundtrip():
         assert restore_order(per_rank, n) == [f"b{i}" for i in range(n)]
     with pytest.raises(ValueError):
         shard_block_indices(4, 2, 2)
+
+
+def test_lean_preprocess_equals_reference_style_tokenisation():
+    """The lean tokenisation path (no per-row Python padding) must produce exactly the arrays of the reference's
+    `tokenizer(a, b, padding="max_length", truncation=True, return_tensors="np")` (JOB/utils.py:23-31), including
+    truncated pairs, empty strings and unicode."""
+    import pandas as pd
+
+    from anyscale_workshop_nyc_2023_b200 import preprocess
+    from anyscale_workshop_nyc_2023_b200.synth import synthetic_alpaca_rows
+    from anyscale_workshop_nyc_2023_b200.workload import ASSETS
+
+    tokdir = str(ASSETS / "tokenizer")
+    rows = pd.DataFrame(synthetic_alpaca_rows(200, seed=11))
+    extra = pd.DataFrame({
+        "instruction": ["", "x", "word " * 700, "short", "naive cafe \u00e9\u00e8 \u4f60\u597d"],
+        "input": ["", "", "tail " * 50, "other " * 900, "\t tabs  and   spaces \n"],
+    })
+    batch = pd.concat([rows[["instruction", "input"]], extra], ignore_index=True)
+    lean = preprocess.make_preprocess_function(tokdir, lean=True)(batch)
+    ref = preprocess.make_preprocess_function(tokdir, lean=False)(batch)
+    for k in ("input_ids", "attention_mask", "labels"):
+        assert lean[k].dtype == ref[k].dtype == np.int64 and lean[k].shape == ref[k].shape
+        assert np.array_equal(lean[k], ref[k]), k
+    assert lean["attention_mask"][-3].sum() == lean["input_ids"].shape[1]  # a truncated pair fills the row
