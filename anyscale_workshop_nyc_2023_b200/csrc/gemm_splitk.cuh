@@ -19,7 +19,9 @@
 // uses (gemm.cuh), so the T5 rounding contract is shared.
 // (Measured alternative: st.async with a receiver-side mbarrier instead of the release fence +
 // cluster barrier - the fence/barrier pair is ~30 % of this kernel's stall samples - was slower,
-// 194.8 vs 188.3 ms per batch: thousands of 16-byte complete_tx updates serialise on the barrier.)
+// 194.8 vs 188.3 ms per batch: thousands of 16-byte complete_tx updates serialise on the barrier; staging
+// the rows locally and moving them with one cp.async.bulk (shared::cta -> shared::cluster) per destination
+// rank was slower too, 195.3 ms: the extra staging pass and the exit barrier outweigh the saved fence.)
 #pragma once
 #include "gemm.cuh"
 
