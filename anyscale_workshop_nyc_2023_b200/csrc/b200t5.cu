@@ -184,6 +184,7 @@ struct Plan {
   DevBuf cross_kv;                      // [Ld][2][B][H][S][64]
   // decoder workspace
   DevBuf dx, dxn, dq, dctx, dh;         // [B,d], [B,d], [B,I], [B,I], [B,F]
+  DevBuf dss;                           // float [B][ceil(d/32)]: sums of squares of x per 32-column chunk (fused RMSNorm)
   DevBuf self_kv;                       // [Ld][2][B][H][Tmax][64]
   DevBuf dec_bias;                      // float [H][Tmax]
   DevBuf pval, pidx;                    // [B][n_tiles]
@@ -195,7 +196,7 @@ struct Plan {
   // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
   struct Chain {
     int b0 = 0, nb = 0;
-    CUtensorMap tm_dxn, tm_dctx, tm_dh;
+    CUtensorMap tm_dxn, tm_dctx, tm_dh, tm_dx;
   };
   int n_chains = 1;
   Chain chains[kMaxChains];
@@ -260,6 +261,8 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool fuse_norm = false;  // B200T5_FUSENORM=1: RMSNorm applied to the A tile inside the consumer split-K GEMM. Correct (tests) but
+                          // measured slower than the separate, PDL-overlapped norm kernels: 201.1 vs 189.1 ms per batch
   bool use_2cta = true;  // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
   bool l2_prefetch = false;  // measured: no gain (189.4 vs 188.1 ms/batch), the weight fetch is not on the critical path. B200T5_L2PF=1: pull the next kernels' weights into L2 from the cross-attention kernel
   bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
@@ -370,6 +373,17 @@ static cudaError_t run_gemm_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, co
   return launch_gemm_splitk<64, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl);
 }
 
+// same, with the RMSNorm of the A operand fused in (A = raw residual stream)
+template <class Epi>
+static cudaError_t run_gemm_sk_norm(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, const CUtensorMap& tmA,
+                                    const CUtensorMap& tmB, int M, int N, int K, const typename Epi::Params& ep,
+                                    const NormA& na, cudaStream_t s, bool pdl) {
+  h->launches++;
+  const int split = splitk_factor(K, ch.split);
+  if (ch.bn == 128) return launch_gemm_splitk<128, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
+  return launch_gemm_splitk<64, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
+}
+
 static cudaError_t run_rmsnorm(b200t5_ctx* h, const bf16* x, const bf16* w, bf16* y, int M, int d, float eps,
                                cudaStream_t s, bool pdl = false) {
   if (h) h->launches++;
@@ -397,6 +411,11 @@ static cudaError_t init_kernel_attrs() {
   PREPSK(64, EpiStore) PREPSK(128, EpiStore) PREPSK(64, EpiResidual) PREPSK(128, EpiResidual)
   PREPSK(64, EpiQkvDecode) PREPSK(128, EpiQkvDecode) PREPSK(64, EpiGeglu) PREPSK(128, EpiGeglu)
 #undef PREPSK
+#define PREPSKN(BN, EPI) \
+  if ((e = prepare_gemm_splitk<BN, EPI, true>()) != cudaSuccess) return e;
+  PREPSKN(64, EpiStore) PREPSKN(128, EpiStore) PREPSKN(64, EpiQkvDecode) PREPSKN(128, EpiQkvDecode)
+  PREPSKN(64, EpiGeglu) PREPSKN(128, EpiGeglu)
+#undef PREPSKN
   if ((e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmemBytes)) != cudaSuccess)
     return e;
   if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -490,6 +509,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* fn_env = getenv("B200T5_FUSENORM")) h->fuse_norm = atoi(fn_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* pf_env = getenv("B200T5_L2PF")) h->l2_prefetch = atoi(pf_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
@@ -914,6 +934,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->dq.alloc(static_cast<size_t>(B) * I * 2));
   CU_OK(h, pl->dctx.alloc(static_cast<size_t>(B) * I * 2));
   CU_OK(h, pl->dh.alloc(static_cast<size_t>(B) * F * 2));
+  CU_OK(h, pl->dss.alloc(static_cast<size_t>(B) * ((d + 31) / 32) * 4));
   CU_OK(h, pl->self_kv.alloc(static_cast<size_t>(c.Ld) * 2 * B * I * Tmax * 2));
   pl->n_vtiles = (c.V + 127) / 128;
   CU_OK(h, pl->pval.alloc(static_cast<size_t>(B) * pl->n_vtiles * 4));
@@ -964,6 +985,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
       ch.b0 = static_cast<int>(static_cast<long long>(B) * i / nc);
       ch.nb = static_cast<int>(static_cast<long long>(B) * (i + 1) / nc) - ch.b0;
       TMAP(h, &ch.tm_dxn, pl->dxn.as<bf16>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
+      TMAP(h, &ch.tm_dx, pl->dx.as<bf16>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
       TMAP(h, &ch.tm_dctx, pl->dctx.as<bf16>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
       TMAP(h, &ch.tm_dh, pl->dh.as<bf16>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
     }
@@ -1085,10 +1107,19 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   DecLayerW& w = h->dec[l];
   // [kv][B][H][T][64]: a row offset of b0 is a pointer offset inside each kv plane
   bf16* skv = p.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
-  CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  // Fused RMSNorm: the residual GEMM that produced x left per-chunk sums of squares in `ss`; the consumer GEMM
+  // normalises its A tile in shared memory (gemm_splitk.cuh, NormA). Layer 0's x comes from the embedding
+  // gather (no producer GEMM), so its first norm stays a kernel.
+  const bool fuse = h->fuse_norm && h->sk_on;
+  const int ss_ld = (d + 31) / 32;
+  float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
+  if (!(fuse && l > 0)) CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T};
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
+    if (fuse && l > 0)
+      CU_OK(h, run_gemm_sk_norm<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dx, w.tm_qkv, v.nb, 3 * I, d, ep,
+                                              NormA{ss, ss_ld, w.ln0.as<bf16>(), c.eps}, s, pdl));
+    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
   if (h->self_block)  // 4 warps per (row, head): two memory round trips whatever t is
@@ -1102,13 +1133,20 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   h->launches++;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
+    if (fuse) {
+      ep.ss = ss;
+      ep.ss_ld = ss_ld;
+    }
     if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiStore::Params ep{v.dq, I};
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
+    if (fuse)
+      CU_OK(h, run_gemm_sk_norm<EpiStore>(h, h->sk_proj, v.ch->tm_dx, w.tm_cq, v.nb, I, d, ep,
+                                          NormA{ss, ss_ld, w.ln1.as<bf16>(), c.eps}, s, pdl));
+    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
@@ -1157,19 +1195,34 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
   const bool pdl = h->use_pdl;
   const int wi_tiles = (F + 31) / 32;
   DecLayerW& w = h->dec[l];
+  Plan& p = *h->plan;
+  const bool fuse = h->fuse_norm && h->sk_on;
+  const int ss_ld = (d + 31) / 32;
+  float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
+    if (fuse) {
+      ep.ss = ss;
+      ep.ss_ld = ss_ld;
+    }
     if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiGeglu::Params ep{v.dh, F, h->gelu_lut};
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
+    if (fuse)
+      CU_OK(h, run_gemm_sk_norm<EpiGeglu>(h, h->sk_wi, v.ch->tm_dx, w.tm_wi, v.nb, w.wi_rows, d, ep,
+                                          NormA{ss, ss_ld, w.ln2.as<bf16>(), c.eps}, s, pdl));
+    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
   }
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
+    if (fuse) {  // consumed by the next layer's QKV GEMM
+      ep.ss = ss;
+      ep.ss_ld = ss_ld;
+    }
     if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_ffo, v.ch->tm_dh, w.tm_ffo, v.nb, d, F, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dh, w.tm_ffo, v.nb, d, F, G_RES32, 1), &ep, s, pdl));
   }
@@ -1601,7 +1654,19 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
     e = run_gemm_sk<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
   } else if (mode == 1) {
     EpiResidual::Params ep{Cb, Cb, N};
+    if (aux) {  // also emit the per-chunk sums of squares: float [M][ceil(N/32)]
+      ep.ss = static_cast<float*>(aux);
+      ep.ss_ld = (N + 31) / 32;
+    }
     e = run_gemm_sk<EpiResidual>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
+  } else if (mode == 5) {
+    // fused RMSNorm on A: aux = float ss[M][ceil(K/32)] followed by bf16 w[K]; eps 1e-6
+    if (!aux) return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: mode 5 needs aux");
+    const int ss_ld = (K + 31) / 32;
+    const float* ssp = static_cast<const float*>(aux);
+    const bf16* wln = reinterpret_cast<const bf16*>(ssp + static_cast<size_t>(M) * ss_ld);
+    EpiStore::Params ep{Cb, N};
+    e = run_gemm_sk_norm<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, NormA{ssp, ss_ld, wln, 1e-6f}, s, false);
   } else if (mode == 2) {
     GeluLut lut;
     int lrc = ensure_gelu_lut(nullptr, pow_mode, &lut);

@@ -284,6 +284,10 @@ struct EpiResidual {
     __nv_bfloat16* C;
     const __nv_bfloat16* R;
     int ld;
+    // optional: sum of squares of the 32 outputs of each (row, chunk) -> ss[m * ss_ld + n0 / 32], for a
+    // consumer GEMM that applies the following RMSNorm to its A operand (gemm_splitk.cuh, NormA)
+    float* ss = nullptr;
+    int ss_ld = 0;
   };
   static constexpr bool kPaired = false;
   struct ChunkPre {
@@ -311,6 +315,18 @@ struct EpiResidual {
       }
     }
     store_row_chunk(p.C + static_cast<size_t>(m) * p.ld + n0, o, n0, N);
+    if (p.ss) {
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (n0 + 2 * i + 2 <= N) {
+          const float a = bf16_lo(o[i]), b = bf16_hi(o[i]);
+          sq = fmaf(a, a, sq);
+          sq = fmaf(b, b, sq);
+        }
+      }
+      p.ss[static_cast<size_t>(m) * p.ss_ld + (n0 >> 5)] = sq;
+    }
   }
   template <int BN>
   static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,

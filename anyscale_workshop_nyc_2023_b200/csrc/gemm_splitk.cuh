@@ -65,11 +65,27 @@ DEVINL void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uin
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Optional fused T5LayerNorm on the A operand (kNormA): A is the RAW residual stream x and the tile the tensor
+// core consumes is xn = bf16(w * bf16(x * rstd)) (modeling_t5.py:55-68), produced in place in shared memory by
+// the four epilogue warps - idle during the main loop - between the TMA completion and the MMA (one tile row
+// per thread, 16-byte units in the 128-B swizzle). rstd comes from per-(row, 32-column chunk) sums of squares
+// that the residual epilogue of the PREVIOUS GEMM left in `ss` (EpiResidual::Params::ss), added in a fixed
+// order. This removes a separate RMSNorm launch before the QKV, cross-Q and wi products of every decoder
+// layer - but measured on B200 it LOSES (201.1 vs 189.1 ms per batch): the partial-sum fetch and the
+// TMA -> transform -> MMA serialisation add more to each GEMM's critical path than the PDL-overlapped norm
+// kernel costs. Kept as an opt-in (B200T5_FUSENORM=1) with its parity test.
+struct NormA {
+  const float* ss;            // [M][ss_ld] partial sums of squares of x
+  int ss_ld;                  // = d / 32
+  const __nv_bfloat16* w;     // [K] layer-norm weight
+  float eps;
+};
+
 // grid = (S, tiles_n, tiles_m), cluster = (S, 1, 1); S in {1,2,4,8} divides 128.
-template <int BN, class Epi>
+template <int BN, class Epi, bool kNormA = false>
 __global__ void __launch_bounds__(kSkThreads, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                   int K, typename Epi::Params ep) {
+                   int K, typename Epi::Params ep, const NormA na) {
   using Cfg = SkCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,7 +93,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* ready = tfull + 1;  // [stages] kNormA: the A tile of the stage has been normalised in place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + Cfg::kStages);
   float* red = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
   uint8_t* epi_smem = reinterpret_cast<uint8_t*>(red) + Cfg::kRedBytes;
 
@@ -104,6 +121,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int i = 0; i < Cfg::kStages; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
+        mbar_init(&ready[i], 128);
       }
       mbar_init(tfull, 1);
       mbar_fence_init();
@@ -153,7 +171,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(kNormA ? &ready[stage] : &full[stage], phase);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
@@ -186,6 +204,47 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int kChunks = Epi::kPaired ? BN / 64 : BN / 32;
     const int items = rows_per * kChunks;
     pdl_wait();
+    if constexpr (kNormA) {
+      // this thread's tile row: 1/rms from the previous epilogue's partial sums, then normalise stage by stage
+      const int m = m0 + row;
+      float ssum = 0.f;
+      if (m < M) {
+        const float* sp = na.ss + static_cast<size_t>(m) * na.ss_ld;
+        for (int c = 0; c < na.ss_ld; ++c) ssum += sp[c];  // fixed order: deterministic
+      }
+      const float inv = rsqrtf(ssum / static_cast<float>(K) + na.eps);  // the normalised width is this GEMM's K
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full[st], ph);
+        const uint32_t rbase = smem_u32(smem + st * Cfg::kStageBytes) + row * 128;
+        const int k0 = (kb0 + i) * kBK;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t addr = rbase + ((u ^ (row & 7)) << 4);  // 128-B swizzle: 16-B unit u of row r sits at u ^ (r & 7)
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+          const int k = k0 + u * 8;
+          const uint4 wv = k + 8 <= K ? *reinterpret_cast<const uint4*>(na.w + k) : make_uint4(0, 0, 0, 0);
+          const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t wsv[4] = {wv.x, wv.y, wv.z, wv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = bf16_round(bf16_lo(xs[j]) * inv);
+            const float b = bf16_round(bf16_hi(xs[j]) * inv);
+            o[j] = pack_bf16x2(bf16_lo(wsv[j]) * a, bf16_hi(wsv[j]) * b);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
+        mbar_arrive(&ready[st]);
+        if (++st == Cfg::kStages) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+    }
     // the first work item's accumulator-independent operands (residual row) are fetched now
     typename Epi::ChunkPre pre0;
     {
@@ -271,12 +330,12 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, bool kNormA = false>
 cudaError_t prepare_gemm_splitk() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SkCfg<BN>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 // Largest split in {8,4,2,1} not above `want` that leaves every rank at least one k-block.
@@ -289,9 +348,9 @@ inline int splitk_factor(int K, int want) {
   return 1;
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, bool kNormA = false>
 cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int split,
-                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl) {
+                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl, const NormA& norm = NormA{}) {
   using Cfg = SkCfg<BN>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(split, (N + BN - 1) / BN, (M + kBM - 1) / kBM);
@@ -317,7 +376,7 @@ cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, i
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi>, tmA, tmB, M, N, K, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi, kNormA>, tmA, tmB, M, N, K, ep, norm);
 }
 
 }  // namespace b200

@@ -139,8 +139,10 @@ int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, i
                      int pow_mode, void* stream);
 /* Same contract through the cluster split-K kernel the decode step uses (csrc/gemm_splitk.cuh):
  * bn in {64,128}; split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
- * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C), 2 GeGLU, 4 decoder QKV: C is the q
- * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written. */
+ * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C; a non-NULL `aux` also receives the sums of
+ * squares of every 32-column output chunk, float [M][ceil(N/32)]), 2 GeGLU, 4 decoder QKV: C is the q
+ * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written, 5 plain store
+ * with the T5 RMSNorm of A fused in: `aux` = float ss[M][ceil(K/32)] followed by the bf16 norm weight [K]. */
 int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int split,
                             int mode, int pow_mode, void* aux, int Tmax, int step, void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);

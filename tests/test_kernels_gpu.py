@@ -227,6 +227,42 @@ def test_gemm_splitk_qkv_append(lib, B, H, K, bn, split, Tmax, step):
     assert (cache[:, :, :, other] == 0).all()  # no other cache row is touched
 
 
+@pytest.mark.parametrize("M,N,K,bn,split", [(256, 768, 768, 64, 4), (256, 4096, 768, 128, 2), (100, 1152, 512, 64, 2), (8, 384, 1024, 64, 4)])
+def test_gemm_splitk_fused_rmsnorm(lib, M, N, K, bn, split):
+    """Producer: the residual epilogue emits per-32-column sums of squares of x; consumer: the GEMM normalises its
+    A tile in shared memory. Together they must equal T5LayerNorm (modeling_t5.py:55-68) followed by the Linear."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    # producer: x = R + bf16(A0 W0^T), ss = chunk sums of squares
+    K0 = 256
+    A0 = (torch.randn(M, K0, device="cuda", generator=g) * 0.5).bfloat16()
+    W0 = (torch.randn(K, K0, device="cuda", generator=g) * 0.2).bfloat16()
+    R = (torch.randn(M, K, device="cuda", generator=g) * 2).bfloat16()
+    x = R.clone()
+    ss_ld = (K + 31) // 32
+    wln = (1 + 0.1 * torch.randn(K, device="cuda", generator=g)).bfloat16()
+    aux = torch.zeros(M * ss_ld * 4 + K * 2 + 64, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A0), P(W0), P(x), M, K, K0, 64, 4, 1, 0, P(aux), 0, 0, None))
+    torch.cuda.synchronize()
+    ss = aux[: M * ss_ld * 4].view(torch.float32).view(M, ss_ld)
+    ref_ss = x.float().pow(2).view(M, ss_ld, 32).sum(-1) if K % 32 == 0 else None
+    if ref_ss is not None:
+        assert torch.allclose(ss, ref_ss, rtol=1e-5, atol=1e-6)
+    # consumer
+    aux[M * ss_ld * 4: M * ss_ld * 4 + K * 2] = wln.view(torch.uint8)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.3).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(x), P(W), P(out), M, N, K, bn, split, 5, 0, P(aux), 0, 0, None))
+    torch.cuda.synchronize()
+    var = x.float().pow(2).mean(-1, keepdim=True)
+    xn = wln * (x * torch.rsqrt(var + 1e-6)).to(torch.bfloat16)
+    ref32 = xn.float() @ W.float().T
+    assert torch.isfinite(out.float()).all()
+    ok = ulp_close(out, ref32.bfloat16(), 1.0) | ((out.float() - ref32).abs() <= 2e-3)
+    # 1/rms differs from torch's by at most an fp32 ulp (summation order), which can flip a bf16 rounding of xn
+    assert ok.float().mean().item() > 0.999, (out.float() - ref32).abs().max().item()
+    assert (out == ref32.bfloat16()).float().mean().item() > 0.98
+
+
 def test_gemm_logits_f32(lib):
     M, N, K = 256, 1000, 512
     g = torch.Generator(device="cuda").manual_seed(9)
