@@ -27,6 +27,7 @@
 #include "gemm.cuh"
 #include "gemm_splitk.cuh"
 #include "gemm_2cta.cuh"
+#include "gemm_mcast.cuh"
 #include "decode_mega.cuh"
 
 using namespace b200;
@@ -168,6 +169,7 @@ struct EncLayerW {
 struct DecLayerW {
   DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved per N-tile of the decode wi GEMM
   CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
+  CUtensorMap tm16_o, tm16_cq, tm16_co;  // box of 16 weight rows: gemm_mcast.cuh
   int wi_rows = 0;
   DevBuf mega_wi_own;  // wi interleaved for the persistent kernel's tile when it differs from `wi`
   void* mega_wi = nullptr;
@@ -261,6 +263,9 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool mcast = false;  // B200T5_MCAST=1: decode O / cross-Q / cross-O products through the A-multicast kernel (gemm_mcast.cuh).
+                      // Correct (tests) but slower than split-K (201.4 vs 191.0 ms per batch): multicast saves L2 reads, not the
+                      // bytes each SM has to take in (196 KB of A per CTA), and that ingest rate is what bounds these kernels
   bool fuse_norm = false;  // B200T5_FUSENORM=1: RMSNorm applied to the A tile inside the consumer split-K GEMM. Correct (tests) but
                           // measured slower than the separate, PDL-overlapped norm kernels: 201.1 vs 189.1 ms per batch
   bool use_2cta = true;  // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
@@ -402,6 +407,7 @@ static cudaError_t init_kernel_attrs() {
   PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
+  if ((e = prepare_gemm_mcast()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiStore>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiResidual>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiGeglu>()) != cudaSuccess) return e;
@@ -509,6 +515,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* mc_env = getenv("B200T5_MCAST")) h->mcast = atoi(mc_env) != 0;
   if (const char* fn_env = getenv("B200T5_FUSENORM")) h->fuse_norm = atoi(fn_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* pf_env = getenv("B200T5_L2PF")) h->l2_prefetch = atoi(pf_env) != 0;
@@ -793,6 +800,9 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TMAP(h, &w.tm_co, w.wco.p, d, I, bn_proj);
     TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, bn_wi);
     TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, bn_ffo);
+    TMAP(h, &w.tm16_o, w.wo.p, d, I, 16);
+    TMAP(h, &w.tm16_cq, w.wcq.p, I, d, 16);
+    TMAP(h, &w.tm16_co, w.wco.p, d, I, 16);
   }
   TMAP(h, &h->tm_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 256);
   TMAP(h, &h->tm2_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 128);
@@ -1137,7 +1147,10 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
       ep.ss = ss;
       ep.ss_ld = ss_ld;
     }
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
+    if (h->sk_on && h->mcast && !fuse && gemm_mcast_supports(d, I)) {
+      h->launches++;
+      CU_OK(h, launch_gemm_mcast<true>(v.ch->tm_dctx, w.tm16_o, v.nb, d, I, ep, EpiStore::Params{}, s, pdl));
+    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
   if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
@@ -1146,7 +1159,10 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
     if (fuse)
       CU_OK(h, run_gemm_sk_norm<EpiStore>(h, h->sk_proj, v.ch->tm_dx, w.tm_cq, v.nb, I, d, ep,
                                           NormA{ss, ss_ld, w.ln1.as<bf16>(), c.eps}, s, pdl));
-    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
+    else if (h->sk_on && h->mcast && gemm_mcast_supports(I, d)) {
+      h->launches++;
+      CU_OK(h, launch_gemm_mcast<false>(v.ch->tm_dxn, w.tm16_cq, v.nb, I, d, EpiResidual::Params{}, ep, s, pdl));
+    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
@@ -1205,7 +1221,10 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
       ep.ss = ss;
       ep.ss_ld = ss_ld;
     }
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
+    if (h->sk_on && h->mcast && !fuse && gemm_mcast_supports(d, I)) {
+      h->launches++;
+      CU_OK(h, launch_gemm_mcast<true>(v.ch->tm_dctx, w.tm16_co, v.nb, d, I, ep, EpiStore::Params{}, s, pdl));
+    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
   if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
@@ -1638,9 +1657,20 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
-  if ((bn != 64 && bn != 128) || (split != 1 && split != 2 && split != 4 && split != 8))
-    return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bn in {64,128}, split in {1,2,4,8}");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bn == 16) {  // A-multicast kernel (gemm_mcast.cuh): modes 0 (store) and 1 (+= residual), split ignored
+    if (!gemm_mcast_supports(N, K) || (mode != 0 && mode != 1))
+      return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk(bn=16): needs K <= 768, N %% 64 == 0, mode 0 or 1");
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, 16)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+    bf16* Cb = static_cast<bf16*>(C);
+    cudaError_t e = mode == 0 ? launch_gemm_mcast<false>(ta, tb, M, N, K, EpiResidual::Params{}, EpiStore::Params{Cb, N}, s, false)
+                              : launch_gemm_mcast<true>(ta, tb, M, N, K, EpiResidual::Params{Cb, Cb, N}, EpiStore::Params{}, s, false);
+    if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm_splitk(bn=16, mode=%d): %s", mode, cudaGetErrorString(e));
+    return B200T5_OK;
+  }
+  if ((bn != 64 && bn != 128) || (split != 1 && split != 2 && split != 4 && split != 8))
+    return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bn in {16,64,128}, split in {1,2,4,8}");
   CUtensorMap ta, tb;
   if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
   b200t5_ctx dummy;

@@ -138,7 +138,8 @@ int b200t5_relative_bucket(int relative_position, int bidirectional, int num_buc
 int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
                      int pow_mode, void* stream);
 /* Same contract through the cluster split-K kernel the decode step uses (csrc/gemm_splitk.cuh):
- * bn in {64,128}; split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
+ * bn in {64,128} (bn = 16 selects the A-multicast kernel of csrc/gemm_mcast.cuh instead: K <= 768, N % 64 == 0,
+ * modes 0 and 1, `split` ignored); split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
  * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C; a non-NULL `aux` also receives the sums of
  * squares of every 32-column output chunk, float [M][ceil(N/32)]), 2 GeGLU, 4 decoder QKV: C is the q
  * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written, 5 plain store

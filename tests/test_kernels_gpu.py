@@ -227,6 +227,26 @@ def test_gemm_splitk_qkv_append(lib, B, H, K, bn, split, Tmax, step):
     assert (cache[:, :, :, other] == 0).all()  # no other cache row is touched
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (128, 768, 768), (64, 384, 512), (8, 512, 384), (300, 1024, 704), (256, 64, 64)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gemm_multicast(lib, M, N, K, mode):
+    """A-multicast cluster kernel (csrc/gemm_mcast.cuh, bn = 16): four CTAs share one copy of the A tile, no
+    reduction; plain store and += residual."""
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N + K + mode)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.3).bfloat16()
+    R = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    Cio = R.clone() if mode == 1 else torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(Cio), M, N, K, 16, 1, mode, 0, None, 0, 0, None))
+    torch.cuda.synchronize()
+    y = (A.float() @ W.float().T).bfloat16()
+    ref = (R.float() + y.float()).bfloat16() if mode == 1 else y
+    assert torch.isfinite(Cio.float()).all()
+    tol = 2.0 ** -7 * (y.float().abs() + ref.float().abs()) + 1e-3
+    assert ((Cio.float() - ref.float()).abs() <= tol).all()
+    assert (Cio == ref).float().mean().item() > 0.99
+
+
 @pytest.mark.parametrize("M,N,K,bn,split", [(256, 768, 768, 64, 4), (256, 4096, 768, 128, 2), (100, 1152, 512, 64, 2), (8, 384, 1024, 64, 4)])
 def test_gemm_splitk_fused_rmsnorm(lib, M, N, K, bn, split):
     """Producer: the residual epilogue emits per-32-column sums of squares of x; consumer: the GEMM normalises its
