@@ -64,6 +64,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
                        const float* __restrict__ rel_bias,         // [H][2S-1], index j - i + S - 1
                        const unsigned char* __restrict__ key_ok,   // [B][S]
                        const int* __restrict__ extent,             // [B]
+                       const int* __restrict__ cu,                 // packed rows: prompt b starts at row cu[b] (NULL: b * S)
                        int S, int H) {
   extern __shared__ uint8_t enc_tc_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(enc_tc_raw) + 1023) & ~uintptr_t(1023));
@@ -139,7 +140,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- loads: Q tile, K and V chunks of this (b,h)
-      const int row0 = b * S;
+      const int row0 = cu ? cu[b] : b * S;
       mbar_arrive_expect_tx(bar_load, 16384u * (1 + 2 * nchunks));
       tma_load_2d(sQ, &tmQKV, bar_load, h * 64, row0 + i0);
       for (int c = 0; c < nchunks; ++c) {
@@ -307,11 +308,11 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       tmem_ld_32x16(trow + part * 16, o);
       tmem_ld_wait();
       const int i = i0 + il;
-      if (i < S) {
+      if (i < ext) {  // rows beyond the prompt's extent are padding (in the packed layout: another prompt's rows)
         uint32_t pkd[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) pkd[t] = pack_bf16x2(__uint_as_float(o[2 * t]), __uint_as_float(o[2 * t + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + i) * I + h * 64 + part * 16);
+        uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(cu ? cu[b] : b * S) + i) * I + h * 64 + part * 16);
         dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
         dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
       }

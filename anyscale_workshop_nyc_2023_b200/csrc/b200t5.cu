@@ -183,6 +183,10 @@ struct Plan {
   // encoder workspace
   DevBuf x, xn, qkv, ctx, hff;          // [B*S, d], [B*S, d], [B*S, 3I], [B*S, I], [B*S, F]
   DevBuf key_ok, extent, enc_bias;      // uint8 [B,S], int [B], float [H][2S-1]
+  DevBuf cu, row_b, row_s;              // packed encoder rows: int [B+1] offsets, int [B*S] row -> (prompt, position)
+  int* h_cu = nullptr;                  // pinned copy of cu[B] (number of packed rows)
+  int packed_rows = 0;                  // rows the last encoder pass ran on
+  bool packed = false;
   DevBuf cross_kv;                      // [Ld][2][B][H][S][64]
   // decoder workspace
   DevBuf dx, dxn, dq, dctx, dh;         // [B,d], [B,d], [B,I], [B,I], [B,F]
@@ -226,6 +230,7 @@ struct Plan {
     if (h_out) cudaFreeHost(h_out);
     if (h_len) cudaFreeHost(h_len);
     if (h_state) cudaFreeHost(h_state);
+    if (h_cu) cudaFreeHost(h_cu);
   }
 };
 
@@ -263,6 +268,7 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool pack_rows = true;  // encoder on the valid rows only (variable-length packing); B200T5_PACK=0: all B*S rows as the reference does
   bool mcast = false;  // B200T5_MCAST=1: decode O / cross-Q / cross-O products through the A-multicast kernel (gemm_mcast.cuh).
                       // Correct (tests) but slower than split-K (201.4 vs 191.0 ms per batch): multicast saves L2 reads, not the
                       // bytes each SM has to take in (196 KB of A per CTA), and that ingest rate is what bounds these kernels
@@ -515,6 +521,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
   if (const char* mc_env = getenv("B200T5_MCAST")) h->mcast = atoi(mc_env) != 0;
   if (const char* fn_env = getenv("B200T5_FUSENORM")) h->fuse_norm = atoi(fn_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
@@ -938,6 +945,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->hff.alloc(M * F * 2));
   CU_OK(h, pl->key_ok.alloc(M));
   CU_OK(h, pl->extent.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->cu.alloc(static_cast<size_t>(B + 1) * 4));
+  CU_OK(h, pl->row_b.alloc(M * 4));
+  CU_OK(h, pl->row_s.alloc(M * 4));
+  CU_OK(h, cudaMallocHost(&pl->h_cu, 16));
   CU_OK(h, pl->cross_kv.alloc(static_cast<size_t>(c.Ld) * 2 * M * I * 2));
   CU_OK(h, pl->dx.alloc(static_cast<size_t>(B) * d * 2));
   CU_OK(h, pl->dxn.alloc(static_cast<size_t>(B) * d * 2));
@@ -1028,10 +1039,28 @@ static GemmOp mk(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K
 static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mask, cudaStream_t s) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
-  const int B = p.B, S = p.S, M = B * S, d = c.d, I = c.I, F = c.F, H = c.H;
+  const int B = p.B, S = p.S, d = c.d, I = c.I, F = c.F, H = c.H;
+  int M = B * S;
   prep_mask_kernel<<<B, 128, 0, s>>>(mask, p.key_ok.as<unsigned char>(), p.extent.as<int>(), B, S);
-  embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), M, d, c.V);
-  h->launches += 2;
+  h->launches++;
+  // Variable-length packing: only rows below extent[b] are ever read downstream, so the encoder runs on those
+  // (elementwise.cuh). The number of packed rows sizes the GEMM grids, hence one 4-byte read-back per call.
+  p.packed = h->pack_rows && h->enc_attn_tc && S <= kEncTcMaxS;
+  const int* cu = nullptr;
+  if (p.packed) {
+    pack_offsets_kernel<<<1, 256, 0, s>>>(p.extent.as<int>(), p.cu.as<int>(), B);
+    CU_OK(h, cudaMemcpyAsync(p.h_cu, p.cu.as<int>() + B, 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(h, cudaStreamSynchronize(s));
+    M = *p.h_cu;
+    cu = p.cu.as<int>();
+    embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), cu, p.row_b.as<int>(),
+                                                               p.row_s.as<int>(), S, d, c.V);
+    h->launches += 2;
+  } else {
+    embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), M, d, c.V);
+    h->launches++;
+  }
+  p.packed_rows = M;
   CU_OK(h, cudaGetLastError());
   const size_t attn_smem = encoder_attn_smem_bytes(S);
   if (attn_smem > 96 * 1024) return fail(h, B200T5_EINVAL, "encoder length S=%d too long for the attention kernel", S);
@@ -1046,7 +1075,7 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     }
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
       encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
-          p.tm_qkv_attn, p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+          p.tm_qkv_attn, p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H);
     } else {
       encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
           p.qkv.as<bf16>(), p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
@@ -1078,8 +1107,13 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
   EpiCrossKV::Params ep{p.cross_kv.as<bf16>(), p.B, c.H, p.S};
-  if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiCrossKV>(h, p.tm_xn, h->tm2_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, ep, s));
-  else CU_OK(h, run_gemm(h, mk(p.tm_xn, h->tm_crosskv, p.B * p.S, c.Ld * 2 * c.I, c.d, G_CROSSKV256, 0), &ep, s));
+  if (p.packed) {
+    ep.row_b = p.row_b.as<int>();
+    ep.row_s = p.row_s.as<int>();
+  }
+  const int M = p.packed ? p.packed_rows : p.B * p.S;
+  if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiCrossKV>(h, p.tm_xn, h->tm2_crosskv, M, c.Ld * 2 * c.I, c.d, ep, s));
+  else CU_OK(h, run_gemm(h, mk(p.tm_xn, h->tm_crosskv, M, c.Ld * 2 * c.I, c.d, G_CROSSKV256, 0), &ep, s));
   return B200T5_OK;
 }
 
@@ -1390,9 +1424,12 @@ static void fill_stats_model(b200t5_ctx* h, int steps) {
     bytes += 2.0 * (wstep + static_cast<double>(c.Ld) * 2 * c.I * sum_s + static_cast<double>(c.Ld) * 2 * c.I * p.B * t +
                     static_cast<double>(c.Ld) * 2 * c.I * p.B);
   h->last_decode_bytes = bytes;
-  const double BS = static_cast<double>(p.B) * p.S;
-  h->last_enc_flops = 2.0 * c.Le * (4.0 * c.d * c.I + 3.0 * c.d * c.F) * BS + c.Le * 4.0 * p.S * static_cast<double>(p.S) * c.I * p.B +
-                      2.0 * c.Ld * 2.0 * c.d * c.I * BS;
+  // encoder + cross-KV projection FLOPs of the rows that matter (positions below extent[b]); for full-length
+  // prompts this is SURVEY 8(d)'s figure, for padded ones it is the work the packed encoder actually does
+  double sum_s2 = 0;
+  for (int v : ext) sum_s2 += static_cast<double>(v) * v;
+  h->last_enc_flops = 2.0 * c.Le * (4.0 * c.d * c.I + 3.0 * c.d * c.F) * sum_s + c.Le * 4.0 * sum_s2 * c.I +
+                      2.0 * c.Ld * 2.0 * c.d * c.I * sum_s;
 }
 
 static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* mask, int B, int S,
@@ -1562,7 +1599,12 @@ extern "C" int b200t5_encode(b200t5_handle h, const int64_t* input_ids, const in
   const int T = h->plan && h->plan->B == B && h->plan->S == S ? h->plan->Tmax : 1;
   TRY(ensure_plan(h, B, S, T));
   TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
-  CU_OK(h, cudaMemcpyAsync(enc_out_bf16, h->plan->xn.p, static_cast<size_t>(B) * S * h->c.d * 2, cudaMemcpyDeviceToDevice, s));
+  if (h->plan->packed) {
+    unpack_rows_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(h->plan->xn.as<bf16>(), h->plan->cu.as<int>(), static_cast<bf16*>(enc_out_bf16), S, h->c.d);
+    CU_OK(h, cudaGetLastError());
+  } else {
+    CU_OK(h, cudaMemcpyAsync(enc_out_bf16, h->plan->xn.p, static_cast<size_t>(B) * S * h->c.d * 2, cudaMemcpyDeviceToDevice, s));
+  }
   return B200T5_OK;
 }
 
@@ -1758,7 +1800,7 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
     CUtensorMap tm;
     if (!make_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, static_cast<uint64_t>(3) * H * 64, 128)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
     encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), static_cast<cudaStream_t>(stream)>>>(
-        tm, static_cast<bf16*>(ctx), rel_bias, key_ok, extent, S, H);
+        tm, static_cast<bf16*>(ctx), rel_bias, key_ok, extent, nullptr, S, H);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn_tc: %s", cudaGetErrorString(e2));
     return B200T5_OK;

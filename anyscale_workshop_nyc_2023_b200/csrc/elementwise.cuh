@@ -18,6 +18,80 @@ __global__ void embed_rows_kernel(const long long* __restrict__ ids, const __nv_
   for (int i = lane_id(); i < d / 8; i += 32) dst[i] = src[i];
 }
 
+// ---------------------------------------------------------------- packed (variable-length) encoder rows
+// The reference pads every prompt to 512 tokens (JOB/utils.py:23-27) and HF runs the encoder over all of them.
+// Rows at or beyond extent[b] (the last attended position + 1) are never read downstream - the keys are
+// masked out of every attention and the cross-attention stops at extent[b] - so the encoder here runs on
+// the valid rows only, packed back to back: row cu[b] + s holds position s of prompt b.
+// One CTA: exclusive scan of extent[] -> cu[0..B]; cu[B] = number of packed rows.
+__global__ void pack_offsets_kernel(const int* __restrict__ extent, int* __restrict__ cu, int B) {
+  __shared__ int s_part[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < B ? extent[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane_id() >= static_cast<uint32_t>(o)) x += y;
+    }
+    if (lane_id() == 31) s_part[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane_id() >= static_cast<uint32_t>(o)) w += y;
+      }
+      s_part[threadIdx.x] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? s_part[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = s_carry + warp_off + x;
+    if (i < B) cu[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cu[B] = s_carry;
+}
+
+// row tables for the packed layout + embedding gather: x[cu[b] + s, :] = E[ids[b, s], :]
+__global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ E,
+                                         __nv_bfloat16* __restrict__ x, const int* __restrict__ cu,
+                                         int* __restrict__ row_b, int* __restrict__ row_s, int S, int d, int vocab) {
+  const int b = blockIdx.y;
+  const int n = cu[b + 1] - cu[b];
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= n) return;
+  const int row = cu[b] + s;
+  if (lane_id() == 0) {
+    row_b[row] = b;
+    row_s[row] = s;
+  }
+  long long id = ids[static_cast<size_t>(b) * S + s];
+  if (id < 0 || id >= vocab) id = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(id) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * d);
+  for (int i = lane_id(); i < d / 8; i += 32) dst[i] = src[i];
+}
+
+// test hook: packed rows back to the padded [B*S, d] layout (rows beyond extent[b] are zero)
+__global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ xp, const int* __restrict__ cu,
+                                   __nv_bfloat16* __restrict__ out, int S, int d) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const int n = cu[b + 1] - cu[b];
+  uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * S + s) * d);
+  const uint4* src = reinterpret_cast<const uint4*>(xp + static_cast<size_t>(cu[b] + s) * d);
+  for (int i = lane_id(); i < d / 8; i += 32) dst[i] = s < n ? src[i] : make_uint4(0, 0, 0, 0);
+}
+
 // ---------------------------------------------------------------- T5 RMSNorm
 // HF (modeling_t5.py:55-68), bf16 weights:
 //   var = mean(float(x)^2)                      fp32

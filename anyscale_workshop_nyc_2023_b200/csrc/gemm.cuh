@@ -451,6 +451,8 @@ struct EpiCrossKV {
   struct Params {
     __nv_bfloat16* arena;
     int B, H, S;
+    const int* row_b = nullptr;  // packed encoder rows: row m is position row_s[m] of prompt row_b[m]
+    const int* row_s = nullptr;
   };
   static constexpr bool kPaired = false;
   typedef NoPre ChunkPre;
@@ -458,7 +460,8 @@ struct EpiCrossKV {
   static DEVINL void chunk_pre(const Params&, int, int, int, ChunkPre&) {}
   static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
                            const ChunkPre&) {
-    const int b = m / p.S, s = m - b * p.S;
+    const int b = p.row_b ? p.row_b[m] : m / p.S;
+    const int s = p.row_s ? p.row_s[m] : m - b * p.S;
     const int hd = p.H * 64;
     const int lkv = n0 / hd;
     const int rem = n0 - lkv * hd;
