@@ -177,6 +177,7 @@ struct DecLayerW {
 };
 
 constexpr int kMaxChains = 8;
+constexpr int kStepsPerGraph = 8;
 
 struct Plan {
   int B = 0, S = 0, Tmax = 0;
@@ -214,6 +215,9 @@ struct Plan {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int graph_nodes = 0;
+  // the same step captured kStepsPerGraph times back to back: one launch per 8 decode steps (= the poll interval)
+  cudaGraph_t graph8 = nullptr;
+  cudaGraphExec_t gexec8 = nullptr;
   long long g_eos = -1, g_pad = -1;
   int g_min_new = -1;
   // pinned staging for the host-buffer entry point and polling
@@ -225,6 +229,8 @@ struct Plan {
   ~Plan() {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
+    if (gexec8) cudaGraphExecDestroy(gexec8);
+    if (graph8) cudaGraphDestroy(graph8);
     if (h_ids) cudaFreeHost(h_ids);
     if (h_mask) cudaFreeHost(h_mask);
     if (h_out) cudaFreeHost(h_out);
@@ -1379,23 +1385,26 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
 static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new) {
   Plan& p = *h->plan;
   if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new) return B200T5_OK;
-  if (p.gexec) {
-    cudaGraphExecDestroy(p.gexec);
-    p.gexec = nullptr;
+  if (p.gexec) cudaGraphExecDestroy(p.gexec);
+  if (p.graph) cudaGraphDestroy(p.graph);
+  if (p.gexec8) cudaGraphExecDestroy(p.gexec8);
+  if (p.graph8) cudaGraphDestroy(p.graph8);
+  p.gexec = p.gexec8 = nullptr;
+  p.graph = p.graph8 = nullptr;
+  for (int which = 0; which < 2; ++which) {
+    const int reps = which ? kStepsPerGraph : 1;
+    cudaGraph_t* g = which ? &p.graph8 : &p.graph;
+    const int64_t before = h->launches;
+    CU_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = B200T5_OK;
+    for (int r = 0; r < reps && rc == B200T5_OK; ++r) rc = run_decode_step(h, h->cap_stream, true, nullptr, 0, eos, pad, min_new);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, g);
+    if (!which) p.graph_nodes = static_cast<int>(h->launches - before);
+    h->launches = before;
+    if (rc != B200T5_OK) return rc;
+    CU_OK(h, e);
+    CU_OK(h, cudaGraphInstantiate(which ? &p.gexec8 : &p.gexec, *g, 0));
   }
-  if (p.graph) {
-    cudaGraphDestroy(p.graph);
-    p.graph = nullptr;
-  }
-  const int64_t before = h->launches;
-  CU_OK(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int rc = run_decode_step(h, h->cap_stream, true, nullptr, 0, eos, pad, min_new);
-  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &p.graph);
-  p.graph_nodes = static_cast<int>(h->launches - before);
-  h->launches = before;
-  if (rc != B200T5_OK) return rc;
-  CU_OK(h, e);
-  CU_OK(h, cudaGraphInstantiate(&p.gexec, p.graph, 0));
   p.g_eos = eos;
   p.g_pad = pad;
   p.g_min_new = min_new;
@@ -1472,9 +1481,17 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
     }
   }
   for (int t = 0; t < T && !mega; ++t) {
-    CU_OK(h, cudaGraphLaunch(p.gexec, s));
-    h->launches += p.graph_nodes;
-    ++steps;
+    if (t % kStepsPerGraph == 0 && t + kStepsPerGraph <= T && poll % kStepsPerGraph == 0) {
+      // eight steps in one launch; the early-exit poll below happens on the same boundaries
+      CU_OK(h, cudaGraphLaunch(p.gexec8, s));
+      h->launches += static_cast<int64_t>(p.graph_nodes) * kStepsPerGraph;
+      steps += kStepsPerGraph;
+      t += kStepsPerGraph - 1;
+    } else {
+      CU_OK(h, cudaGraphLaunch(p.gexec, s));
+      h->launches += p.graph_nodes;
+      ++steps;
+    }
     if ((t + 1) % poll == 0 && t + 1 < T && min_new < T) {
       // every row emitted EOS -> the remaining steps would only append pad tokens
       CU_OK(h, cudaMemcpyAsync(p.h_state, p.state.p, sizeof(DecodeState), cudaMemcpyDeviceToHost, s));
