@@ -200,27 +200,24 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
 // same arithmetic and rounding points as attn_decode_kernel<true>, only warp-level syncs.
 constexpr int kSelfWarpsPerCta = 4;
 
-__global__ void __launch_bounds__(kSelfWarpsPerCta * 32)
-self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
-                             const __nv_bfloat16* __restrict__ Kc,  // [B][H][Tk][64]
-                             const __nv_bfloat16* __restrict__ Vc,
-                             __nv_bfloat16* __restrict__ ctx,       // [B, H*64]
-                             int BH, int H, int Tk, const int* __restrict__ step,
-                             const float* __restrict__ dist_bias) {  // [H][Tk]
-  extern __shared__ float s_all[];  // kSelfWarpsPerCta * Tk floats
-  pdl_launch_dependents();
-  pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x * kSelfWarpsPerCta + warp;
-  if (bh >= BH) return;
+// One (row, head) item handled by one warp; `sc` is this warp's score scratch (Tk floats of shared memory).
+// kNc: read K/V through the non-coherent path (stand-alone kernel: the cache rows were written by an earlier
+// kernel) or with plain loads (resident kernel: they may have been written by another CTA in the same launch).
+template <bool kNc>
+DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
+                                const __nv_bfloat16* __restrict__ Vc, __nv_bfloat16* __restrict__ ctx, int bh, int H, int Tk,
+                                int t, const float* __restrict__ dist_bias, float* sc) {
+  const int lane = threadIdx.x & 31;
   const int h = bh % H;
-  float* sc = s_all + warp * Tk;
   const int ks = lane >> 3, dg = lane & 7;
-  const int t = *step;
   const int nkeys = t + 1;
   const size_t slab = static_cast<size_t>(bh) * Tk * 64;
   const __nv_bfloat16* Kp = Kc + slab + dg * 8;
   const __nv_bfloat16* Vp = Vc + slab + dg * 8;
+  auto load16 = [](const __nv_bfloat16* p) -> uint4 {
+    if constexpr (kNc) return ldg_nc_v4(p);
+    else return *reinterpret_cast<const uint4*>(p);
+  };
   float qf[8];
   {
     const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
@@ -233,7 +230,7 @@ self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = jb + ks + 4 * u;
-      kv[u] = j < nkeys ? ldg_nc_v4(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      kv[u] = j < nkeys ? load16(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -270,7 +267,7 @@ self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
     for (int u = 0; u < U; ++u) {
       const int j = jb + ks + 4 * u;
       const bool ok = j < nkeys;
-      vv[u] = ok ? ldg_nc_v4(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? load16(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
       p[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
@@ -298,6 +295,23 @@ self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
     o.w = pack_bf16x2(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(bh) * 64 + dg * 8) = o;
   }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSelfWarpsPerCta * 32)
+self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
+                             const __nv_bfloat16* __restrict__ Kc,  // [B][H][Tk][64]
+                             const __nv_bfloat16* __restrict__ Vc,
+                             __nv_bfloat16* __restrict__ ctx,       // [B, H*64]
+                             int BH, int H, int Tk, const int* __restrict__ step,
+                             const float* __restrict__ dist_bias) {  // [H][Tk]
+  extern __shared__ float s_all[];  // kSelfWarpsPerCta * Tk floats
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5;
+  const int bh = blockIdx.x * kSelfWarpsPerCta + warp;
+  if (bh >= BH) return;
+  self_attn_warp_item<true>(q, Kc, Vc, ctx, bh, H, Tk, *step, dist_bias, s_all + warp * Tk);
 }
 
 }  // namespace b200

@@ -578,9 +578,16 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
       return lrc;
     }
   }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
-  for (int i = 0; i < kMaxChains; ++i) cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking);
-  for (int i = 0; i <= kMaxChains; ++i) cudaEventCreateWithFlags(&h->chain_ev[i], cudaEventDisableTiming);
+  {
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < kMaxChains && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking);
+    for (int i = 0; i <= kMaxChains && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->chain_ev[i], cudaEventDisableTiming);
+    if (ce != cudaSuccess) {
+      b200t5_destroy(h);
+      return fail(nullptr, B200T5_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(ce));
+    }
+  }
   *out = h;
   return B200T5_OK;
 }
@@ -1424,8 +1431,9 @@ static void fill_stats_model(b200t5_ctx* h, int steps) {
   const Plan& p = *h->plan;
   // weights once per step + cross-KV + self-KV read/write, bf16.
   const double wstep = static_cast<double>(c.Ld) * (6.0 * c.d * c.I + 3.0 * c.d * c.F) + static_cast<double>(c.V) * c.d;
-  std::vector<int> ext(p.B);
-  cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost);
+  std::vector<int> ext(p.B, p.S);
+  if (cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    ext.assign(p.B, p.S);  // statistics only: fall back to the padded length
   double sum_s = 0;
   for (int v : ext) sum_s += v;
   double bytes = 0;

@@ -418,99 +418,15 @@ __device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* w
 }
 
 // ---------------------------------------------------------------- self-attention phase
-// One warp per (row, head); same arithmetic and rounding points as self_attn_decode_warp_kernel.
+// One warp per (row, head): the shared per-item routine of attention_decode.cuh with plain (coherent) loads -
+// the cache rows of this step were written by other CTAs of the same launch.
 __device__ __noinline__ void mega_self_attn_phase(const __nv_bfloat16* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc,
-                                 __nv_bfloat16* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
-                                 float* scratch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                                  __nv_bfloat16* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
+                                                  float* scratch) {
+  const int warp = threadIdx.x >> 5;
   if (warp >= kMegaWarps) return;  // control warp
-  float* sc = scratch + warp * Tk;
-  const int ks = lane >> 3, dg = lane & 7;
-  const int nkeys = t + 1;
-  constexpr int U = 4;
-  for (int bh = blockIdx.x * kMegaWarps + warp; bh < BH; bh += gridDim.x * kMegaWarps) {
-    const int h = bh % H;
-    const size_t slab = static_cast<size_t>(bh) * Tk * 64;
-    const __nv_bfloat16* Kp = Kc + slab + dg * 8;
-    const __nv_bfloat16* Vp = Vc + slab + dg * 8;
-    float qf[8];
-    {
-      const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
-      qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
-      qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
-    }
-    for (int jb = 0; jb < nkeys; jb += 4 * U) {
-      uint4 kv[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = jb + ks + 4 * u;
-        kv[u] = j < nkeys ? *reinterpret_cast<const uint4*>(Kp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = jb + ks + 4 * u;
-        float s = dot8(kv[u], qf);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (dg == 0 && j < nkeys) sc[j] = bf16_round(bf16_round(s) + dist_bias[h * Tk + (t - j)]);
-      }
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int j = lane; j < nkeys; j += 32) mx = fmaxf(mx, sc[j]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int j = lane; j < nkeys; j += 32) {
-      const float e = expf(sc[j] - mx);
-      sc[j] = e;
-      sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    for (int j = lane; j < nkeys; j += 32) sc[j] = bf16_round(sc[j] / sum);
-    __syncwarp();
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int jb = 0; jb < nkeys; jb += 4 * U) {
-      uint4 vv[U];
-      float p[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = jb + ks + 4 * u;
-        const bool ok = j < nkeys;
-        vv[u] = ok ? *reinterpret_cast<const uint4*>(Vp + static_cast<size_t>(j) * 64) : make_uint4(0, 0, 0, 0);
-        p[u] = ok ? sc[j] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        acc[0] = fmaf(p[u], bf16_lo(vv[u].x), acc[0]);
-        acc[1] = fmaf(p[u], bf16_hi(vv[u].x), acc[1]);
-        acc[2] = fmaf(p[u], bf16_lo(vv[u].y), acc[2]);
-        acc[3] = fmaf(p[u], bf16_hi(vv[u].y), acc[3]);
-        acc[4] = fmaf(p[u], bf16_lo(vv[u].z), acc[4]);
-        acc[5] = fmaf(p[u], bf16_hi(vv[u].z), acc[5]);
-        acc[6] = fmaf(p[u], bf16_lo(vv[u].w), acc[6]);
-        acc[7] = fmaf(p[u], bf16_hi(vv[u].w), acc[7]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-    }
-    if (ks == 0) {
-      uint4 o;
-      o.x = pack_bf16x2(acc[0], acc[1]);
-      o.y = pack_bf16x2(acc[2], acc[3]);
-      o.z = pack_bf16x2(acc[4], acc[5]);
-      o.w = pack_bf16x2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(bh) * 64 + dg * 8) = o;
-    }
-    __syncwarp();
-  }
+  for (int bh = blockIdx.x * kMegaWarps + warp; bh < BH; bh += gridDim.x * kMegaWarps)
+    self_attn_warp_item<false>(q, Kc, Vc, ctx, bh, H, Tk, t, dist_bias, scratch + warp * Tk);
 }
 
 // ---------------------------------------------------------------- cross-attention phase
