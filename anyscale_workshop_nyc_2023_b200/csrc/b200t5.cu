@@ -21,6 +21,7 @@
 
 #include "../../include/b200t5.h"
 #include "attention_decode.cuh"
+#include "attention_decode_tc.cuh"
 #include "attention_encoder.cuh"
 #include "attention_encoder_tc.cuh"
 #include "elementwise.cuh"
@@ -199,6 +200,7 @@ struct Plan {
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
   CUtensorMap tm_xn, tm_ctx, tm_hff, tm_qkv_attn;
+  CUtensorMap tm_cross_kv;  // [Ld*2*B*H*S, 64] view of the cross-KV arena, box 64 x 128 keys (attention_decode_tc.cuh)
   // decode chains: the batch is cut into independent row ranges that run concurrently (one
   // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
   struct Chain {
@@ -274,6 +276,7 @@ struct b200t5_ctx {
   // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
   bool mega_on = false;
   int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
+  bool xattn_tc = false;  // B200T5_XATTN=tc: decode cross-attention on the tensor cores (attention_decode_tc.cuh), S <= 512
   bool pack_rows = true;  // encoder on the valid rows only (variable-length packing); B200T5_PACK=0: all B*S rows as the reference does
   bool mcast = false;  // B200T5_MCAST=1: decode O / cross-Q / cross-O products through the A-multicast kernel (gemm_mcast.cuh).
                       // Correct (tests) but slower than split-K (201.4 vs 191.0 ms per batch): multicast saves L2 reads, not the
@@ -420,6 +423,7 @@ static cudaError_t init_kernel_attrs() {
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
   if ((e = prepare_gemm_mcast()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXtcSmemBytes)) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiStore>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiResidual>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiGeglu>()) != cudaSuccess) return e;
@@ -527,6 +531,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
   if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
+  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_tc = strcmp(xa_env, "tc") == 0;
   if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
   if (const char* mc_env = getenv("B200T5_MCAST")) h->mcast = atoi(mc_env) != 0;
   if (const char* fn_env = getenv("B200T5_FUSENORM")) h->fuse_norm = atoi(fn_env) != 0;
@@ -963,6 +968,9 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->row_s.alloc(M * 4));
   CU_OK(h, cudaMallocHost(&pl->h_cu, 16));
   CU_OK(h, pl->cross_kv.alloc(static_cast<size_t>(c.Ld) * 2 * M * I * 2));
+  // finite everywhere: keys beyond a prompt's extent are never written, and the tensor-core decode attention
+  // multiplies them by p = 0
+  CU_OK(h, cudaMemset(pl->cross_kv.p, 0, pl->cross_kv.bytes));
   CU_OK(h, pl->dx.alloc(static_cast<size_t>(B) * d * 2));
   CU_OK(h, pl->dxn.alloc(static_cast<size_t>(B) * d * 2));
   CU_OK(h, pl->dq.alloc(static_cast<size_t>(B) * I * 2));
@@ -1006,6 +1014,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
   TMAP(h, &pl->tm_hff, pl->hff.p, M, F, 128);
   TMAP(h, &pl->tm_qkv_attn, pl->qkv.p, M, 3 * I, 128);
+  TMAP(h, &pl->tm_cross_kv, pl->cross_kv.p, static_cast<uint64_t>(c.Ld) * 2 * B * H * S, 64, 128);
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
     // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
@@ -1244,9 +1253,17 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
       add(5, n.wcq);
     }
   }
-  CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
-                         v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
-                         p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf));
+  if (h->xattn_tc && S <= kXtcMaxS) {
+    const int nitems = v.nb * H;
+    const int k_row0 = (l * 2) * B * H * S, v_row0 = (l * 2 + 1) * B * H * S;
+    CU_OK(h, launch_kernel(attn_decode_tc_kernel, dim3(nitems < h->num_sms ? nitems : h->num_sms), dim3(kXtcThreads), kXtcSmemBytes, s,
+                           pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, p.dq.as<bf16>(), p.dctx.as<bf16>(), v.b0 * H, nitems, H,
+                           S, p.extent.as<int>(), p.key_ok.as<unsigned char>(), static_cast<long long*>(nullptr)));
+  } else {
+    CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
+                           v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
+                           p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf));
+  }
   h->launches++;
   return B200T5_OK;
 }
@@ -1584,9 +1601,23 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_
   Plan& p = *h->plan;
   const Cfg& c = h->c;
   const size_t cross_layer = static_cast<size_t>(2) * p.B * c.I * p.S;
+  long long* xtc_prof = nullptr;  // B200T5_XTC_PROF=1: per-item stamps of the tensor-core kernel (diagnostic)
+  DevBuf prof_buf;
+  if (getenv("B200T5_XTC_PROF") && h->xattn_tc) {
+    CU_OK(h, prof_buf.alloc(32 * 8 * 8));
+    CU_OK(h, cudaMemset(prof_buf.p, 0, 32 * 8 * 8));
+    xtc_prof = prof_buf.as<long long>();
+  }
   auto sweep = [&]() {
     for (int l = 0; l < c.Ld; ++l) {
       bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
+      if (h->xattn_tc && p.S <= kXtcMaxS) {
+        const int nitems = p.B * c.H;
+        attn_decode_tc_kernel<<<nitems < h->num_sms ? nitems : h->num_sms, kXtcThreads, kXtcSmemBytes, s>>>(
+            p.tm_cross_kv, p.tm_cross_kv, (l * 2) * nitems * p.S, (l * 2 + 1) * nitems * p.S, p.dq.as<bf16>(), p.dctx.as<bf16>(), 0,
+            nitems, c.H, p.S, p.extent.as<int>(), p.key_ok.as<unsigned char>(), xtc_prof);
+        continue;
+      }
       attn_decode_kernel<false><<<p.B * c.H, kAttnDecThreads, p.S * sizeof(float), s>>>(
           p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<bf16>(), c.H, p.S,
           p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr, L2Prefetch{});
@@ -1606,6 +1637,15 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_
   cudaEventDestroy(e1);
   CU_OK(h, cudaGetLastError());
   *avg_ms_per_launch = ms / (static_cast<float>(reps) * c.Ld);
+  if (xtc_prof) {
+    long long st[32 * 8];
+    CU_OK(h, cudaMemcpy(st, prof_buf.p, sizeof(st), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "XTC_PROF (SM clocks, CTA 0 softmax thread 0; per item: start, s_full, scores read, softmax, p_free, p staged, epilogue):\n");
+    for (int i = 0; i < 24 && st[i * 8]; ++i)
+      fprintf(stderr, "  item %2d: +%lld | %lld %lld %lld %lld %lld %lld\n", i, i ? st[i * 8] - st[(i - 1) * 8] : 0LL, st[i * 8 + 1] - st[i * 8],
+              st[i * 8 + 2] - st[i * 8 + 1], st[i * 8 + 3] - st[i * 8 + 2], st[i * 8 + 4] - st[i * 8 + 3], st[i * 8 + 5] - st[i * 8 + 4],
+              st[i * 8 + 6] - st[i * 8 + 5]);
+  }
   std::vector<int> ext(p.B);
   CU_OK(h, cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost));
   double sum_s = 0;
@@ -1796,7 +1836,7 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (self) {
+  if (self == 1) {
     DevBuf st;
     if (st.alloc(sizeof(DecodeState)) != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "alloc");
     set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
@@ -1805,6 +1845,14 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
         static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx),
         B * H, H, Tk, &st.as<DecodeState>()->step, dist_bias);
     cudaStreamSynchronize(s);
+  } else if (self == 2) {  // cross-attention on the tensor cores (attention_decode_tc.cuh)
+    if (Tk > kXtcMaxS) return fail(nullptr, B200T5_EINVAL, "attn_decode(tc): Tk <= %d", kXtcMaxS);
+    CUtensorMap tk, tv;
+    if (!make_tmap(&tk, K, static_cast<uint64_t>(B) * H * Tk, 64, 128) || !make_tmap(&tv, V, static_cast<uint64_t>(B) * H * Tk, 64, 128))
+      return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+    const int nitems = B * H;
+    attn_decode_tc_kernel<<<nitems < sms ? nitems : sms, kXtcThreads, kXtcSmemBytes, s>>>(
+        tk, tv, 0, 0, static_cast<const bf16*>(q), static_cast<bf16*>(ctx), 0, nitems, H, Tk, extent, key_ok);
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
         static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,

@@ -147,7 +147,9 @@ int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, i
 int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int split,
                             int mode, int pow_mode, void* aux, int Tmax, int step, void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);
-/* self != 0: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk]. */
+/* self == 1: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk];
+ * self == 2: as 0 through the tensor-core kernel (csrc/attention_decode_tc.cuh, Tk <= 512; K and V must be finite
+ * beyond the extent as well). */
 int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx, int B,
                             int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
                             const float* dist_bias, void* stream);

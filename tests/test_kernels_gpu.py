@@ -321,8 +321,9 @@ def torch_attn_decode(q, K, V, bias_add):
     return torch.matmul(p.float(), V.float()).bfloat16().squeeze(2)
 
 
-@pytest.mark.parametrize("B,H,S", [(4, 6, 512), (3, 2, 77), (16, 12, 256)])
-def test_cross_attn_decode(lib, B, H, S):
+@pytest.mark.parametrize("impl", [0, 2])  # 0: CUDA-core streaming kernel, 2: tensor-core kernel (attention_decode_tc.cuh)
+@pytest.mark.parametrize("B,H,S", [(4, 6, 512), (3, 2, 77), (16, 12, 256), (40, 12, 512), (5, 3, 130)])
+def test_cross_attn_decode(lib, B, H, S, impl):
     g = torch.Generator(device="cuda").manual_seed(B * S)
     q = (torch.randn(B, H, 64, device="cuda", generator=g) * 0.3).bfloat16()
     K = torch.randn(B, H, S, 64, device="cuda", generator=g).bfloat16()
@@ -337,7 +338,7 @@ def test_cross_attn_decode(lib, B, H, S):
     extent = torch.where(ok.any(1), ok.float().cumsum(1).argmax(1) + 1, torch.tensor(S, device="cuda")).int()
     key_ok = ok.to(torch.uint8).contiguous()
     ctx = torch.empty(B, H * 64, device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.b200t5_test_attn_decode(DEV, 0, P(q), P(K), P(V), P(ctx), B, H, S, P(extent), P(key_ok), 0, None, None))
+    _lib.check(lib.b200t5_test_attn_decode(DEV, impl, P(q), P(K), P(V), P(ctx), B, H, S, P(extent), P(key_ok), 0, None, None))
     torch.cuda.synchronize()
     mask_add = torch.where(ok, 0.0, BF16_MIN).to(torch.bfloat16)[:, None, :].expand(B, H, S)
     ref = torch_attn_decode(q, K, V, mask_add).reshape(B, H * 64)
