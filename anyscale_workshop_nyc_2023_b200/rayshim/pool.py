@@ -1,4 +1,6 @@
-"""One scoring process per GPU (what Ray's ActorPoolStrategy + num_gpus=1 gives the reference).
+"""One scoring process per GPU (what Ray's ActorPoolStrategy + num_gpus=1 gives the reference:
+`predictor.predict(..., num_gpus_per_worker=int(use_gpu), batch_size=256)`,
+NLP_workloads/Anyscale_job/flan-t5-batch-inference.py:129-134; notebook :908-913).
 
 Batches are dealt round-robin to the workers (static sharding, no collective, no GPU<->GPU
 traffic); results come back tagged with their index and are re-assembled in input order.
