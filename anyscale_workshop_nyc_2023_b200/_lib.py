@@ -73,6 +73,7 @@ SIGNATURES = {
     "b200t5_last_global_error": (C.c_char_p, []),
     "b200t5_generate": (_i, [_vp, _i64p, _i64p, _i, _i, C.POINTER(GenParams), _i64p, _i32p, _vp]),
     "b200t5_generate_host": (_i, [_vp, _i64p, _i64p, _i, _i, C.POINTER(GenParams), _i64p, _i32p]),
+    "b200t5_generate_stream": (_i, [_vp, _i64p, _i64p, C.c_int64, _i, C.POINTER(GenParams), _i, _i, _i64p, _i32p]),
     "b200t5_get_stats": (_i, [_vp, C.POINTER(Stats)]),
     "b200t5_bench_cross_attn": (_i, [_vp, _i, C.POINTER(C.c_float), C.POINTER(C.c_double), _vp]),
     "b200t5_encode": (_i, [_vp, _i64p, _i64p, _i, _i, _vp, _vp]),

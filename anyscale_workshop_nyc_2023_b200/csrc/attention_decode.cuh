@@ -55,9 +55,10 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
                    int H, int Tk,
                    const int* __restrict__ extent,            // cross: [B] keys to visit
                    const unsigned char* __restrict__ key_ok,  // cross: [B][Tk] 1 = attended
-                   const int* __restrict__ step,              // self: device scalar t
+                   const int* __restrict__ step,              // self: device scalar t (or per-row positions)
                    const float* __restrict__ dist_bias,       // self: [H][Tk] bias by distance t-j
-                   const L2Prefetch pf) {                     // cross: weight slices to pull into L2 (bytes 0 = none)
+                   const L2Prefetch pf,                       // cross: weight slices to pull into L2 (bytes 0 = none)
+                   const int step_stride = 0) {               // self: 1 = slot pool, row b is at position step[b]
   extern __shared__ float s_scores[];  // Tk floats
   __shared__ float s_red[4][64];
   __shared__ float s_stat[8];
@@ -81,7 +82,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = lane >> 3, dg = lane & 7;
-  const int t = kSelf ? *step : 0;
+  const int t = kSelf ? step[b * step_stride] : 0;
   const int nkeys = kSelf ? t + 1 : extent[b];
   const size_t slab = (static_cast<size_t>(b) * H + h) * static_cast<size_t>(Tk) * 64;
   const __nv_bfloat16* Kp = Kc + slab + dg * 8;
@@ -304,14 +305,15 @@ self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
                              const __nv_bfloat16* __restrict__ Vc,
                              __nv_bfloat16* __restrict__ ctx,       // [B, H*64]
                              int BH, int H, int Tk, const int* __restrict__ step,
-                             const float* __restrict__ dist_bias) {  // [H][Tk]
+                             const float* __restrict__ dist_bias,    // [H][Tk]
+                             const int step_stride = 0) {            // 1 = slot pool: per-row positions
   extern __shared__ float s_all[];  // kSelfWarpsPerCta * Tk floats
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int bh = blockIdx.x * kSelfWarpsPerCta + warp;
   if (bh >= BH) return;
-  self_attn_warp_item<true>(q, Kc, Vc, ctx, bh, H, Tk, *step, dist_bias, s_all + warp * Tk);
+  self_attn_warp_item<true>(q, Kc, Vc, ctx, bh, H, Tk, step[(bh / H) * step_stride], dist_bias, s_all + warp * Tk);
 }
 
 }  // namespace b200

@@ -197,6 +197,18 @@ struct Plan {
   DevBuf dec_bias;                      // float [H][Tmax]
   DevBuf pval, pidx;                    // [B][n_tiles]
   DevBuf state, unfinished, out_ids, out_len, ids_dev, mask_dev;
+  // what the decode kernels attend to: copies of extent / key_ok in which a finished row's extent drops to 0
+  // (retired: its K/V are no longer streamed). In slot-pool mode they describe the slots' CURRENT prompts while
+  // extent / key_ok describe the prompts of the encoder pass being admitted.
+  DevBuf live_extent, live_key_ok;
+  // slot pool (b200t5_generate_stream): per-slot position and result row, admission lists, [N, Tmax+1] results
+  DevBuf pos, out_row, admit;
+  DevBuf stream_out, stream_len;
+  size_t stream_cap = 0;   // rows stream_out / stream_len hold (the step graph bakes their addresses)
+  bool stream_mode = false;
+  int g_stream = -1;
+  int* h_unf = nullptr;    // pinned: unfinished[B] read back every graph launch
+  int* h_admit = nullptr;  // pinned: [3][B] = row_on flags, slots, rows
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
   CUtensorMap tm_xn, tm_ctx, tm_hff, tm_qkv_attn;
@@ -239,6 +251,8 @@ struct Plan {
     if (h_len) cudaFreeHost(h_len);
     if (h_state) cudaFreeHost(h_state);
     if (h_cu) cudaFreeHost(h_cu);
+    if (h_unf) cudaFreeHost(h_unf);
+    if (h_admit) cudaFreeHost(h_admit);
   }
 };
 
@@ -992,6 +1006,15 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, cudaMallocHost(&pl->h_out, static_cast<size_t>(B) * (Tmax + 1) * 8));
   CU_OK(h, cudaMallocHost(&pl->h_len, static_cast<size_t>(B) * 4));
   CU_OK(h, cudaMallocHost(&pl->h_state, sizeof(DecodeState)));
+  CU_OK(h, pl->live_extent.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->live_key_ok.alloc(M));
+  CU_OK(h, pl->pos.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->out_row.alloc(static_cast<size_t>(B) * 4));
+  CU_OK(h, pl->admit.alloc(static_cast<size_t>(3) * B * 4));
+  CU_OK(h, cudaMemset(pl->pos.p, 0, pl->pos.bytes));
+  CU_OK(h, cudaMemset(pl->out_row.p, 0, pl->out_row.bytes));
+  CU_OK(h, cudaMallocHost(&pl->h_unf, static_cast<size_t>(B) * 4));
+  CU_OK(h, cudaMallocHost(&pl->h_admit, static_cast<size_t>(3) * B * 4));
 
   // bias tables (values are the bf16 embedding entries widened to fp32)
   {
@@ -1058,16 +1081,18 @@ static GemmOp mk(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K
 }
 
 // ================================================================== encoder
-static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mask, cudaStream_t s) {
+static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mask, cudaStream_t s, const int* row_on = nullptr) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
   const int B = p.B, S = p.S, d = c.d, I = c.I, F = c.F, H = c.H;
   int M = B * S;
-  prep_mask_kernel<<<B, 128, 0, s>>>(mask, p.key_ok.as<unsigned char>(), p.extent.as<int>(), B, S);
+  prep_mask_kernel<<<B, 128, 0, s>>>(mask, p.key_ok.as<unsigned char>(), p.extent.as<int>(), B, S, row_on);
   h->launches++;
   // Variable-length packing: only rows below extent[b] are ever read downstream, so the encoder runs on those
   // (elementwise.cuh). The number of packed rows sizes the GEMM grids, hence one 4-byte read-back per call.
   p.packed = h->pack_rows && h->enc_attn_tc && S <= kEncTcMaxS;
+  if (row_on && !p.packed)
+    return fail(h, B200T5_EINVAL, "slot-pool admission needs the packed encoder path (S <= %d, B200T5_PACK/B200T5_ENC_ATTN at their defaults)", kEncTcMaxS);
   const int* cu = nullptr;
   if (p.packed) {
     pack_offsets_kernel<<<1, 256, 0, s>>>(p.extent.as<int>(), p.cu.as<int>(), B);
@@ -1169,7 +1194,9 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   Plan& p = *h->plan;
   const int B = p.B, d = c.d, I = c.I, H = c.H, T = p.Tmax;
   const bool pdl = h->use_pdl;
-  const int* step = &p.state.as<DecodeState>()->step;
+  // static batch: one position for all rows; slot pool: row b of the chain is at pos[b0 + b]
+  const int sstride = p.stream_mode ? 1 : 0;
+  const int* step = p.stream_mode ? p.pos.as<int>() + v.b0 : &p.state.as<DecodeState>()->step;
   DecLayerW& w = h->dec[l];
   // [kv][B][H][T][64]: a row offset of b0 is a pointer offset inside each kv plane
   bf16* skv = p.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
@@ -1181,7 +1208,7 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
   if (!(fuse && l > 0)) CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
-    EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T};
+    EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T, sstride};
     if (fuse && l > 0)
       CU_OK(h, run_gemm_sk_norm<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dx, w.tm_qkv, v.nb, 3 * I, d, ep,
                                               NormA{ss, ss_ld, w.ln0.as<bf16>(), c.eps}, s, pdl));
@@ -1191,11 +1218,11 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   if (h->self_block)  // 4 warps per (row, head): two memory round trips whatever t is
     CU_OK(h, launch_kernel(attn_decode_kernel<true>, dim3(v.nb * H), dim3(kAttnDecThreads), T * sizeof(float), s, pdl, v.dq, skv,
                            skv + static_cast<size_t>(B) * I * T, v.dctx, H, T, nullptr, nullptr, step, p.dec_bias.as<float>(),
-                           L2Prefetch{}));
+                           L2Prefetch{}, sstride));
   else
     CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
                            dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
-                           skv + static_cast<size_t>(B) * I * T, v.dctx, v.nb * H, H, T, step, p.dec_bias.as<float>()));
+                           skv + static_cast<size_t>(B) * I * T, v.dctx, v.nb * H, H, T, step, p.dec_bias.as<float>(), sstride));
   h->launches++;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
@@ -1258,11 +1285,11 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
     const int k_row0 = (l * 2) * B * H * S, v_row0 = (l * 2 + 1) * B * H * S;
     CU_OK(h, launch_kernel(attn_decode_tc_kernel, dim3(nitems < h->num_sms ? nitems : h->num_sms), dim3(kXtcThreads), kXtcSmemBytes, s,
                            pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, p.dq.as<bf16>(), p.dctx.as<bf16>(), v.b0 * H, nitems, H,
-                           S, p.extent.as<int>(), p.key_ok.as<unsigned char>(), static_cast<long long*>(nullptr)));
+                           S, p.live_extent.as<int>(), p.live_key_ok.as<unsigned char>(), static_cast<long long*>(nullptr)));
   } else {
     CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
-                           v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.extent.as<int>() + v.b0,
-                           p.key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf));
+                           v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.live_extent.as<int>() + v.b0,
+                           p.live_key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf, 0));
   }
   h->launches++;
   return B200T5_OK;
@@ -1327,11 +1354,16 @@ static int chain_head(b200t5_ctx* h, cudaStream_t s, const ChainView& v, float* 
   } else {
     float* pval = p.pval.as<float>() + static_cast<size_t>(v.b0) * p.n_vtiles;
     int* pidx = p.pidx.as<int>() + static_cast<size_t>(v.b0) * p.n_vtiles;
-    EpiArgmax::Params ep{pval, pidx, p.n_vtiles, &st->step, static_cast<int>(eos), min_new};
+    const bool sm = p.stream_mode;
+    EpiArgmax::Params ep{pval, pidx, p.n_vtiles, sm ? p.pos.as<int>() + v.b0 : &st->step, static_cast<int>(eos), min_new, sm ? 1 : 0};
     CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, h->tm_lm, v.nb, c.V, d, G_ARGMAX128, 1), &ep, s, pdl));
+    // static batch: rows b0.. of the plan's [B, T+1] result; slot pool: row out_row[slot] of the [N, T+1] result
+    long long* oid = sm ? p.stream_out.as<long long>() : p.out_ids.as<long long>() + static_cast<size_t>(v.b0) * (T + 1);
+    int* olen = sm ? p.stream_len.as<int>() : p.out_len.as<int>() + v.b0;
     CU_OK(h, launch_kernel(finalize_step_kernel, dim3(v.nb), dim3(128), 0, s, pdl, pval, pidx, p.n_vtiles, st,
-                           p.unfinished.as<int>() + v.b0, p.out_ids.as<long long>() + static_cast<size_t>(v.b0) * (T + 1),
-                           p.out_len.as<int>() + v.b0, T + 1, eos, pad, h->shared.as<bf16>(), v.dx, d));
+                           p.unfinished.as<int>() + v.b0, oid, olen, T + 1, eos, pad, h->shared.as<bf16>(), v.dx, d,
+                           p.live_extent.as<int>() + v.b0, sm ? p.pos.as<int>() + v.b0 : static_cast<int*>(nullptr),
+                           sm ? p.out_row.as<int>() + v.b0 : static_cast<const int*>(nullptr), T));
     h->launches++;
   }
   return B200T5_OK;
@@ -1408,7 +1440,7 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
 // Graph of one decode step; eos/pad/min_new are baked in, so the graph is rebuilt when they change.
 static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new) {
   Plan& p = *h->plan;
-  if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new) return B200T5_OK;
+  if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new && p.g_stream == (p.stream_mode ? 1 : 0)) return B200T5_OK;
   if (p.gexec) cudaGraphExecDestroy(p.gexec);
   if (p.graph) cudaGraphDestroy(p.graph);
   if (p.gexec8) cudaGraphExecDestroy(p.gexec8);
@@ -1432,6 +1464,7 @@ static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new
   p.g_eos = eos;
   p.g_pad = pad;
   p.g_min_new = min_new;
+  p.g_stream = p.stream_mode ? 1 : 0;
   return B200T5_OK;
 }
 
@@ -1478,12 +1511,15 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   const int poll = gp->poll_interval > 0 ? gp->poll_interval : 8;
   TRY(ensure_plan(h, B, S, T));
   Plan& p = *h->plan;
+  p.stream_mode = false;
   const bool mega = p.mega_ok;
   if (!mega) TRY(ensure_graph(h, eos, pad, min_new));
   h->launches = 0;
   CU_OK(h, cudaEventRecord(h->ev[0], s));
   TRY(run_encoder(h, ids, mask, s));
   TRY(run_cross_kv(h, s));
+  CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
+  CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   decode_init_kernel<<<B, 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.out_ids.as<long long>(),
                                        p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
   h->launches++;
@@ -1568,6 +1604,132 @@ extern "C" int b200t5_generate_host(b200t5_handle h, const int64_t* input_ids, c
   CU_OK(h, cudaStreamSynchronize(s));
   memcpy(out_ids, p.h_out, static_cast<size_t>(B) * (T + 1) * 8);
   memcpy(out_len, p.h_len, static_cast<size_t>(B) * 4);
+  return B200T5_OK;
+}
+
+// ================================================================== slot pool (continuous batching)
+// N prompts through a pool of `pool` decode slots. A slot whose row has finished (EOS or max_new tokens) is
+// retired at the next poll and refilled with the next prompt: an encoder pass over the newly admitted prompts
+// only (packed rows; every other slot has extent 0 in that pass) writes their cross-KV into the slots' arena
+// rows, then the same step graph as the static path runs with per-slot positions. Rows are independent in every
+// kernel, so a prompt's tokens are bit-identical to what b200t5_generate returns for it in a `pool`-row batch.
+// Replaces, for a caller that hands over more than one batch at a time, the per-batch generate() of
+// predictor.py:102 under BatchPredictor.predict (NB:908-913): finished rows stop costing bandwidth and the
+// pool stays full instead of draining to the slowest row of each 256-row batch.
+extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int64_t N,
+                                      int S, const b200t5_gen_params* gp, int pool, int admit_min, int64_t* out_ids,
+                                      int32_t* out_len) {
+  if (!h) return fail(nullptr, B200T5_EINVAL, "null handle");
+  if (!gp || !input_ids || !out_ids || !out_len) return fail(h, B200T5_EINVAL, "null argument");
+  if (N < 1 || N > (1ll << 30)) return fail(h, B200T5_EINVAL, "bad prompt count N=%lld", static_cast<long long>(N));
+  if (pool < 1) pool = 256;
+  if (pool > N) pool = static_cast<int>(N);
+  TRY(validate(h, pool, S, gp));
+  CU_OK(h, cudaSetDevice(h->device));
+  const Cfg& c = h->c;
+  const long long eos = gp->eos_token_id >= 0 ? gp->eos_token_id : c.eos;
+  const long long pad = gp->pad_token_id >= 0 ? gp->pad_token_id : c.pad;
+  const long long start = gp->decoder_start_token_id >= 0 ? gp->decoder_start_token_id : c.start;
+  if (start >= c.V || pad >= c.V) return fail(h, B200T5_EINVAL, "special token id out of range");
+  const int T = gp->max_new_tokens;
+  const int min_new = gp->min_new_tokens > 0 ? gp->min_new_tokens : 0;
+  const int B = pool;
+  if (admit_min < 1) admit_min = B >= 8 ? B / 8 : 1;
+  TRY(ensure_plan(h, B, S, T));
+  Plan& p = *h->plan;
+  cudaStream_t s = h->exec_stream;
+  if (p.stream_cap < static_cast<size_t>(N)) {
+    // the step graph bakes the result addresses: a larger result buffer means a new graph
+    CU_OK(h, cudaStreamSynchronize(s));
+    size_t cap = p.stream_cap ? p.stream_cap : 1024;
+    while (cap < static_cast<size_t>(N)) cap *= 2;
+    CU_OK(h, p.stream_out.alloc(cap * (T + 1) * 8));
+    CU_OK(h, p.stream_len.alloc(cap * 4));
+    p.stream_cap = cap;
+    p.g_stream = -1;
+  }
+  p.stream_mode = true;
+  TRY(ensure_graph(h, eos, pad, min_new));
+  h->launches = 0;
+  CU_OK(h, cudaEventRecord(h->ev[0], s));
+  {
+    const long long rows = N > B ? N : B;
+    stream_init_kernel<<<static_cast<unsigned>(rows), 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.pos.as<int>(),
+                                                                  p.live_extent.as<int>(), p.stream_out.as<long long>(),
+                                                                  p.stream_len.as<int>(), T + 1, static_cast<int>(N), B, start, pad,
+                                                                  h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+    h->launches++;
+    CU_OK(h, cudaGetLastError());
+  }
+  CU_OK(h, cudaEventRecord(h->ev[1], s));
+  std::vector<long long> slot_row(B, -1);
+  long long next = 0, done = 0;
+  int active = 0, steps = 0;
+  double enc_flops = 0;
+  int* row_on = p.h_admit;
+  int* a_slot = p.h_admit + B;
+  int* a_row = p.h_admit + 2 * B;
+  const size_t row_bytes = static_cast<size_t>(S) * 8;
+  while (done < N) {
+    const int nfree = B - active;
+    const long long left = N - next;
+    if (left > 0 && nfree > 0 && (active == 0 || nfree >= (left < admit_min ? left : admit_min))) {
+      // ---- admission: the next k prompts go to the free slots
+      const int k = static_cast<int>(left < nfree ? left : nfree);
+      int j = 0;
+      for (int b = 0; b < B; ++b) {
+        row_on[b] = 0;
+        if (slot_row[b] < 0 && j < k) {
+          const long long r = next + j;
+          row_on[b] = 1;
+          a_slot[j] = b;
+          a_row[j] = static_cast<int>(r);
+          slot_row[b] = r;
+          memcpy(p.h_ids + static_cast<size_t>(b) * S, input_ids + static_cast<size_t>(r) * S, row_bytes);
+          if (attention_mask) memcpy(p.h_mask + static_cast<size_t>(b) * S, attention_mask + static_cast<size_t>(r) * S, row_bytes);
+          ++j;
+        }
+      }
+      const size_t nb = static_cast<size_t>(B) * row_bytes;
+      CU_OK(h, cudaMemcpyAsync(p.ids_dev.p, p.h_ids, nb, cudaMemcpyHostToDevice, s));
+      if (attention_mask) CU_OK(h, cudaMemcpyAsync(p.mask_dev.p, p.h_mask, nb, cudaMemcpyHostToDevice, s));
+      CU_OK(h, cudaMemcpyAsync(p.admit.p, p.h_admit, static_cast<size_t>(3) * B * 4, cudaMemcpyHostToDevice, s));
+      // rows that are not admitted keep stale ids / masks in the staging buffers: row_on switches them off
+      TRY(run_encoder(h, p.ids_dev.as<long long>(), attention_mask ? p.mask_dev.as<long long>() : nullptr, s, p.admit.as<int>()));
+      TRY(run_cross_kv(h, s));
+      admit_slots_kernel<<<k, 128, 0, s>>>(p.admit.as<int>() + B, p.admit.as<int>() + 2 * B, p.unfinished.as<int>(), p.pos.as<int>(),
+                                           p.out_row.as<int>(), p.extent.as<int>(), p.live_extent.as<int>(),
+                                           p.key_ok.as<unsigned char>(), p.live_key_ok.as<unsigned char>(), S, start,
+                                           h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+      h->launches++;
+      CU_OK(h, cudaGetLastError());
+      fill_stats_model(h, 0);
+      enc_flops += h->last_enc_flops;
+      next += k;
+      active += k;
+    }
+    // ---- eight decode steps for every slot, then see which slots have finished
+    CU_OK(h, cudaGraphLaunch(p.gexec8, s));
+    h->launches += static_cast<int64_t>(p.graph_nodes) * kStepsPerGraph;
+    steps += kStepsPerGraph;
+    CU_OK(h, cudaMemcpyAsync(p.h_unf, p.unfinished.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(h, cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b) {
+      if (slot_row[b] >= 0 && !p.h_unf[b]) {
+        slot_row[b] = -1;
+        --active;
+        ++done;
+      }
+    }
+  }
+  CU_OK(h, cudaEventRecord(h->ev[2], s));
+  CU_OK(h, cudaMemcpyAsync(out_ids, p.stream_out.p, static_cast<size_t>(N) * (T + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CU_OK(h, cudaMemcpyAsync(out_len, p.stream_len.p, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToHost, s));
+  CU_OK(h, cudaStreamSynchronize(s));
+  h->last_steps = steps;
+  h->last_decode_bytes = 0;  // not modelled for a pool whose occupancy varies
+  h->last_enc_flops = enc_flops;
+  h->ev_valid = true;
   return B200T5_OK;
 }
 
@@ -1684,6 +1846,9 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
   const Cfg& c = h->c;
   TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
   TRY(run_cross_kv(h, s));
+  p.stream_mode = false;
+  CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
+  CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   set_state_kernel<<<1, 1, 0, s>>>(p.state.as<DecodeState>(), 0);
   DevBuf col;
   CU_OK(h, col.alloc(static_cast<size_t>(B) * 8));

@@ -159,10 +159,17 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
 // attended key. A row with no attended key gets extent = S: every score is then
 // finfo(bf16).min and the fp32 softmax is uniform over all S keys, exactly what
 // HF's additive mask produces (masking_utils.py:610-612, modeling_t5.py:323-331).
+// row_on (optional, slot pool admission): rows with row_on[b] == 0 are not part of this encoder pass at all:
+// extent 0, so the packed encoder and the cross-KV projection never touch their rows.
 __global__ void prep_mask_kernel(const long long* __restrict__ mask, unsigned char* __restrict__ key_ok,
-                                 int* __restrict__ extent, int B, int S) {
+                                 int* __restrict__ extent, int B, int S, const int* __restrict__ row_on = nullptr) {
   const int b = blockIdx.x;
   if (b >= B) return;
+  if (row_on != nullptr && !row_on[b]) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) key_ok[static_cast<size_t>(b) * S + j] = 0;
+    if (threadIdx.x == 0) extent[b] = 0;
+    return;
+  }
   int last = -1;
   for (int j = threadIdx.x; j < S; j += blockDim.x) {
     const bool ok = mask == nullptr ? true : mask[static_cast<size_t>(b) * S + j] != 0;
@@ -206,20 +213,75 @@ __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
 }
 
+// ---------------------------------------------------------------- slot pool (b200t5_generate_stream)
+// Start of a streamed run: result rows = [start, pad, ...], every slot idle (position 0, nothing to attend,
+// decoder input = E[pad] so that idle slots compute on finite numbers).
+__global__ void stream_init_kernel(DecodeState* st, int* __restrict__ unfinished, int* __restrict__ pos,
+                                   int* __restrict__ live_extent, long long* __restrict__ out_ids,
+                                   int* __restrict__ out_len, int out_ld, int N, int B, long long start_tok,
+                                   long long pad_tok, const __nv_bfloat16* __restrict__ E, __nv_bfloat16* __restrict__ x,
+                                   int d) {
+  const int r = blockIdx.x;
+  if (r == 0 && threadIdx.x == 0) {
+    st->step = 0;
+    st->finished_rows = 0;
+  }
+  if (r < N) {
+    for (int j = threadIdx.x; j < out_ld; j += blockDim.x)
+      out_ids[static_cast<size_t>(r) * out_ld + j] = j == 0 ? start_tok : pad_tok;
+    if (threadIdx.x == 0) out_len[r] = 0;
+  }
+  if (r < B) {
+    if (threadIdx.x == 0) {
+      unfinished[r] = 0;
+      pos[r] = 0;
+      live_extent[r] = 0;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(pad_tok) * d);
+    uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(r) * d);
+    for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// Admission of n prompts whose encoder pass has just run: slot slots[i] starts prompt rows[i] at position 0.
+__global__ void admit_slots_kernel(const int* __restrict__ slots, const int* __restrict__ rows, int* __restrict__ unfinished,
+                                   int* __restrict__ pos, int* __restrict__ out_row, const int* __restrict__ extent,
+                                   int* __restrict__ live_extent, const unsigned char* __restrict__ key_ok,
+                                   unsigned char* __restrict__ live_key_ok, int S, long long start_tok,
+                                   const __nv_bfloat16* __restrict__ E, __nv_bfloat16* __restrict__ x, int d) {
+  const int b = slots[blockIdx.x];
+  if (threadIdx.x == 0) {
+    unfinished[b] = 1;
+    pos[b] = 0;
+    out_row[b] = rows[blockIdx.x];
+    live_extent[b] = extent[b];
+  }
+  for (int j = threadIdx.x; j < S; j += blockDim.x) live_key_ok[static_cast<size_t>(b) * S + j] = key_ok[static_cast<size_t>(b) * S + j];
+  const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(start_tok) * d);
+  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
 // One CTA per row: reduce the per-tile (max, index) partials of the fused lm_head
 // epilogue with the torch.argmax tie rule (lowest index), then HF's greedy
 // bookkeeping (generation/utils.py:2793-2805):
 //   tok = unfinished ? argmax : pad ; out[b, t+1] = tok ; unfinished &= tok != eos
 // and fetch the embedding of tok as the next step's decoder input.
+// A finished row is RETIRED: live_extent[b] = 0, so the cross-attention of the remaining steps no longer streams
+// its K/V (its outputs are pad tokens whatever it computes).
+// Slot-pool mode (pos != nullptr, b200t5_generate_stream): every slot has its own position pos[b] and writes to
+// row out_row[b] of an [N, out_ld] result; a slot also finishes when it has emitted max_new tokens, idle slots
+// (unfinished == 0) write nothing and stay at position 0.
 __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int n_tiles,
                                      DecodeState* st, int* __restrict__ unfinished,
                                      long long* __restrict__ out_ids, int* __restrict__ out_len, int out_ld,
                                      long long eos_tok, long long pad_tok, const __nv_bfloat16* __restrict__ E,
-                                     __nv_bfloat16* __restrict__ x, int d) {
+                                     __nv_bfloat16* __restrict__ x, int d, int* __restrict__ live_extent,
+                                     int* __restrict__ pos, const int* __restrict__ out_row, int max_new) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
-  const int t = st->step;
+  const int t = pos != nullptr ? pos[b] : st->step;
   float best = -INFINITY;
   int bidx = 0x7fffffff;
   for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
@@ -257,15 +319,20 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
     }
     const int unf = unfinished[b];
     const long long tok = unf ? static_cast<long long>(bidx) : pad_tok;
-    out_ids[static_cast<size_t>(b) * out_ld + t + 1] = tok;
+    const int row = out_row != nullptr ? out_row[b] : b;
+    if (pos == nullptr || unf) out_ids[static_cast<size_t>(row) * out_ld + t + 1] = tok;
+    bool fin = false;
     if (unf) {
-      out_len[b] = t + 1;
-      if (tok == eos_tok) {
+      out_len[row] = t + 1;
+      fin = tok == eos_tok || (pos != nullptr && t + 1 >= max_new);
+      if (fin) {
         unfinished[b] = 0;
+        live_extent[b] = 0;
         atomicAdd(&st->finished_rows, 1);
       }
     }
-    s_tok = tok;
+    if (pos != nullptr) pos[b] = (unf && !fin) ? t + 1 : 0;
+    s_tok = (pos != nullptr && fin) ? pad_tok : tok;
   }
   __syncthreads();
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(s_tok) * d);

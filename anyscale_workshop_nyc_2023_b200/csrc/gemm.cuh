@@ -487,6 +487,7 @@ struct EpiQkvDecode {
     __nv_bfloat16* cache;  // this layer: [2][B][H][Tmax][64]
     const int* step;       // device scalar: current decode position t
     int B, H, Tmax;
+    int step_stride = 0;   // 1 = slot pool: row m appends at its own position step[m]
   };
   static constexpr bool kPaired = false;
   typedef NoPre ChunkPre;
@@ -501,7 +502,7 @@ struct EpiQkvDecode {
     if (n0 < I) {
       dst = p.q + static_cast<size_t>(m) * I + n0;
     } else {
-      const int t = *p.step;
+      const int t = p.step[m * p.step_stride];
       const int r = n0 - I;
       const int kv = r / I;
       const int rem = r - kv * I;
@@ -528,13 +529,14 @@ struct EpiArgmax {
     int n_tiles;
     const int* step;
     int eos, min_new;
+    int step_stride = 0;  // 1 = slot pool: per-row positions
   };
   static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
   template <int BN>
   static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t*, int, int) {
     float best = -INFINITY;
     int bidx = n_tile * BN;  // all -inf (cannot happen with finite logits) -> first column, like torch
-    const bool block_eos = *p.step < p.min_new;
+    const bool block_eos = m_ok && p.step[m * p.step_stride] < p.min_new;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t acc[32];

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 import warnings
 from pathlib import Path
 from types import SimpleNamespace
@@ -75,6 +76,8 @@ class B200T5ForConditionalGeneration:
         self._h = h
         self._index = index
         self.last_lengths: Optional[torch.Tensor] = None
+        # decode slots of the continuous-batching path; generate() switches to it for batches larger than this
+        self.pool_size = int(os.environ.get("B200T5_POOL", "256"))
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -227,6 +230,10 @@ class B200T5ForConditionalGeneration:
             mask = torch.as_tensor(attention_mask).to(device=self._device, dtype=torch.long).contiguous()
             if mask.shape != ids.shape:
                 raise ValueError("attention_mask shape must match input_ids")
+        if B > self.pool_size and os.environ.get("B200T5_STREAM", "1") != "0":
+            # more rows than one pool of decode slots: continuous batching, same tokens row for row
+            out_np, _ = self.generate_stream(ids.cpu().numpy(), None if mask is None else mask.cpu().numpy(), _gen_params=gp)
+            return torch.from_numpy(out_np).to(self._device)
         T = gp.max_new_tokens
         with torch.cuda.device(self._index):
             out = torch.empty((B, T + 1), dtype=torch.long, device=self._device)
@@ -252,6 +259,34 @@ class B200T5ForConditionalGeneration:
         _lib.check(self._lib.b200t5_generate_host(
             self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), B, S,
             C.byref(gp), out.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)), self._h)
+        return out[:, : int(lens.max()) + 1], lens
+
+    def generate_stream(self, input_ids: np.ndarray, attention_mask: Optional[np.ndarray] = None, *, pool: Optional[int] = None,
+                        admit_min: int = 0, _gen_params=None, **kw):
+        """N prompts through a pool of decode slots (b200t5_generate_stream): a slot whose row has finished is
+        refilled with the next prompt, so short answers do not wait for the slowest row of a fixed batch as they do
+        when BatchPredictor hands `generate` one batch at a time (NB:908-913 -> JOB/predictor.py:102). Returns
+        (int64 [N, 1+T'], int32 lengths [N]) with the rows in input order; every row equals what `generate` returns
+        for that prompt."""
+        gp = _gen_params or self._gen_params(kw.get("max_new_tokens"), kw.get("max_length"), kw.get("min_new_tokens"),
+                                             kw.get("min_length"), kw.get("eos_token_id"), kw.get("pad_token_id"),
+                                             kw.get("decoder_start_token_id"), kw.get("poll_interval", 8))
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        if ids.ndim != 2:
+            raise ValueError(f"input_ids must be [batch, seq], got {ids.shape}")
+        N, S = ids.shape
+        if ids.size and (int(ids.min()) < 0 or int(ids.max()) >= self.config.vocab_size):
+            raise IndexError("input_ids contain token ids outside [0, vocab_size)")
+        mask = None if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
+        if mask is not None and mask.shape != ids.shape:
+            raise ValueError("attention_mask shape must match input_ids")
+        out = np.empty((N, gp.max_new_tokens + 1), dtype=np.int64)
+        lens = np.empty((N,), dtype=np.int32)
+        _lib.check(self._lib.b200t5_generate_stream(
+            self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), N, S,
+            C.byref(gp), int(pool or self.pool_size), int(admit_min), out.ctypes.data_as(C.c_void_p),
+            lens.ctypes.data_as(C.c_void_p)), self._h)
+        self.last_lengths = torch.from_numpy(lens)
         return out[:, : int(lens.max()) + 1], lens
 
     def stats(self) -> Dict[str, float]:

@@ -111,6 +111,17 @@ int b200t5_generate(b200t5_handle h, const int64_t* input_ids, const int64_t* at
  * copies results D2H and synchronises. */
 int b200t5_generate_host(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
                          const b200t5_gen_params* params, int64_t* out_ids, int32_t* out_len);
+/* Slot-pool (continuous-batching) variant for a caller that holds more than one batch: the driver loop of
+ * BatchPredictor.predict (Text_generation_with_FLAN_T5.ipynb cell "predictor.predict(...)", NB:908-913) hands
+ * every `batch_size` rows to predictor.py:102 separately, so each batch runs until its slowest row has finished.
+ * Here N prompts (host int64 [N,S] buffers, attention_mask may be NULL) share `pool` decode slots (<= 0: 256):
+ * a slot whose row has emitted EOS or max_new_tokens is refilled with the next prompt once at least `admit_min`
+ * slots are free (<= 0: pool / 8); finished rows stop streaming their K/V at once. out_ids: host int64
+ * [N, max_new_tokens+1], out_len: host int32 [N], row r = prompt r, same layout and - token for token - the same
+ * values as b200t5_generate_host gives for that prompt in a `pool`-row batch. Synchronous. */
+int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids, const int64_t* attention_mask, int64_t N, int S,
+                           const b200t5_gen_params* params, int pool, int admit_min, int64_t* out_ids,
+                           int32_t* out_len);
 int b200t5_get_stats(b200t5_handle h, b200t5_stats* out);
 
 /* ---- measurement hook (bench.py) ---------------------------------------------------- */

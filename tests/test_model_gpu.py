@@ -305,3 +305,82 @@ def test_persistent_decode_kernel_matches_goldens(case, tmp_path, monkeypatch):
     assert np.array_equal(out, again)
     forced = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=T, min_new_tokens=T).cpu().numpy()
     assert forced.shape[1] == T + 1 and (forced[:, 1:] != 1).all()
+
+
+def _static_rows(model, ids, mask, pool, **kw):
+    """Per-prompt tokens of the static path in `pool`-row batches (the last batch is filled up with copies of its
+    first row, so every batch runs the same kernels as the slot pool does)."""
+    N = ids.shape[0]
+    T = kw["max_new_tokens"]
+    out = np.zeros((N, T + 1), dtype=np.int64)
+    lens = np.zeros(N, dtype=np.int32)
+    for lo in range(0, N, pool):
+        hi = min(lo + pool, N)
+        bi, bm = ids[lo:hi], mask[lo:hi]
+        if hi - lo < pool:
+            fill = pool - (hi - lo)
+            bi = np.concatenate([bi, np.repeat(bi[:1], fill, 0)])
+            bm = np.concatenate([bm, np.repeat(bm[:1], fill, 0)])
+        o, ln = model.generate_host(bi, bm, **kw)
+        out[lo:hi, : o.shape[1]] = o[: hi - lo]
+        lens[lo:hi] = ln[: hi - lo]
+    return out, lens
+
+
+@pytest.mark.parametrize("spec_name,seed,N,S,pool,T,admit", [
+    ("tiny", 1, 150, 24, 32, 20, 0),     # several refill rounds, natural EOS
+    ("mini", 2, 300, 40, 128, 16, 1),    # two row-chains, refill as soon as one slot is free
+    ("tiny", 1, 20, 16, 64, 12, 0),      # fewer prompts than slots
+])
+def test_slot_pool_equals_static_batches(models, spec_name, seed, N, S, pool, T, admit):
+    """Continuous batching (b200t5_generate_stream) is a scheduling change only: rows are independent in every
+    kernel, so each prompt's tokens and length are bit-identical to the static path's."""
+    spec = SPECS[spec_name]
+    model, _ = models(spec_name, seed)
+    ids, mask = synthetic_token_batch(N, S, spec.vocab_size, seed=21, lengths="uniform")
+    kw = dict(max_new_tokens=T)
+    ref, ref_len = _static_rows(model, ids, mask, min(pool, N), **kw)
+    out, lens = model.generate_stream(ids, mask, pool=pool, admit_min=admit, **kw)
+    assert len(set(ref_len.tolist())) > 3, "the workload should have varied natural lengths"
+    assert (lens == ref_len).all()
+    w = out.shape[1]
+    assert w == int(ref_len.max()) + 1
+    assert (out == ref[:, :w]).all() and (ref[:, w:] == 0).all()
+    # and again: the pool state of a previous call must not leak into the next one
+    out2, lens2 = model.generate_stream(ids[::-1].copy(), mask[::-1].copy(), pool=pool, admit_min=admit, **kw)
+    assert (out2[::-1] == out).all() and (lens2[::-1] == lens).all()
+
+
+def test_slot_pool_forced_length_and_generate_dispatch(models):
+    """min_new_tokens == max_new_tokens: every slot runs to max_new and is then refilled; generate() itself
+    switches to the slot pool for batches larger than model.pool_size; the static path still works afterwards
+    (the step graph is re-captured when the mode changes)."""
+    spec = SPECS["tiny"]
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(70, 20, spec.vocab_size, seed=22, lengths="uniform")
+    kw = dict(max_new_tokens=9, min_new_tokens=9)
+    ref, ref_len = _static_rows(model, ids, mask, 16, **kw)
+    assert (ref_len == 9).all()
+    old = model.pool_size
+    try:
+        model.pool_size = 16
+        out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), **kw).cpu().numpy()
+    finally:
+        model.pool_size = old
+    assert out.shape == (70, 10) and (out == ref).all()
+    again, _ = model.generate_host(ids[:16], mask[:16], **kw)
+    assert (again == ref[:16]).all()
+
+
+def test_finished_rows_are_retired_in_static_batches(models):
+    """A row that has emitted EOS keeps producing pad tokens and stops reading its cross-KV (live extent 0):
+    results equal the oracle-checked goldens' format (pads after EOS) and a solo run of each row."""
+    spec = SPECS["tiny"]
+    model, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(12, 24, spec.vocab_size, seed=23, lengths="uniform")
+    out, lens = model.generate_host(ids, mask, max_new_tokens=24)
+    assert lens.min() < lens.max()
+    for b in (int(np.argmin(lens)), int(np.argmax(lens))):
+        solo, sl = model.generate_host(ids[b:b + 1], mask[b:b + 1], max_new_tokens=24)
+        assert int(sl[0]) == int(lens[b])
+        assert (out[b, : solo.shape[1]] == solo[0]).all() and (out[b, solo.shape[1]:] == 0).all()
