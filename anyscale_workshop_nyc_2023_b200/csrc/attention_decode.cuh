@@ -20,19 +20,23 @@
 
 namespace b200 {
 
-constexpr float kBf16Min = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
+#if B200T5_F16
+constexpr float kActMin = -65504.0f;                // torch.finfo(torch.float16).min
+#else
+constexpr float kActMin = -3.3895313892515355e38f;  // torch.finfo(torch.bfloat16).min
+#endif
 constexpr int kAttnDecThreads = 128;
 constexpr int kAttnDecUnroll = 8;
 
 DEVINL float dot8(const uint4& kv, const float (&qf)[8]) {
-  float s = bf16_lo(kv.x) * qf[0];
-  s = fmaf(bf16_hi(kv.x), qf[1], s);
-  s = fmaf(bf16_lo(kv.y), qf[2], s);
-  s = fmaf(bf16_hi(kv.y), qf[3], s);
-  s = fmaf(bf16_lo(kv.z), qf[4], s);
-  s = fmaf(bf16_hi(kv.z), qf[5], s);
-  s = fmaf(bf16_lo(kv.w), qf[6], s);
-  s = fmaf(bf16_hi(kv.w), qf[7], s);
+  float s = act_lo(kv.x) * qf[0];
+  s = fmaf(act_hi(kv.x), qf[1], s);
+  s = fmaf(act_lo(kv.y), qf[2], s);
+  s = fmaf(act_hi(kv.y), qf[3], s);
+  s = fmaf(act_lo(kv.z), qf[4], s);
+  s = fmaf(act_hi(kv.z), qf[5], s);
+  s = fmaf(act_lo(kv.w), qf[6], s);
+  s = fmaf(act_hi(kv.w), qf[7], s);
   return s;
 }
 
@@ -48,10 +52,10 @@ struct L2Prefetch {
 
 template <bool kSelf>
 __global__ void __launch_bounds__(kAttnDecThreads)
-attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
-                   const __nv_bfloat16* __restrict__ Kc,   // [B][H][Tk][64]
-                   const __nv_bfloat16* __restrict__ Vc,   // [B][H][Tk][64]
-                   __nv_bfloat16* __restrict__ ctx,        // [B, H*64]
+attn_decode_kernel(const act_t* __restrict__ q,    // [B, H*64]
+                   const act_t* __restrict__ Kc,   // [B][H][Tk][64]
+                   const act_t* __restrict__ Vc,   // [B][H][Tk][64]
+                   act_t* __restrict__ ctx,        // [B, H*64]
                    int H, int Tk,
                    const int* __restrict__ extent,            // cross: [B] keys to visit
                    const unsigned char* __restrict__ key_ok,  // cross: [B][Tk] 1 = attended
@@ -85,14 +89,14 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
   const int t = kSelf ? step[b * step_stride] : 0;
   const int nkeys = kSelf ? t + 1 : extent[b];
   const size_t slab = (static_cast<size_t>(b) * H + h) * static_cast<size_t>(Tk) * 64;
-  const __nv_bfloat16* Kp = Kc + slab + dg * 8;
-  const __nv_bfloat16* Vp = Vc + slab + dg * 8;
+  const act_t* Kp = Kc + slab + dg * 8;
+  const act_t* Vp = Vc + slab + dg * 8;
 
   float qf[8];
   {
     const uint4 qv = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(b) * H + h) * 64 + dg * 8);
-    qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
-    qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+    qf[0] = act_lo(qv.x); qf[1] = act_hi(qv.x); qf[2] = act_lo(qv.y); qf[3] = act_hi(qv.y);
+    qf[4] = act_lo(qv.z); qf[5] = act_hi(qv.z); qf[6] = act_lo(qv.w); qf[7] = act_hi(qv.w);
   }
 
   // ---------------- phase 1: scores
@@ -115,11 +119,11 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
       if (dg == 0 && j < nkeys) {
-        s = bf16_round(s);
+        s = act_round(s);
         if (kSelf) {
-          s = bf16_round(s + dist_bias[h * Tk + (t - j)]);
+          s = act_round(s + dist_bias[h * Tk + (t - j)]);
         } else if (!key_ok[static_cast<size_t>(b) * Tk + j]) {
-          s = kBf16Min;
+          s = kActMin;
         }
         s_scores[j] = s;
       }
@@ -146,7 +150,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
   if (lane == 0) s_stat[4 + warp] = sum;
   __syncthreads();
   sum = (s_stat[4] + s_stat[5]) + (s_stat[6] + s_stat[7]);
-  for (int j = threadIdx.x; j < nkeys; j += kAttnDecThreads) s_scores[j] = bf16_round(s_scores[j] / sum);
+  for (int j = threadIdx.x; j < nkeys; j += kAttnDecThreads) s_scores[j] = act_round(s_scores[j] / sum);
   __syncthreads();
 
   // ---------------- phase 2: out = P . V
@@ -167,14 +171,14 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
     }
 #pragma unroll
     for (int u = 0; u < kAttnDecUnroll; ++u) {
-      acc[0] = fmaf(p[u], bf16_lo(vv[u].x), acc[0]);
-      acc[1] = fmaf(p[u], bf16_hi(vv[u].x), acc[1]);
-      acc[2] = fmaf(p[u], bf16_lo(vv[u].y), acc[2]);
-      acc[3] = fmaf(p[u], bf16_hi(vv[u].y), acc[3]);
-      acc[4] = fmaf(p[u], bf16_lo(vv[u].z), acc[4]);
-      acc[5] = fmaf(p[u], bf16_hi(vv[u].z), acc[5]);
-      acc[6] = fmaf(p[u], bf16_lo(vv[u].w), acc[6]);
-      acc[7] = fmaf(p[u], bf16_hi(vv[u].w), acc[7]);
+      acc[0] = fmaf(p[u], act_lo(vv[u].x), acc[0]);
+      acc[1] = fmaf(p[u], act_hi(vv[u].x), acc[1]);
+      acc[2] = fmaf(p[u], act_lo(vv[u].y), acc[2]);
+      acc[3] = fmaf(p[u], act_hi(vv[u].y), acc[3]);
+      acc[4] = fmaf(p[u], act_lo(vv[u].z), acc[4]);
+      acc[5] = fmaf(p[u], act_hi(vv[u].z), acc[5]);
+      acc[6] = fmaf(p[u], act_lo(vv[u].w), acc[6]);
+      acc[7] = fmaf(p[u], act_hi(vv[u].w), acc[7]);
     }
   }
 #pragma unroll
@@ -191,7 +195,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q,    // [B, H*64]
     const int d0 = threadIdx.x * 2;
     const float o0 = (s_red[0][d0] + s_red[1][d0]) + (s_red[2][d0] + s_red[3][d0]);
     const float o1 = (s_red[0][d0 + 1] + s_red[1][d0 + 1]) + (s_red[2][d0 + 1] + s_red[3][d0 + 1]);
-    *reinterpret_cast<uint32_t*>(ctx + (static_cast<size_t>(b) * H + h) * 64 + d0) = pack_bf16x2(o0, o1);
+    *reinterpret_cast<uint32_t*>(ctx + (static_cast<size_t>(b) * H + h) * 64 + d0) = pack_act2(o0, o1);
   }
 }
 
@@ -205,25 +209,25 @@ constexpr int kSelfWarpsPerCta = 4;
 // kNc: read K/V through the non-coherent path (stand-alone kernel: the cache rows were written by an earlier
 // kernel) or with plain loads (resident kernel: they may have been written by another CTA in the same launch).
 template <bool kNc>
-DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ Kc,
-                                const __nv_bfloat16* __restrict__ Vc, __nv_bfloat16* __restrict__ ctx, int bh, int H, int Tk,
+DEVINL void self_attn_warp_item(const act_t* __restrict__ q, const act_t* __restrict__ Kc,
+                                const act_t* __restrict__ Vc, act_t* __restrict__ ctx, int bh, int H, int Tk,
                                 int t, const float* __restrict__ dist_bias, float* sc) {
   const int lane = threadIdx.x & 31;
   const int h = bh % H;
   const int ks = lane >> 3, dg = lane & 7;
   const int nkeys = t + 1;
   const size_t slab = static_cast<size_t>(bh) * Tk * 64;
-  const __nv_bfloat16* Kp = Kc + slab + dg * 8;
-  const __nv_bfloat16* Vp = Vc + slab + dg * 8;
-  auto load16 = [](const __nv_bfloat16* p) -> uint4 {
+  const act_t* Kp = Kc + slab + dg * 8;
+  const act_t* Vp = Vc + slab + dg * 8;
+  auto load16 = [](const act_t* p) -> uint4 {
     if constexpr (kNc) return ldg_nc_v4(p);
     else return *reinterpret_cast<const uint4*>(p);
   };
   float qf[8];
   {
     const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
-    qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
-    qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+    qf[0] = act_lo(qv.x); qf[1] = act_hi(qv.x); qf[2] = act_lo(qv.y); qf[3] = act_hi(qv.y);
+    qf[4] = act_lo(qv.z); qf[5] = act_hi(qv.z); qf[6] = act_lo(qv.w); qf[7] = act_hi(qv.w);
   }
   constexpr int U = 4;
   for (int jb = 0; jb < nkeys; jb += 4 * U) {
@@ -240,7 +244,7 @@ DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (dg == 0 && j < nkeys) sc[j] = bf16_round(bf16_round(s) + dist_bias[h * Tk + (t - j)]);
+      if (dg == 0 && j < nkeys) sc[j] = act_round(act_round(s) + dist_bias[h * Tk + (t - j)]);
     }
   }
   __syncwarp();
@@ -256,7 +260,7 @@ DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  for (int j = lane; j < nkeys; j += 32) sc[j] = bf16_round(sc[j] / sum);
+  for (int j = lane; j < nkeys; j += 32) sc[j] = act_round(sc[j] / sum);
   __syncwarp();
   float acc[8];
 #pragma unroll
@@ -273,14 +277,14 @@ DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      acc[0] = fmaf(p[u], bf16_lo(vv[u].x), acc[0]);
-      acc[1] = fmaf(p[u], bf16_hi(vv[u].x), acc[1]);
-      acc[2] = fmaf(p[u], bf16_lo(vv[u].y), acc[2]);
-      acc[3] = fmaf(p[u], bf16_hi(vv[u].y), acc[3]);
-      acc[4] = fmaf(p[u], bf16_lo(vv[u].z), acc[4]);
-      acc[5] = fmaf(p[u], bf16_hi(vv[u].z), acc[5]);
-      acc[6] = fmaf(p[u], bf16_lo(vv[u].w), acc[6]);
-      acc[7] = fmaf(p[u], bf16_hi(vv[u].w), acc[7]);
+      acc[0] = fmaf(p[u], act_lo(vv[u].x), acc[0]);
+      acc[1] = fmaf(p[u], act_hi(vv[u].x), acc[1]);
+      acc[2] = fmaf(p[u], act_lo(vv[u].y), acc[2]);
+      acc[3] = fmaf(p[u], act_hi(vv[u].y), acc[3]);
+      acc[4] = fmaf(p[u], act_lo(vv[u].z), acc[4]);
+      acc[5] = fmaf(p[u], act_hi(vv[u].z), acc[5]);
+      acc[6] = fmaf(p[u], act_lo(vv[u].w), acc[6]);
+      acc[7] = fmaf(p[u], act_hi(vv[u].w), acc[7]);
     }
   }
 #pragma unroll
@@ -290,20 +294,20 @@ DEVINL void self_attn_warp_item(const __nv_bfloat16* __restrict__ q, const __nv_
   }
   if (ks == 0) {
     uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
+    o.x = pack_act2(acc[0], acc[1]);
+    o.y = pack_act2(acc[2], acc[3]);
+    o.z = pack_act2(acc[4], acc[5]);
+    o.w = pack_act2(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(bh) * 64 + dg * 8) = o;
   }
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(kSelfWarpsPerCta * 32)
-self_attn_decode_warp_kernel(const __nv_bfloat16* __restrict__ q,   // [B, H*64]
-                             const __nv_bfloat16* __restrict__ Kc,  // [B][H][Tk][64]
-                             const __nv_bfloat16* __restrict__ Vc,
-                             __nv_bfloat16* __restrict__ ctx,       // [B, H*64]
+self_attn_decode_warp_kernel(const act_t* __restrict__ q,   // [B, H*64]
+                             const act_t* __restrict__ Kc,  // [B][H][Tk][64]
+                             const act_t* __restrict__ Vc,
+                             act_t* __restrict__ ctx,       // [B, H*64]
                              int BH, int H, int Tk, const int* __restrict__ step,
                              const float* __restrict__ dist_bias,    // [H][Tk]
                              const int step_stride = 0) {            // 1 = slot pool: per-row positions

@@ -51,7 +51,7 @@ DEVINL void xtc_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthread
 // tmK/tmV: [rows, 64] bf16 maps (box 64 x 128, 128-B swizzle) whose row k_row0 + bh * Tk + j is key j of item bh.
 __global__ void __launch_bounds__(kXtcThreads, 1)
 attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, int k_row0,
-                      int v_row0, const __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ ctx, int bh0, int nitems,
+                      int v_row0, const act_t* __restrict__ q, act_t* __restrict__ ctx, int bh0, int nitems,
                       int H, int Tk, const int* __restrict__ extent, const unsigned char* __restrict__ key_ok,
                       long long* prof = nullptr) {  // diagnostic: SM-clock stamps of CTA 0's softmax thread 0, 8 per item
   extern __shared__ uint8_t xtc_raw[];
@@ -158,8 +158,8 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && my_items > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 16, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+      constexpr uint32_t idesc_s = make_idesc_act(128, 16, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_act(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       auto scores = [&](int i) {  // S[i&1][:, 16c .. 16c+16) = K_c . q^T
@@ -176,7 +176,7 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           const uint64_t dk = make_desc_sw128_kmajor(smem_u32(kring + ks * kXtcChunkBytes));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ss(tmem_base + ib * 64 + c * 16, dk + 2 * kk, dq + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + ib * 64 + c * 16, dk + 2 * kk, dq + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
           umma_commit(&empty[ks]);
           if (++ks == kXtcKStages) {
             ks = 0;
@@ -201,7 +201,7 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA
             const uint64_t dv = make_desc_sw128_mnmajor(smem_u32(vring + vs * kXtcChunkBytes + kk * 2048), 1024, 1024);
             const uint64_t dp = make_desc_sw128_kmajor(smem_u32(ptile + ib * kXtcPTileBytes + (c * 2 + (kk >> 2)) * 1024)) + 2 * (kk & 3);
-            umma_bf16_ss(tmem_base + 128 + ib * 64, dp, dv, idesc_o, (c | kk) != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + 128 + ib * 64, dp, dv, idesc_o, (c | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[kXtcKStages + vs]);
           if (++vs == kXtcVStages) {
@@ -266,16 +266,16 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           uint4* dst = reinterpret_cast<uint4*>(ctx + static_cast<size_t>(item_bh(k)) * 64);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            dst[g] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * g]), __uint_as_float(o0[8 * g + 1])),
-                                pack_bf16x2(__uint_as_float(o0[8 * g + 2]), __uint_as_float(o0[8 * g + 3])),
-                                pack_bf16x2(__uint_as_float(o0[8 * g + 4]), __uint_as_float(o0[8 * g + 5])),
-                                pack_bf16x2(__uint_as_float(o0[8 * g + 6]), __uint_as_float(o0[8 * g + 7])));
+            dst[g] = make_uint4(pack_act2(__uint_as_float(o0[8 * g]), __uint_as_float(o0[8 * g + 1])),
+                                pack_act2(__uint_as_float(o0[8 * g + 2]), __uint_as_float(o0[8 * g + 3])),
+                                pack_act2(__uint_as_float(o0[8 * g + 4]), __uint_as_float(o0[8 * g + 5])),
+                                pack_act2(__uint_as_float(o0[8 * g + 6]), __uint_as_float(o0[8 * g + 7])));
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            dst[4 + g] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * g]), __uint_as_float(o1[8 * g + 1])),
-                                    pack_bf16x2(__uint_as_float(o1[8 * g + 2]), __uint_as_float(o1[8 * g + 3])),
-                                    pack_bf16x2(__uint_as_float(o1[8 * g + 4]), __uint_as_float(o1[8 * g + 5])),
-                                    pack_bf16x2(__uint_as_float(o1[8 * g + 6]), __uint_as_float(o1[8 * g + 7])));
+            dst[4 + g] = make_uint4(pack_act2(__uint_as_float(o1[8 * g]), __uint_as_float(o1[8 * g + 1])),
+                                    pack_act2(__uint_as_float(o1[8 * g + 2]), __uint_as_float(o1[8 * g + 3])),
+                                    pack_act2(__uint_as_float(o1[8 * g + 4]), __uint_as_float(o1[8 * g + 5])),
+                                    pack_act2(__uint_as_float(o1[8 * g + 6]), __uint_as_float(o1[8 * g + 7])));
         }
       }
       tc_fence_before_sync();
@@ -317,8 +317,8 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         const int jg = c * kXtcChunkKeys + j;
         float v = -INFINITY;
         if (c < nc && jg < nk) {
-          v = bf16_round(__uint_as_float(raw[c]));
-          if (!((okbits >> c) & 1u)) v = kBf16Min;
+          v = act_round(__uint_as_float(raw[c]));
+          if (!((okbits >> c) & 1u)) v = kActMin;
         }
         sc[c] = v;
         mx = fmaxf(mx, v);
@@ -344,8 +344,8 @@ attn_decode_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       mbar_wait(&p_free[ib], par ^ 1u);  // the P.V MMAs of item i-2 have consumed this buffer
       if (pr) prof[i * 8 + 4] = clock64();
       for (int c = 0; c < nc; ++c)
-        *reinterpret_cast<__nv_bfloat16*>(ptile + ib * kXtcPTileBytes + (c * 2 + (j >> 6)) * 1024 + (j & 63) * 2) =
-            __float2bfloat16_rn(sc[c] / sum);
+        *reinterpret_cast<act_t*>(ptile + ib * kXtcPTileBytes + (c * 2 + (j >> 6)) * 1024 + (j & 63) * 2) =
+            float2act(sc[c] / sum);
       fence_proxy_async_smem();
       mbar_arrive(&p_full[ib]);
       if (pr) prof[i * 8 + 5] = clock64();

@@ -41,7 +41,7 @@ DEVINL void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+DEVINL void mma_act_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -52,18 +52,18 @@ DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, u
 DEVINL uint32_t tile_off(int row, int chunk) { return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 // Load a 64x64 bf16 tile (rows row0.. of a [rows, ld] matrix at column col0) into swizzled smem.
-DEVINL void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, int ld, int row0, int nrows_valid) {
+DEVINL void load_tile_async(uint32_t smem_base, const act_t* g, int ld, int row0, int nrows_valid) {
   for (int i = threadIdx.x; i < 64 * 8; i += kEncThreads) {
     const int r = i >> 3, c = i & 7;
     const bool ok = r < nrows_valid;
-    const __nv_bfloat16* src = g + static_cast<size_t>(row0 + (ok ? r : 0)) * ld + c * 8;
+    const act_t* src = g + static_cast<size_t>(row0 + (ok ? r : 0)) * ld + c * 8;
     cp_async_16(smem_base + tile_off(r, c), src, ok);
   }
 }
 
 __global__ void __launch_bounds__(kEncThreads)
-encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
-                    __nv_bfloat16* __restrict__ ctx,           // [B*S, I]
+encoder_attn_kernel(const act_t* __restrict__ qkv,     // [B*S, 3I]
+                    act_t* __restrict__ ctx,           // [B*S, I]
                     const float* __restrict__ rel_bias,        // [H][2S-1], index j - i + S - 1
                     const unsigned char* __restrict__ key_ok,  // [B][S]
                     const int* __restrict__ extent,            // [B]
@@ -86,9 +86,9 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
 
   const int ext = extent[b];
   const int nchunks = (ext + kEncKC - 1) / kEncKC;
-  const __nv_bfloat16* qg = qkv + static_cast<size_t>(b) * S * ld + h * 64;
-  const __nv_bfloat16* kg = qg + I;
-  const __nv_bfloat16* vg = qg + 2 * I;
+  const act_t* qg = qkv + static_cast<size_t>(b) * S * ld + h * 64;
+  const act_t* kg = qg + I;
+  const act_t* vg = qg + 2 * I;
 
   // bias slice + mask row (plain loads), Q tile + first K chunk (async)
   {
@@ -164,8 +164,8 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
           const int ch = kk * 2 + (mi & 1);
           uint32_t b0, b1, b2, b3;
           ldmatrix_x4(kbase + tile_off(key, ch), b0, b1, b2, b3);
-          mma_bf16_16816(sacc[2 * np], qa[kk], b0, b1);
-          mma_bf16_16816(sacc[2 * np + 1], qa[kk], b2, b3);
+          mma_act_16816(sacc[2 * np], qa[kk], b0, b1);
+          mma_act_16816(sacc[2 * np + 1], qa[kk], b2, b3);
         }
       }
 
@@ -177,10 +177,10 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
         for (int e = 0; e < 4; ++e) {
           const int j = jc + nt * 8 + tq * 2 + (e & 1);
           const int rl = row_l0 + (e >> 1) * 8;
-          float s = bf16_round(sacc[nt][e]);
+          float s = act_round(sacc[nt][e]);
           if (j < ext) {
-            s = bf16_round(s + sBias[j - rl + 63]);
-            if (!sOk[j]) s = kBf16Min;
+            s = act_round(s + sBias[j - rl + 63]);
+            if (!sOk[j]) s = kActMin;
           } else {
             s = -INFINITY;
           }
@@ -209,11 +209,11 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // 16 keys per k-step = n-tiles 2kk, 2kk+1 of S
           uint32_t pa[4];
-          pa[0] = pack_bf16x2(expf(sacc[2 * kk][0] - m_run[0]) / l_run[0], expf(sacc[2 * kk][1] - m_run[0]) / l_run[0]);
-          pa[1] = pack_bf16x2(expf(sacc[2 * kk][2] - m_run[1]) / l_run[1], expf(sacc[2 * kk][3] - m_run[1]) / l_run[1]);
-          pa[2] = pack_bf16x2(expf(sacc[2 * kk + 1][0] - m_run[0]) / l_run[0],
+          pa[0] = pack_act2(expf(sacc[2 * kk][0] - m_run[0]) / l_run[0], expf(sacc[2 * kk][1] - m_run[0]) / l_run[0]);
+          pa[1] = pack_act2(expf(sacc[2 * kk][2] - m_run[1]) / l_run[1], expf(sacc[2 * kk][3] - m_run[1]) / l_run[1]);
+          pa[2] = pack_act2(expf(sacc[2 * kk + 1][0] - m_run[0]) / l_run[0],
                               expf(sacc[2 * kk + 1][1] - m_run[0]) / l_run[0]);
-          pa[3] = pack_bf16x2(expf(sacc[2 * kk + 1][2] - m_run[1]) / l_run[1],
+          pa[3] = pack_act2(expf(sacc[2 * kk + 1][2] - m_run[1]) / l_run[1],
                               expf(sacc[2 * kk + 1][3] - m_run[1]) / l_run[1]);
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {  // pairs of d-tiles (16 dims)
@@ -222,8 +222,8 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
             const int ch = dp * 2 + (mi >> 1);
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4_trans(vbase + tile_off(key, ch), b0, b1, b2, b3);
-            mma_bf16_16816(oacc[2 * dp], pa, b0, b1);
-            mma_bf16_16816(oacc[2 * dp + 1], pa, b2, b3);
+            mma_act_16816(oacc[2 * dp], pa, b0, b1);
+            mma_act_16816(oacc[2 * dp + 1], pa, b2, b3);
           }
         }
       }
@@ -236,10 +236,10 @@ encoder_attn_kernel(const __nv_bfloat16* __restrict__ qkv,     // [B*S, 3I]
   for (int r = 0; r < 2; ++r) {
     const int i = i0 + row_l0 + r * 8;
     if (i < S) {
-      __nv_bfloat16* dst = ctx + (static_cast<size_t>(b) * S + i) * I + h * 64 + tq * 2;
+      act_t* dst = ctx + (static_cast<size_t>(b) * S + i) * I + h * 64 + tq * 2;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
-        *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16x2(oacc[nt][2 * r], oacc[nt][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_act2(oacc[nt][2 * r], oacc[nt][2 * r + 1]);
     }
   }
 }

@@ -60,7 +60,7 @@ struct EncTcSmem {
 
 __global__ void __launch_bounds__(kEncTcThreads, 1)
 encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] bf16, box 64 x 128
-                       __nv_bfloat16* __restrict__ ctx,            // [B*S, I]
+                       act_t* __restrict__ ctx,            // [B*S, I]
                        const float* __restrict__ rel_bias,         // [H][2S-1], index j - i + S - 1
                        const unsigned char* __restrict__ key_ok,   // [B][S]
                        const int* __restrict__ extent,             // [B]
@@ -121,8 +121,8 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     };
     for (int k = t; k < (S + 128) / 2; k += kEncTcCompute) {
       const float b0 = bias_at(2 * k), b1 = bias_at(2 * k + 1), b2 = bias_at(2 * k + 2);
-      sT0[k] = pack_bf16x2(b0, b1);
-      sT1[k] = pack_bf16x2(b1, b2);
+      sT0[k] = pack_act2(b0, b1);
+      sT1[k] = pack_act2(b1, b2);
     }
     int holes = 0;
     for (int x = t; x < S; x += kEncTcCompute) {
@@ -150,17 +150,17 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       mbar_wait(bar_load, 0);
       tc_fence_after_sync();
       // ---------------- S[:, 128c : 128c+128] = Q K_c^T
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_act(128, 128, 0, 0);
       const uint64_t dq = make_desc_sw128_kmajor(smem_u32(sQ));
       for (int c = 0; c < nchunks; ++c) {
         const uint64_t dk = make_desc_sw128_kmajor(smem_u32(sK + c * 16384));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(tmem_base + c * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + c * 128, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
       }
       umma_commit(bar_s);
       // ---------------- O += P_c V_c as the softmax warps hand chunks over
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+      constexpr uint32_t idesc_o = make_idesc_act(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
         mbar_wait(&bar_pfull[buf], (c >> 1) & 1);
@@ -170,7 +170,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t dp = make_desc_sw128_kmajor(pbase + (kk >> 2) * 16384) + 2 * (kk & 3);
           const uint64_t dv = make_desc_sw128_mnmajor(smem_u32(sV + c * 16384 + kk * 2048), 1024, 1024);
-          umma_bf16_ss(tmem_base, dp, dv, idesc_o, (c | kk) != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base, dp, dv, idesc_o, (c | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&bar_pfree[buf]);
       }
@@ -193,7 +193,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     // back over the first 16 columns of the 32-column block they came from.
     const bool holes = *sHoles != 0;
     const uint32_t* tab = ((127 - il) & 1) ? sT1 : sT0;
-    __nv_bfloat162 mx2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    act2_t mx2 = floats2act2(-INFINITY, -INFINITY);
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       const int jb = c * kEncTcChunk + part * 32;
@@ -205,9 +205,9 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       if (jb + 32 <= ext && !holes) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
-          const uint32_t sb = pack_bf16x2(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1]));
+          const uint32_t sb = pack_act2(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1]));
           const uint32_t bb = tab[k0 + t];
-          const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&sb), *reinterpret_cast<const __nv_bfloat162*>(&bb));
+          const act2_t r = __hadd2(*reinterpret_cast<const act2_t*>(&sb), *reinterpret_cast<const act2_t*>(&bb));
           mx2 = __hmax2(mx2, r);
           pk[t] = *reinterpret_cast<const uint32_t*>(&r);
         }
@@ -218,17 +218,17 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int j = jb + 2 * t + e;
-            float sc = bf16_round(__uint_as_float(v[2 * t + e]));
+            float sc = act_round(__uint_as_float(v[2 * t + e]));
             if (j < ext) {
               const uint32_t bb = tab[k0 + t];
-              sc = bf16_round(sc + (e ? bf16_hi(bb) : bf16_lo(bb)));
-              if (holes && !sOk[j]) sc = kBf16Min;
+              sc = act_round(sc + (e ? act_hi(bb) : act_lo(bb)));
+              if (holes && !sOk[j]) sc = kActMin;
             } else {
               sc = -INFINITY;
             }
             r2[e] = sc;
           }
-          const __nv_bfloat162 r = __floats2bfloat162_rn(r2[0], r2[1]);  // exact: both are bf16 values
+          const act2_t r = floats2act2(r2[0], r2[1]);  // exact: both are bf16 values
           mx2 = __hmax2(mx2, r);
           pk[t] = *reinterpret_cast<const uint32_t*>(&r);
         }
@@ -253,8 +253,8 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       uint32_t v[32];
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
-        const float e0 = expf(bf16_lo(pk[t]) - mx);
-        const float e1 = expf(bf16_hi(pk[t]) - mx);
+        const float e0 = expf(act_lo(pk[t]) - mx);
+        const float e1 = expf(act_hi(pk[t]) - mx);
         sum += e0;
         sum += e1;
         v[2 * t] = __float_as_uint(e0);
@@ -285,7 +285,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       uint32_t pk[16];  // 32 keys of this thread's row, packed bf16x2
 #pragma unroll
       for (int t = 0; t < 16; ++t)
-        pk[t] = pack_bf16x2(__uint_as_float(v[2 * t]) * inv_sum, __uint_as_float(v[2 * t + 1]) * inv_sum);
+        pk[t] = pack_act2(__uint_as_float(v[2 * t]) * inv_sum, __uint_as_float(v[2 * t + 1]) * inv_sum);
       if (c >= 2) mbar_wait(&bar_pfree[buf], ((c - 2) >> 1) & 1);
       // (chunks 0/1: K's smem is free once bar_s completed, i.e. all Q K^T MMAs are done)
       // keys part*32.. of the chunk = sub-tile part/2 (64 keys each), 16-B groups (part&1)*4 .. +3 of the row
@@ -311,7 +311,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       if (i < ext) {  // rows beyond the prompt's extent are padding (in the packed layout: another prompt's rows)
         uint32_t pkd[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) pkd[t] = pack_bf16x2(__uint_as_float(o[2 * t]), __uint_as_float(o[2 * t + 1]));
+        for (int t = 0; t < 8; ++t) pkd[t] = pack_act2(__uint_as_float(o[2 * t]), __uint_as_float(o[2 * t + 1]));
         uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(cu ? cu[b] : b * S) + i) * I + h * 64 + part * 16);
         dst[0] = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
         dst[1] = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);

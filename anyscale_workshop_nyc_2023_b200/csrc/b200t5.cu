@@ -32,7 +32,6 @@
 #include "decode_mega.cuh"
 
 using namespace b200;
-typedef __nv_bfloat16 bf16;
 
 // ================================================================== error plumbing
 static thread_local char g_err[512] = "";
@@ -91,28 +90,28 @@ static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
 }
 
 // ================================================================== small device helpers
-__global__ void convert_to_bf16_kernel(const void* src, int dtype, bf16* dst, size_t n) {
+__global__ void convert_to_act_kernel(const void* src, int dtype, act_t* dst, size_t n) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) {
     float v;
     if (dtype == B200T5_DTYPE_F32) v = reinterpret_cast<const float*>(src)[i];
     else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
-    dst[i] = __float2bfloat16_rn(v);
+    dst[i] = float2act(v);
   }
 }
 // mode 0: the engine's path (table lookup); 1/2: op-by-op arithmetic with pow_mode 1/0
-__global__ void geglu_elementwise_kernel(const bf16* gate, const bf16* up, bf16* out, long long n, int mode, GeluLut lut) {
+__global__ void geglu_elementwise_kernel(const act_t* gate, const act_t* up, act_t* out, long long n, int mode, GeluLut lut) {
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
-  const float x = __bfloat162float(gate[i]);
-  const float g = mode == 0 ? gelu_from_lut(x, lut.table, lut.lo, lut.hi) : gelu_new_bf16_exact(x, mode == 1 ? 1 : 0);
-  out[i] = __float2bfloat16_rn(g * __bfloat162float(up[i]));
+  const float x = act2float(gate[i]);
+  const float g = mode == 0 ? gelu_from_lut(x, lut.table, lut.lo, lut.hi) : gelu_new_act_exact(x, mode == 1 ? 1 : 0);
+  out[i] = float2act(g * act2float(up[i]));
 }
 __global__ void build_gelu_table_kernel(uint16_t* full, int pow_mode) {
   const uint32_t bits = blockIdx.x * blockDim.x + threadIdx.x;  // every bf16 bit pattern
   if (bits >= 65536u) return;
-  const float g = gelu_new_bf16_exact(__uint_as_float(bits << 16), pow_mode);
+  const float g = gelu_new_act_exact(__uint_as_float(bits << 16), pow_mode);
   full[bits] = static_cast<uint16_t>(__float_as_uint(g) >> 16);
 }
 __global__ void set_state_kernel(DecodeState* st, int step) {
@@ -418,7 +417,7 @@ static cudaError_t run_gemm_sk_norm(b200t5_ctx* h, const b200t5_ctx::SkChoice& c
   return launch_gemm_splitk<64, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
 }
 
-static cudaError_t run_rmsnorm(b200t5_ctx* h, const bf16* x, const bf16* w, bf16* y, int M, int d, float eps,
+static cudaError_t run_rmsnorm(b200t5_ctx* h, const act_t* x, const act_t* w, act_t* y, int M, int d, float eps,
                                cudaStream_t s, bool pdl = false) {
   if (h) h->launches++;
   const int wpb = 8;
@@ -643,11 +642,11 @@ extern "C" int b200t5_set_weight(b200t5_handle h, const char* name, const void* 
     n *= static_cast<size_t>(shape[i]);
   }
   std::unique_ptr<DevBuf> buf(new DevBuf());
-  CU_OK(h, buf->alloc(n * sizeof(bf16)));
+  CU_OK(h, buf->alloc(n * sizeof(act_t)));
   if (dtype == B200T5_DTYPE_BF16) {
-    CU_OK(h, cudaMemcpy(buf->p, dev_ptr, n * sizeof(bf16), cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(buf->p, dev_ptr, n * sizeof(act_t), cudaMemcpyDeviceToDevice));
   } else {
-    convert_to_bf16_kernel<<<1024, 256>>>(dev_ptr, dtype, buf->as<bf16>(), n);
+    convert_to_act_kernel<<<1024, 256>>>(dev_ptr, dtype, buf->as<act_t>(), n);
     CU_OK(h, cudaGetLastError());
     CU_OK(h, cudaDeviceSynchronize());
   }
@@ -657,7 +656,7 @@ extern "C" int b200t5_set_weight(b200t5_handle h, const char* name, const void* 
 }
 
 // fetch a raw tensor, checking its shape
-static bf16* take(b200t5_ctx* h, const std::string& name, int64_t r, int64_t c, int* rc) {
+static act_t* take(b200t5_ctx* h, const std::string& name, int64_t r, int64_t c, int* rc) {
   auto it = h->raw.find(name);
   if (it == h->raw.end()) {
     *rc = fail(h, B200T5_ESTATE, "finalize: missing weight '%s'", name.c_str());
@@ -669,29 +668,29 @@ static bf16* take(b200t5_ctx* h, const std::string& name, int64_t r, int64_t c, 
     *rc = fail(h, B200T5_EINVAL, "finalize: weight '%s' has the wrong shape", name.c_str());
     return nullptr;
   }
-  return it->second->as<bf16>();
+  return it->second->as<act_t>();
 }
 
 // dst[ntiles*bn, d]: per tile, bn/2 rows of wi_0 followed by the matching bn/2 rows of wi_1.
-static int interleave_geglu(b200t5_ctx* h, const bf16* wi0, const bf16* wi1, DevBuf& dst, int F, int d, int bn,
+static int interleave_geglu(b200t5_ctx* h, const act_t* wi0, const act_t* wi1, DevBuf& dst, int F, int d, int bn,
                             int* rows_out) {
   const int half = bn / 2;
   const int ntiles = (F + half - 1) / half;
-  CU_OK(h, dst.alloc(static_cast<size_t>(ntiles) * bn * d * sizeof(bf16)));
+  CU_OK(h, dst.alloc(static_cast<size_t>(ntiles) * bn * d * sizeof(act_t)));
   CU_OK(h, cudaMemset(dst.p, 0, dst.bytes));
   for (int j = 0; j < ntiles; ++j) {
     const int rows = (j + 1) * half <= F ? half : F - j * half;
-    bf16* base = dst.as<bf16>() + static_cast<size_t>(j) * bn * d;
-    CU_OK(h, cudaMemcpy(base, wi0 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(bf16), cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(base + static_cast<size_t>(half) * d, wi1 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(bf16), cudaMemcpyDeviceToDevice));
+    act_t* base = dst.as<act_t>() + static_cast<size_t>(j) * bn * d;
+    CU_OK(h, cudaMemcpy(base, wi0 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(act_t), cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(base + static_cast<size_t>(half) * d, wi1 + static_cast<size_t>(j) * half * d, static_cast<size_t>(rows) * d * sizeof(act_t), cudaMemcpyDeviceToDevice));
   }
   *rows_out = ntiles * bn;
   return B200T5_OK;
 }
 
-static int clone_buf(b200t5_ctx* h, DevBuf& dst, const bf16* src, size_t n) {
-  CU_OK(h, dst.alloc(n * sizeof(bf16)));
-  CU_OK(h, cudaMemcpy(dst.p, src, n * sizeof(bf16), cudaMemcpyDeviceToDevice));
+static int clone_buf(b200t5_ctx* h, DevBuf& dst, const act_t* src, size_t n) {
+  CU_OK(h, dst.alloc(n * sizeof(act_t)));
+  CU_OK(h, cudaMemcpy(dst.p, src, n * sizeof(act_t), cudaMemcpyDeviceToDevice));
   return B200T5_OK;
 }
 
@@ -713,16 +712,16 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
   int rc = B200T5_OK;
   const int d = c.d, I = c.I, F = c.F;
 
-  bf16* shared = take(h, "shared.weight", c.V, d, &rc);
+  act_t* shared = take(h, "shared.weight", c.V, d, &rc);
   if (!shared) return rc;
   TRY(clone_buf(h, h->shared, shared, static_cast<size_t>(c.V) * d));
   // real FLAN-T5 checkpoints carry a separate lm_head; a checkpoint without one is tied
-  const bf16* lm = h->raw.count("lm_head.weight") ? take(h, "lm_head.weight", c.V, d, &rc) : shared;
+  const act_t* lm = h->raw.count("lm_head.weight") ? take(h, "lm_head.weight", c.V, d, &rc) : shared;
   if (!lm) return rc;
   TRY(clone_buf(h, h->lm_head, lm, static_cast<size_t>(c.V) * d));
   TMAP(h, &h->tm_lm, h->lm_head.p, c.V, d, 128);
 
-  bf16* p;
+  act_t* p;
   if (!(p = take(h, "encoder.final_layer_norm.weight", d, 0, &rc))) return rc;
   TRY(clone_buf(h, h->enc_final_ln, p, d));
   if (!(p = take(h, "decoder.final_layer_norm.weight", d, 0, &rc))) return rc;
@@ -732,11 +731,11 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
   for (int side = 0; side < 2; ++side) {
     const std::string nm = std::string(side ? "decoder" : "encoder") + ".block.0.layer.0.SelfAttention.relative_attention_bias.weight";
     if (!(p = take(h, nm, c.nb, c.H, &rc))) return rc;
-    std::vector<bf16> tmp(static_cast<size_t>(c.nb) * c.H);
-    CU_OK(h, cudaMemcpy(tmp.data(), p, tmp.size() * sizeof(bf16), cudaMemcpyDeviceToHost));
+    std::vector<act_t> tmp(static_cast<size_t>(c.nb) * c.H);
+    CU_OK(h, cudaMemcpy(tmp.data(), p, tmp.size() * sizeof(act_t), cudaMemcpyDeviceToHost));
     std::vector<float>& dst = side ? h->dec_relbias_h : h->enc_relbias_h;
     dst.resize(tmp.size());
-    for (size_t i = 0; i < tmp.size(); ++i) dst[i] = __bfloat162float(tmp[i]);
+    for (size_t i = 0; i < tmp.size(); ++i) dst[i] = act2float(tmp[i]);
   }
 
   char nm[256];
@@ -750,19 +749,19 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TRY(clone_buf(h, w.ln0, p, d));
     if (!(p = take(h, key("layer.1.layer_norm.weight"), d, 0, &rc))) return rc;
     TRY(clone_buf(h, w.ln1, p, d));
-    const bf16* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
-    const bf16* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
-    const bf16* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
+    const act_t* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
+    const act_t* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
+    const act_t* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
     if (!v) return rc;
-    CU_OK(h, w.wqkv.alloc(static_cast<size_t>(3) * I * d * sizeof(bf16)));
+    CU_OK(h, w.wqkv.alloc(static_cast<size_t>(3) * I * d * sizeof(act_t)));
     const size_t blk = static_cast<size_t>(I) * d;
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>(), q, blk * 2, cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>(), q, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
     if (!(p = take(h, key("layer.0.SelfAttention.o.weight"), d, I, &rc))) return rc;
     TRY(clone_buf(h, w.wo, p, static_cast<size_t>(d) * I));
-    const bf16* wi0 = take(h, key("layer.1.DenseReluDense.wi_0.weight"), F, d, &rc);
-    const bf16* wi1 = wi0 ? take(h, key("layer.1.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
+    const act_t* wi0 = take(h, key("layer.1.DenseReluDense.wi_0.weight"), F, d, &rc);
+    const act_t* wi1 = wi0 ? take(h, key("layer.1.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
     if (!wi1) return rc;
     int wi_rows = 0;
     TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, 256, &wi_rows));
@@ -778,7 +777,7 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TMAP(h, &w.tm2_ffo, w.wff_o.p, d, F, 128);
   }
 
-  CU_OK(h, h->wcrosskv.alloc(static_cast<size_t>(c.Ld) * 2 * I * d * sizeof(bf16)));
+  CU_OK(h, h->wcrosskv.alloc(static_cast<size_t>(c.Ld) * 2 * I * d * sizeof(act_t)));
   for (int l = 0; l < c.Ld; ++l) {
     DecLayerW& w = h->dec[l];
     auto key = [&](const char* suffix) {
@@ -791,28 +790,28 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TRY(clone_buf(h, w.ln1, p, d));
     if (!(p = take(h, key("layer.2.layer_norm.weight"), d, 0, &rc))) return rc;
     TRY(clone_buf(h, w.ln2, p, d));
-    const bf16* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
-    const bf16* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
-    const bf16* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
+    const act_t* q = take(h, key("layer.0.SelfAttention.q.weight"), I, d, &rc);
+    const act_t* k = q ? take(h, key("layer.0.SelfAttention.k.weight"), I, d, &rc) : nullptr;
+    const act_t* v = k ? take(h, key("layer.0.SelfAttention.v.weight"), I, d, &rc) : nullptr;
     if (!v) return rc;
     const size_t blk = static_cast<size_t>(I) * d;
-    CU_OK(h, w.wqkv.alloc(3 * blk * sizeof(bf16)));
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>(), q, blk * 2, cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(w.wqkv.as<bf16>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, w.wqkv.alloc(3 * blk * sizeof(act_t)));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>(), q, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>() + blk, k, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(w.wqkv.as<act_t>() + 2 * blk, v, blk * 2, cudaMemcpyDeviceToDevice));
     if (!(p = take(h, key("layer.0.SelfAttention.o.weight"), d, I, &rc))) return rc;
     TRY(clone_buf(h, w.wo, p, static_cast<size_t>(d) * I));
     if (!(p = take(h, key("layer.1.EncDecAttention.q.weight"), I, d, &rc))) return rc;
     TRY(clone_buf(h, w.wcq, p, blk));
-    const bf16* ck = take(h, key("layer.1.EncDecAttention.k.weight"), I, d, &rc);
-    const bf16* cv = ck ? take(h, key("layer.1.EncDecAttention.v.weight"), I, d, &rc) : nullptr;
+    const act_t* ck = take(h, key("layer.1.EncDecAttention.k.weight"), I, d, &rc);
+    const act_t* cv = ck ? take(h, key("layer.1.EncDecAttention.v.weight"), I, d, &rc) : nullptr;
     if (!cv) return rc;
-    CU_OK(h, cudaMemcpy(h->wcrosskv.as<bf16>() + (static_cast<size_t>(l) * 2 + 0) * blk, ck, blk * 2, cudaMemcpyDeviceToDevice));
-    CU_OK(h, cudaMemcpy(h->wcrosskv.as<bf16>() + (static_cast<size_t>(l) * 2 + 1) * blk, cv, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(h->wcrosskv.as<act_t>() + (static_cast<size_t>(l) * 2 + 0) * blk, ck, blk * 2, cudaMemcpyDeviceToDevice));
+    CU_OK(h, cudaMemcpy(h->wcrosskv.as<act_t>() + (static_cast<size_t>(l) * 2 + 1) * blk, cv, blk * 2, cudaMemcpyDeviceToDevice));
     if (!(p = take(h, key("layer.1.EncDecAttention.o.weight"), d, I, &rc))) return rc;
     TRY(clone_buf(h, w.wco, p, static_cast<size_t>(d) * I));
-    const bf16* wi0 = take(h, key("layer.2.DenseReluDense.wi_0.weight"), F, d, &rc);
-    const bf16* wi1 = wi0 ? take(h, key("layer.2.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
+    const act_t* wi0 = take(h, key("layer.2.DenseReluDense.wi_0.weight"), F, d, &rc);
+    const act_t* wi1 = wi0 ? take(h, key("layer.2.DenseReluDense.wi_1.weight"), F, d, &rc) : nullptr;
     if (!wi1) return rc;
     int wi_rows = 0;
     // TMA box rows = the N-tile of the kernel that will read the weight (split-K or persistent)
@@ -906,11 +905,11 @@ static int build_mega(b200t5_ctx* h, Plan& pl) {
     L.tm_co = dmaps + 6 * l + 3;
     L.tm_wi = dmaps + 6 * l + 4;
     L.tm_ffo = dmaps + 6 * l + 5;
-    L.ln0 = w.ln0.as<bf16>();
-    L.ln1 = w.ln1.as<bf16>();
-    L.ln2 = w.ln2.as<bf16>();
-    L.self_kv = pl.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T);
-    L.cross_kv = pl.cross_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * S);
+    L.ln0 = w.ln0.as<act_t>();
+    L.ln1 = w.ln1.as<act_t>();
+    L.ln2 = w.ln2.as<act_t>();
+    L.self_kv = pl.self_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * T);
+    L.cross_kv = pl.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S);
     L.wi_rows = w.mega_wi_rows;
   }
   CUtensorMap* a = &maps[6 * c.Ld];
@@ -923,11 +922,11 @@ static int build_mega(b200t5_ctx* h, Plan& pl) {
   MegaParams& P = pl.mega;
   P.B = B; P.S = S; P.T = T; P.d = d; P.I = I; P.F = F; P.H = c.H; P.V = c.V; P.Ld = c.Ld;
   P.eps = c.eps;
-  P.dx = pl.dx.as<bf16>(); P.dxn = pl.dxn.as<bf16>(); P.dq = pl.dq.as<bf16>(); P.dctx = pl.dctx.as<bf16>(); P.dh = pl.dh.as<bf16>();
+  P.dx = pl.dx.as<act_t>(); P.dxn = pl.dxn.as<act_t>(); P.dq = pl.dq.as<act_t>(); P.dctx = pl.dctx.as<act_t>(); P.dh = pl.dh.as<act_t>();
   P.ws = pl.mega_ws.as<float>();
   P.tm_dxn = dmaps + 6 * c.Ld; P.tm_dctx = dmaps + 6 * c.Ld + 1; P.tm_dh = dmaps + 6 * c.Ld + 2; P.tm_lm = dmaps + 6 * c.Ld + 3;
   P.layers = pl.mega_layers.as<MegaLayer>();
-  P.final_ln = h->dec_final_ln.as<bf16>(); P.E = h->shared.as<bf16>();
+  P.final_ln = h->dec_final_ln.as<act_t>(); P.E = h->shared.as<act_t>();
   P.extent = pl.extent.as<int>(); P.key_ok = pl.key_ok.as<unsigned char>(); P.dec_bias = pl.dec_bias.as<float>();
   P.st = pl.state.as<DecodeState>(); P.unfinished = pl.unfinished.as<int>(); P.out_ids = pl.out_ids.as<long long>();
   P.out_len = pl.out_len.as<int>(); P.pval = pl.pval.as<float>(); P.pidx = pl.pidx.as<int>(); P.n_vtiles = pl.n_vtiles;
@@ -1050,10 +1049,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
       Plan::Chain& ch = pl->chains[i];
       ch.b0 = static_cast<int>(static_cast<long long>(B) * i / nc);
       ch.nb = static_cast<int>(static_cast<long long>(B) * (i + 1) / nc) - ch.b0;
-      TMAP(h, &ch.tm_dxn, pl->dxn.as<bf16>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
-      TMAP(h, &ch.tm_dx, pl->dx.as<bf16>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
-      TMAP(h, &ch.tm_dctx, pl->dctx.as<bf16>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
-      TMAP(h, &ch.tm_dh, pl->dh.as<bf16>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
+      TMAP(h, &ch.tm_dxn, pl->dxn.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
+      TMAP(h, &ch.tm_dx, pl->dx.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
+      TMAP(h, &ch.tm_dctx, pl->dctx.as<act_t>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
+      TMAP(h, &ch.tm_dh, pl->dh.as<act_t>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
     }
   }
   TRY(build_mega(h, *pl));
@@ -1100,11 +1099,11 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     CU_OK(h, cudaStreamSynchronize(s));
     M = *p.h_cu;
     cu = p.cu.as<int>();
-    embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), cu, p.row_b.as<int>(),
+    embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<act_t>(), cu, p.row_b.as<int>(),
                                                                p.row_s.as<int>(), S, d, c.V);
     h->launches += 2;
   } else {
-    embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<bf16>(), p.x.as<bf16>(), M, d, c.V);
+    embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<act_t>(), M, d, c.V);
     h->launches++;
   }
   p.packed_rows = M;
@@ -1114,46 +1113,46 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
   const int wi_tiles = (F + 127) / 128;
   for (int l = 0; l < c.Le; ++l) {
     EncLayerW& w = h->enc[l];
-    CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln0.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), w.ln0.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
     {
-      EpiStore::Params ep{p.qkv.as<bf16>(), 3 * I};
+      EpiStore::Params ep{p.qkv.as<act_t>(), 3 * I};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiStore>(h, p.tm_xn, w.tm2_qkv, M, 3 * I, d, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
     }
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
       encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
-          p.tm_qkv_attn, p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H);
+          p.tm_qkv_attn, p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H);
     } else {
       encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
-          p.qkv.as<bf16>(), p.ctx.as<bf16>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
+          p.qkv.as<act_t>(), p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
     }
     h->launches++;
     CU_OK(h, cudaGetLastError());
     {
-      EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
+      EpiResidual::Params ep{p.x.as<act_t>(), p.x.as<act_t>(), d};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_ctx, w.tm2_o, M, d, I, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_ctx, w.tm_o, M, d, I, G_RES256, 0), &ep, s));
     }
-    CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), w.ln1.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), w.ln1.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
     {
-      EpiGeglu::Params ep{p.hff.as<bf16>(), F, h->gelu_lut};
+      EpiGeglu::Params ep{p.hff.as<act_t>(), F, h->gelu_lut};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiGeglu>(h, p.tm_xn, w.tm2_wi, M, wi_tiles * 256, d, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
     }
     {
-      EpiResidual::Params ep{p.x.as<bf16>(), p.x.as<bf16>(), d};
+      EpiResidual::Params ep{p.x.as<act_t>(), p.x.as<act_t>(), d};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_hff, w.tm2_ffo, M, d, F, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_hff, w.tm_ffo, M, d, F, G_RES256, 0), &ep, s));
     }
   }
-  CU_OK(h, run_rmsnorm(h, p.x.as<bf16>(), h->enc_final_ln.as<bf16>(), p.xn.as<bf16>(), M, d, c.eps, s));
+  CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), h->enc_final_ln.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
   return B200T5_OK;
 }
 
 static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
-  EpiCrossKV::Params ep{p.cross_kv.as<bf16>(), p.B, c.H, p.S};
+  EpiCrossKV::Params ep{p.cross_kv.as<act_t>(), p.B, c.H, p.S};
   if (p.packed) {
     ep.row_b = p.row_b.as<int>();
     ep.row_s = p.row_s.as<int>();
@@ -1170,7 +1169,7 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
 // step counter) and write disjoint row ranges of the same buffers.
 struct ChainView {
   int b0, nb;
-  bf16 *dx, *dxn, *dq, *dctx, *dh;
+  act_t *dx, *dxn, *dq, *dctx, *dh;
   const Plan::Chain* ch;
 };
 static ChainView chain_view(b200t5_ctx* h, const Plan::Chain& ch) {
@@ -1179,11 +1178,11 @@ static ChainView chain_view(b200t5_ctx* h, const Plan::Chain& ch) {
   ChainView v;
   v.b0 = ch.b0;
   v.nb = ch.nb;
-  v.dx = p.dx.as<bf16>() + static_cast<size_t>(ch.b0) * c.d;
-  v.dxn = p.dxn.as<bf16>() + static_cast<size_t>(ch.b0) * c.d;
-  v.dq = p.dq.as<bf16>() + static_cast<size_t>(ch.b0) * c.I;
-  v.dctx = p.dctx.as<bf16>() + static_cast<size_t>(ch.b0) * c.I;
-  v.dh = p.dh.as<bf16>() + static_cast<size_t>(ch.b0) * c.F;
+  v.dx = p.dx.as<act_t>() + static_cast<size_t>(ch.b0) * c.d;
+  v.dxn = p.dxn.as<act_t>() + static_cast<size_t>(ch.b0) * c.d;
+  v.dq = p.dq.as<act_t>() + static_cast<size_t>(ch.b0) * c.I;
+  v.dctx = p.dctx.as<act_t>() + static_cast<size_t>(ch.b0) * c.I;
+  v.dh = p.dh.as<act_t>() + static_cast<size_t>(ch.b0) * c.F;
   v.ch = &ch;
   return v;
 }
@@ -1199,19 +1198,19 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   const int* step = p.stream_mode ? p.pos.as<int>() + v.b0 : &p.state.as<DecodeState>()->step;
   DecLayerW& w = h->dec[l];
   // [kv][B][H][T][64]: a row offset of b0 is a pointer offset inside each kv plane
-  bf16* skv = p.self_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
+  act_t* skv = p.self_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
   // Fused RMSNorm: the residual GEMM that produced x left per-chunk sums of squares in `ss`; the consumer GEMM
   // normalises its A tile in shared memory (gemm_splitk.cuh, NormA). Layer 0's x comes from the embedding
   // gather (no producer GEMM), so its first norm stays a kernel.
   const bool fuse = h->fuse_norm && h->sk_on;
   const int ss_ld = (d + 31) / 32;
   float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
-  if (!(fuse && l > 0)) CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  if (!(fuse && l > 0)) CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T, sstride};
     if (fuse && l > 0)
       CU_OK(h, run_gemm_sk_norm<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dx, w.tm_qkv, v.nb, 3 * I, d, ep,
-                                              NormA{ss, ss_ld, w.ln0.as<bf16>(), c.eps}, s, pdl));
+                                              NormA{ss, ss_ld, w.ln0.as<act_t>(), c.eps}, s, pdl));
     else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
@@ -1236,12 +1235,12 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
     } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiStore::Params ep{v.dq, I};
     if (fuse)
       CU_OK(h, run_gemm_sk_norm<EpiStore>(h, h->sk_proj, v.ch->tm_dx, w.tm_cq, v.nb, I, d, ep,
-                                          NormA{ss, ss_ld, w.ln1.as<bf16>(), c.eps}, s, pdl));
+                                          NormA{ss, ss_ld, w.ln1.as<act_t>(), c.eps}, s, pdl));
     else if (h->sk_on && h->mcast && gemm_mcast_supports(I, d)) {
       h->launches++;
       CU_OK(h, launch_gemm_mcast<false>(v.ch->tm_dxn, w.tm16_cq, v.nb, I, d, EpiResidual::Params{}, ep, s, pdl));
@@ -1256,7 +1255,7 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
   const Cfg& c = h->c;
   Plan& p = *h->plan;
   const int B = p.B, S = p.S, I = c.I, H = c.H;
-  bf16* ckv = p.cross_kv.as<bf16>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
+  act_t* ckv = p.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
   struct PrioGuard {
     int saved;
     PrioGuard() : saved(launch_priority()) { launch_priority() = 0; }
@@ -1284,7 +1283,7 @@ static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, 
     const int nitems = v.nb * H;
     const int k_row0 = (l * 2) * B * H * S, v_row0 = (l * 2 + 1) * B * H * S;
     CU_OK(h, launch_kernel(attn_decode_tc_kernel, dim3(nitems < h->num_sms ? nitems : h->num_sms), dim3(kXtcThreads), kXtcSmemBytes, s,
-                           pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, p.dq.as<bf16>(), p.dctx.as<bf16>(), v.b0 * H, nitems, H,
+                           pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, p.dq.as<act_t>(), p.dctx.as<act_t>(), v.b0 * H, nitems, H,
                            S, p.live_extent.as<int>(), p.live_key_ok.as<unsigned char>(), static_cast<long long*>(nullptr)));
   } else {
     CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
@@ -1318,12 +1317,12 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
     } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiGeglu::Params ep{v.dh, F, h->gelu_lut};
     if (fuse)
       CU_OK(h, run_gemm_sk_norm<EpiGeglu>(h, h->sk_wi, v.ch->tm_dx, w.tm_wi, v.nb, w.wi_rows, d, ep,
-                                          NormA{ss, ss_ld, w.ln2.as<bf16>(), c.eps}, s, pdl));
+                                          NormA{ss, ss_ld, w.ln2.as<act_t>(), c.eps}, s, pdl));
     else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
   }
@@ -1347,7 +1346,7 @@ static int chain_head(b200t5_ctx* h, cudaStream_t s, const ChainView& v, float* 
   const int d = c.d, T = p.Tmax;
   const bool pdl = h->use_pdl;
   DecodeState* st = p.state.as<DecodeState>();
-  CU_OK(h, run_rmsnorm(h, v.dx, h->dec_final_ln.as<bf16>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  CU_OK(h, run_rmsnorm(h, v.dx, h->dec_final_ln.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   if (logits_out) {
     EpiStoreF32::Params ep{logits_out + static_cast<size_t>(v.b0) * ldl, ldl};
     CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, h->tm_lm, v.nb, c.V, d, G_LOGITS128, 1), &ep, s, pdl));
@@ -1361,7 +1360,7 @@ static int chain_head(b200t5_ctx* h, cudaStream_t s, const ChainView& v, float* 
     long long* oid = sm ? p.stream_out.as<long long>() : p.out_ids.as<long long>() + static_cast<size_t>(v.b0) * (T + 1);
     int* olen = sm ? p.stream_len.as<int>() : p.out_len.as<int>() + v.b0;
     CU_OK(h, launch_kernel(finalize_step_kernel, dim3(v.nb), dim3(128), 0, s, pdl, pval, pidx, p.n_vtiles, st,
-                           p.unfinished.as<int>() + v.b0, oid, olen, T + 1, eos, pad, h->shared.as<bf16>(), v.dx, d,
+                           p.unfinished.as<int>() + v.b0, oid, olen, T + 1, eos, pad, h->shared.as<act_t>(), v.dx, d,
                            p.live_extent.as<int>() + v.b0, sm ? p.pos.as<int>() + v.b0 : static_cast<int*>(nullptr),
                            sm ? p.out_row.as<int>() + v.b0 : static_cast<const int*>(nullptr), T));
     h->launches++;
@@ -1521,7 +1520,7 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
   CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   decode_init_kernel<<<B, 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.out_ids.as<long long>(),
-                                       p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+                                       p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
   h->launches++;
   CU_OK(h, cudaGetLastError());
   CU_OK(h, cudaEventRecord(h->ev[1], s));
@@ -1657,7 +1656,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     stream_init_kernel<<<static_cast<unsigned>(rows), 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.pos.as<int>(),
                                                                   p.live_extent.as<int>(), p.stream_out.as<long long>(),
                                                                   p.stream_len.as<int>(), T + 1, static_cast<int>(N), B, start, pad,
-                                                                  h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+                                                                  h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
     h->launches++;
     CU_OK(h, cudaGetLastError());
   }
@@ -1700,7 +1699,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
       admit_slots_kernel<<<k, 128, 0, s>>>(p.admit.as<int>() + B, p.admit.as<int>() + 2 * B, p.unfinished.as<int>(), p.pos.as<int>(),
                                            p.out_row.as<int>(), p.extent.as<int>(), p.live_extent.as<int>(),
                                            p.key_ok.as<unsigned char>(), p.live_key_ok.as<unsigned char>(), S, start,
-                                           h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+                                           h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
       h->launches++;
       CU_OK(h, cudaGetLastError());
       fill_stats_model(h, 0);
@@ -1772,16 +1771,16 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_
   }
   auto sweep = [&]() {
     for (int l = 0; l < c.Ld; ++l) {
-      bf16* ckv = p.cross_kv.as<bf16>() + l * cross_layer;
+      act_t* ckv = p.cross_kv.as<act_t>() + l * cross_layer;
       if (h->xattn_tc && p.S <= kXtcMaxS) {
         const int nitems = p.B * c.H;
         attn_decode_tc_kernel<<<nitems < h->num_sms ? nitems : h->num_sms, kXtcThreads, kXtcSmemBytes, s>>>(
-            p.tm_cross_kv, p.tm_cross_kv, (l * 2) * nitems * p.S, (l * 2 + 1) * nitems * p.S, p.dq.as<bf16>(), p.dctx.as<bf16>(), 0,
+            p.tm_cross_kv, p.tm_cross_kv, (l * 2) * nitems * p.S, (l * 2 + 1) * nitems * p.S, p.dq.as<act_t>(), p.dctx.as<act_t>(), 0,
             nitems, c.H, p.S, p.extent.as<int>(), p.key_ok.as<unsigned char>(), xtc_prof);
         continue;
       }
       attn_decode_kernel<false><<<p.B * c.H, kAttnDecThreads, p.S * sizeof(float), s>>>(
-          p.dq.as<bf16>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<bf16>(), c.H, p.S,
+          p.dq.as<act_t>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<act_t>(), c.H, p.S,
           p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr, L2Prefetch{});
     }
   };
@@ -1827,7 +1826,7 @@ extern "C" int b200t5_encode(b200t5_handle h, const int64_t* input_ids, const in
   TRY(ensure_plan(h, B, S, T));
   TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
   if (h->plan->packed) {
-    unpack_rows_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(h->plan->xn.as<bf16>(), h->plan->cu.as<int>(), static_cast<bf16*>(enc_out_bf16), S, h->c.d);
+    unpack_rows_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(h->plan->xn.as<act_t>(), h->plan->cu.as<int>(), static_cast<act_t*>(enc_out_bf16), S, h->c.d);
     CU_OK(h, cudaGetLastError());
   } else {
     CU_OK(h, cudaMemcpyAsync(enc_out_bf16, h->plan->xn.p, static_cast<size_t>(B) * S * h->c.d * 2, cudaMemcpyDeviceToDevice, s));
@@ -1854,7 +1853,7 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
   CU_OK(h, col.alloc(static_cast<size_t>(B) * 8));
   for (int t = 0; t < T; ++t) {
     CU_OK(h, cudaMemcpy2DAsync(col.p, 8, reinterpret_cast<const long long*>(decoder_input_ids) + t, static_cast<size_t>(T) * 8, 8, B, cudaMemcpyDeviceToDevice, s));
-    force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<bf16>(), p.dx.as<bf16>(), c.d);
+    force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
     TRY(run_decode_step(h, s, false, logits + static_cast<size_t>(t) * c.V, T * c.V, c.eos, c.pad, 0));
   }
   CU_OK(h, cudaStreamSynchronize(s));
@@ -1881,7 +1880,7 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
   b200t5_ctx dummy;
   dummy.num_sms = sms;
   cudaError_t e = cudaErrorInvalidValue;
-  bf16* Cb = static_cast<bf16*>(C);
+  act_t* Cb = static_cast<act_t*>(C);
   if (bn == 512) {  // CTA-pair kernel, 256 x 256 tiles (gemm_2cta.cuh)
     if (mode == 0) {
       EpiStore::Params ep{Cb, N};
@@ -1935,7 +1934,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
       return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk(bn=16): needs K <= 768, N %% 64 == 0, mode 0 or 1");
     CUtensorMap ta, tb;
     if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, 16)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
-    bf16* Cb = static_cast<bf16*>(C);
+    act_t* Cb = static_cast<act_t*>(C);
     cudaError_t e = mode == 0 ? launch_gemm_mcast<false>(ta, tb, M, N, K, EpiResidual::Params{}, EpiStore::Params{Cb, N}, s, false)
                               : launch_gemm_mcast<true>(ta, tb, M, N, K, EpiResidual::Params{Cb, Cb, N}, EpiStore::Params{}, s, false);
     if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm_splitk(bn=16, mode=%d): %s", mode, cudaGetErrorString(e));
@@ -1949,7 +1948,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
   dummy.num_sms = sms;
   b200t5_ctx::SkChoice ch{bn, split};
   cudaError_t e = cudaErrorInvalidValue;
-  bf16* Cb = static_cast<bf16*>(C);
+  act_t* Cb = static_cast<act_t*>(C);
   DevBuf st;
   if (mode == 0) {
     EpiStore::Params ep{Cb, N};
@@ -1966,7 +1965,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
     if (!aux) return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: mode 5 needs aux");
     const int ss_ld = (K + 31) / 32;
     const float* ssp = static_cast<const float*>(aux);
-    const bf16* wln = reinterpret_cast<const bf16*>(ssp + static_cast<size_t>(M) * ss_ld);
+    const act_t* wln = reinterpret_cast<const act_t*>(ssp + static_cast<size_t>(M) * ss_ld);
     EpiStore::Params ep{Cb, N};
     e = run_gemm_sk_norm<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, NormA{ssp, ss_ld, wln, 1e-6f}, s, false);
   } else if (mode == 2) {
@@ -1979,7 +1978,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
     if (!aux || N % 192 || Tmax <= step) return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bad QKV arguments");
     if (st.alloc(sizeof(DecodeState)) != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "alloc");
     set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
-    EpiQkvDecode::Params ep{Cb, static_cast<bf16*>(aux), &st.as<DecodeState>()->step, M, N / 192, Tmax};
+    EpiQkvDecode::Params ep{Cb, static_cast<act_t*>(aux), &st.as<DecodeState>()->step, M, N / 192, Tmax};
     e = run_gemm_sk<EpiQkvDecode>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   }
@@ -1990,7 +1989,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
 extern "C" int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream) {
   const int sms = hook_device(device);
   if (sms < 0) return sms;
-  cudaError_t e = run_rmsnorm(nullptr, static_cast<const bf16*>(x), static_cast<const bf16*>(w), static_cast<bf16*>(y), M, d, eps, static_cast<cudaStream_t>(stream));
+  cudaError_t e = run_rmsnorm(nullptr, static_cast<const act_t*>(x), static_cast<const act_t*>(w), static_cast<act_t*>(y), M, d, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "rmsnorm: %s", cudaGetErrorString(e));
   return B200T5_OK;
 }
@@ -2007,7 +2006,7 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
     set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
     self_attn_decode_warp_kernel<<<(B * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta, kSelfWarpsPerCta * 32,
                                    kSelfWarpsPerCta * Tk * sizeof(float), s>>>(
-        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx),
+        static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx),
         B * H, H, Tk, &st.as<DecodeState>()->step, dist_bias);
     cudaStreamSynchronize(s);
   } else if (self == 2) {  // cross-attention on the tensor cores (attention_decode_tc.cuh)
@@ -2017,10 +2016,10 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
       return fail(nullptr, B200T5_ECUDA, "%s", g_err);
     const int nitems = B * H;
     attn_decode_tc_kernel<<<nitems < sms ? nitems : sms, kXtcThreads, kXtcSmemBytes, s>>>(
-        tk, tv, 0, 0, static_cast<const bf16*>(q), static_cast<bf16*>(ctx), 0, nitems, H, Tk, extent, key_ok);
+        tk, tv, 0, 0, static_cast<const act_t*>(q), static_cast<act_t*>(ctx), 0, nitems, H, Tk, extent, key_ok);
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
-        static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V), static_cast<bf16*>(ctx), H,
+        static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), H,
         Tk, extent, key_ok, nullptr, nullptr, L2Prefetch{});
   }
   cudaError_t e = cudaGetLastError();
@@ -2038,7 +2037,7 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
     CUtensorMap tm;
     if (!make_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, static_cast<uint64_t>(3) * H * 64, 128)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
     encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), static_cast<cudaStream_t>(stream)>>>(
-        tm, static_cast<bf16*>(ctx), rel_bias, key_ok, extent, nullptr, S, H);
+        tm, static_cast<act_t*>(ctx), rel_bias, key_ok, extent, nullptr, S, H);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn_tc: %s", cudaGetErrorString(e2));
     return B200T5_OK;
@@ -2047,7 +2046,7 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
   cudaError_t e = smem <= 96 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
   if (e == cudaSuccess) {
     encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx), rel_bias, key_ok, extent, S, H);
+        static_cast<const act_t*>(qkv), static_cast<act_t*>(ctx), rel_bias, key_ok, extent, S, H);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn: %s", cudaGetErrorString(e));
@@ -2061,7 +2060,7 @@ extern "C" int b200t5_test_geglu(int device, const void* gate, const void* up, v
   int lrc = ensure_gelu_lut(nullptr, 0, &lut);
   if (lrc != B200T5_OK) return lrc;
   geglu_elementwise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(gate), static_cast<const bf16*>(up), static_cast<bf16*>(out), n, pow_mode, lut);
+      static_cast<const act_t*>(gate), static_cast<const act_t*>(up), static_cast<act_t*>(out), n, pow_mode, lut);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "geglu: %s", cudaGetErrorString(e));
   return B200T5_OK;

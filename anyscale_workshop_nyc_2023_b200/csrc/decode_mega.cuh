@@ -51,20 +51,20 @@ constexpr int kMegaSmemBytes = kMegaStages * kMegaStageBytes + kMegaXaRingBytes 
 
 struct MegaLayer {
   const CUtensorMap *tm_qkv, *tm_o, *tm_cq, *tm_co, *tm_wi, *tm_ffo;  // device-resident tensor maps
-  const __nv_bfloat16 *ln0, *ln1, *ln2;
-  __nv_bfloat16* self_kv;         // [2][B][H][T][64]
-  const __nv_bfloat16* cross_kv;  // [2][B][H][S][64]
+  const act_t *ln0, *ln1, *ln2;
+  act_t* self_kv;         // [2][B][H][T][64]
+  const act_t* cross_kv;  // [2][B][H][S][64]
   int wi_rows;                    // padded N of the interleaved wi weight
 };
 
 struct MegaParams {
   int B, S, T, d, I, F, H, V, Ld;
   float eps;
-  __nv_bfloat16 *dx, *dxn, *dq, *dctx, *dh;
+  act_t *dx, *dxn, *dq, *dctx, *dh;
   float* ws;  // [ks][B][d] fp32 split-K partials
   const CUtensorMap *tm_dxn, *tm_dctx, *tm_dh, *tm_lm;
   const MegaLayer* layers;
-  const __nv_bfloat16 *final_ln, *E;
+  const act_t *final_ln, *E;
   const int* extent;
   const unsigned char* key_ok;
   const float* dec_bias;
@@ -221,7 +221,7 @@ DEVINL void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_ba
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBM, g.bn, 0, 0);
+      const uint32_t idesc = make_idesc_act(kBM, g.bn, 0, 0);
       for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         const int ks = job % g.ksplit;
         const int kb0 = ks * kb_per;
@@ -237,7 +237,7 @@ DEVINL void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_ba
           const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + kBM * kBK * 2);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+            umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                          (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&sh.empty[ps.stage]);
           if (++ps.stage == kMegaStages) {
@@ -284,7 +284,7 @@ DEVINL void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_ba
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
-            float v = bf16_round(__uint_as_float(acc[j]));
+            float v = act_round(__uint_as_float(acc[j]));
             if (n >= g.N || (block_eos && n == g.amax.eos)) v = -INFINITY;
             if (v > best) {
               best = v;
@@ -334,7 +334,7 @@ DEVINL void mega_gemm_phase(const MegaShared& sh, MegaPipe& ps, uint32_t tmem_ba
 // that every lane owns ONE 16-byte vector and all of its loads (x, the ksplit partials, w) are
 // issued back to back - one L2 round trip instead of ksplit * d/256 dependent ones.
 
-__device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* ws, int ksplit, const __nv_bfloat16* w, __nv_bfloat16* xn,
+__device__ __noinline__ void mega_resnorm_phase(act_t* x, const float* ws, int ksplit, const act_t* w, act_t* xn,
                                int rows, int d, float eps, float* scratch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;  // the control warp (12) falls outside every row group
   const int nvec = d >> 3;
@@ -379,12 +379,12 @@ __device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* w
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            xs[j] = pack_bf16x2(bf16_lo(xs[j]) + bf16_round(y[2 * j]), bf16_hi(xs[j]) + bf16_round(y[2 * j + 1]));
+            xs[j] = pack_act2(act_lo(xs[j]) + act_round(y[2 * j]), act_hi(xs[j]) + act_round(y[2 * j + 1]));
           *xr = make_uint4(xs[0], xs[1], xs[2], xs[3]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = bf16_lo(xs[j]), b = bf16_hi(xs[j]);
+          const float a = act_lo(xs[j]), b = act_hi(xs[j]);
           ss = fmaf(a, a, ss);
           ss = fmaf(b, b, ss);
         }
@@ -406,9 +406,9 @@ __device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* w
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float a = bf16_round(bf16_lo(xs[j]) * inv);
-          const float b = bf16_round(bf16_hi(xs[j]) * inv);
-          o[j] = pack_bf16x2(bf16_lo(wsv[j]) * a, bf16_hi(wsv[j]) * b);
+          const float a = act_round(act_lo(xs[j]) * inv);
+          const float b = act_round(act_hi(xs[j]) * inv);
+          o[j] = pack_act2(act_lo(wsv[j]) * a, act_hi(wsv[j]) * b);
         }
         reinterpret_cast<uint4*>(xn + static_cast<size_t>(row) * d)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -420,8 +420,8 @@ __device__ __noinline__ void mega_resnorm_phase(__nv_bfloat16* x, const float* w
 // ---------------------------------------------------------------- self-attention phase
 // One warp per (row, head): the shared per-item routine of attention_decode.cuh with plain (coherent) loads -
 // the cache rows of this step were written by other CTAs of the same launch.
-__device__ __noinline__ void mega_self_attn_phase(const __nv_bfloat16* q, const __nv_bfloat16* Kc, const __nv_bfloat16* Vc,
-                                                  __nv_bfloat16* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
+__device__ __noinline__ void mega_self_attn_phase(const act_t* q, const act_t* Kc, const act_t* Vc,
+                                                  act_t* ctx, int BH, int H, int Tk, int t, const float* dist_bias,
                                                   float* scratch) {
   const int warp = threadIdx.x >> 5;
   if (warp >= kMegaWarps) return;  // control warp
@@ -449,8 +449,8 @@ DEVINL void bulk_load_1d_evict_first(void* smem_dst, const void* gsrc, uint32_t 
       : "memory");
 }
 
-__device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPipe& ps, const __nv_bfloat16* q,
-                                                   const __nv_bfloat16* Kc, const __nv_bfloat16* Vc, __nv_bfloat16* ctx,
+__device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPipe& ps, const act_t* q,
+                                                   const act_t* Kc, const act_t* Vc, act_t* ctx,
                                                    int BH, int H, int Tk, const int* extent, const unsigned char* key_ok) {
   const int stride = gridDim.x * kMegaGroups;
   if (threadIdx.x >= kMegaWarps * 32) {
@@ -481,7 +481,7 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
         uint64_t* full = &sh.xa_full[g * kXaSlots + slot];
         mbar_wait(&sh.xa_empty[g * kXaSlots + slot], ((seq / kXaSlots) & 1u) ^ 1u);
         mbar_arrive_expect_tx(full, static_cast<uint32_t>(rows) * 128u);
-        const __nv_bfloat16* src = (isv ? Vc : Kc) + (static_cast<size_t>(bh[g]) * Tk + static_cast<size_t>(c) * kXaChunkKeys) * 64;
+        const act_t* src = (isv ? Vc : Kc) + (static_cast<size_t>(bh[g]) * Tk + static_cast<size_t>(c) * kXaChunkKeys) * 64;
         bulk_load_1d_evict_first(sh.xa_ring + (g * kXaSlots + slot) * kXaChunkBytes, src, static_cast<uint32_t>(rows) * 128u, full, policy);
         if (++e[g] == 2 * nck[g]) {
           bh[g] += stride;
@@ -511,8 +511,8 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
     float qf[8];
     {
       const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(bh) * 64 + dg * 8);
-      qf[0] = bf16_lo(qv.x); qf[1] = bf16_hi(qv.x); qf[2] = bf16_lo(qv.y); qf[3] = bf16_hi(qv.y);
-      qf[4] = bf16_lo(qv.z); qf[5] = bf16_hi(qv.z); qf[6] = bf16_lo(qv.w); qf[7] = bf16_hi(qv.w);
+      qf[0] = act_lo(qv.x); qf[1] = act_hi(qv.x); qf[2] = act_lo(qv.y); qf[3] = act_hi(qv.y);
+      qf[4] = act_lo(qv.z); qf[5] = act_hi(qv.z); qf[6] = act_lo(qv.w); qf[7] = act_hi(qv.w);
     }
     // ---- scores: chunk c holds keys [64c, 64c+64); this thread reads keys 64c + 16r + 4*warp + ks, r = 0..3
     for (int c = 0; c < nck; ++c) {
@@ -538,8 +538,8 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
         sc += __shfl_xor_sync(0xffffffffu, sc, 2);
         sc += __shfl_xor_sync(0xffffffffu, sc, 4);
         if (dg == 0 && j < nkeys) {
-          sc = bf16_round(sc);
-          if (!key_ok[static_cast<size_t>(b) * Tk + j]) sc = kBf16Min;
+          sc = act_round(sc);
+          if (!key_ok[static_cast<size_t>(b) * Tk + j]) sc = kActMin;
           s_scores[j] = sc;
         }
       }
@@ -563,7 +563,7 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
     if (lane == 0) s_stat[4 + warp] = sum;
     group_sync(group);
     sum = (s_stat[4] + s_stat[5]) + (s_stat[6] + s_stat[7]);
-    for (int j = gt; j < nkeys; j += 128) s_scores[j] = bf16_round(s_scores[j] / sum);
+    for (int j = gt; j < nkeys; j += 128) s_scores[j] = act_round(s_scores[j] / sum);
     group_sync(group);
     // ---- out = P . V
     float acc[8];
@@ -590,14 +590,14 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
       if (lane == 0) mbar_arrive(&empty0[slot]);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        acc[0] = fmaf(pj[r], bf16_lo(vv[r].x), acc[0]);
-        acc[1] = fmaf(pj[r], bf16_hi(vv[r].x), acc[1]);
-        acc[2] = fmaf(pj[r], bf16_lo(vv[r].y), acc[2]);
-        acc[3] = fmaf(pj[r], bf16_hi(vv[r].y), acc[3]);
-        acc[4] = fmaf(pj[r], bf16_lo(vv[r].z), acc[4]);
-        acc[5] = fmaf(pj[r], bf16_hi(vv[r].z), acc[5]);
-        acc[6] = fmaf(pj[r], bf16_lo(vv[r].w), acc[6]);
-        acc[7] = fmaf(pj[r], bf16_hi(vv[r].w), acc[7]);
+        acc[0] = fmaf(pj[r], act_lo(vv[r].x), acc[0]);
+        acc[1] = fmaf(pj[r], act_hi(vv[r].x), acc[1]);
+        acc[2] = fmaf(pj[r], act_lo(vv[r].y), acc[2]);
+        acc[3] = fmaf(pj[r], act_hi(vv[r].y), acc[3]);
+        acc[4] = fmaf(pj[r], act_lo(vv[r].z), acc[4]);
+        acc[5] = fmaf(pj[r], act_hi(vv[r].z), acc[5]);
+        acc[6] = fmaf(pj[r], act_lo(vv[r].w), acc[6]);
+        acc[7] = fmaf(pj[r], act_hi(vv[r].w), acc[7]);
       }
     }
 #pragma unroll
@@ -614,7 +614,7 @@ __device__ __noinline__ void mega_cross_attn_phase(const MegaShared& sh, MegaPip
       const int d0 = gt * 2;
       const float o0 = (s_red[d0] + s_red[64 + d0]) + (s_red[128 + d0] + s_red[192 + d0]);
       const float o1 = (s_red[d0 + 1] + s_red[64 + d0 + 1]) + (s_red[128 + d0 + 1] + s_red[192 + d0 + 1]);
-      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(bh) * 64 + d0) = pack_bf16x2(o0, o1);
+      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(bh) * 64 + d0) = pack_act2(o0, o1);
     }
     group_sync(group);  // s_scores / s_red are reused by the next item
   }

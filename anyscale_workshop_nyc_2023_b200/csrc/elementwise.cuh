@@ -7,8 +7,8 @@ namespace b200 {
 
 // ---------------------------------------------------------------- embedding gather
 // x[m, :] = E[ids[m], :]   (modeling_t5.py:682).  One warp per row, 16-B vectors.
-__global__ void embed_rows_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ E,
-                                  __nv_bfloat16* __restrict__ x, int M, int d, int vocab) {
+__global__ void embed_rows_kernel(const long long* __restrict__ ids, const act_t* __restrict__ E,
+                                  act_t* __restrict__ x, int M, int d, int vocab) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   long long id = ids[row];
@@ -61,8 +61,8 @@ __global__ void pack_offsets_kernel(const int* __restrict__ extent, int* __restr
 }
 
 // row tables for the packed layout + embedding gather: x[cu[b] + s, :] = E[ids[b, s], :]
-__global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ E,
-                                         __nv_bfloat16* __restrict__ x, const int* __restrict__ cu,
+__global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, const act_t* __restrict__ E,
+                                         act_t* __restrict__ x, const int* __restrict__ cu,
                                          int* __restrict__ row_b, int* __restrict__ row_s, int S, int d, int vocab) {
   const int b = blockIdx.y;
   const int n = cu[b + 1] - cu[b];
@@ -81,8 +81,8 @@ __global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, cons
 }
 
 // test hook: packed rows back to the padded [B*S, d] layout (rows beyond extent[b] are zero)
-__global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ xp, const int* __restrict__ cu,
-                                   __nv_bfloat16* __restrict__ out, int S, int d) {
+__global__ void unpack_rows_kernel(const act_t* __restrict__ xp, const int* __restrict__ cu,
+                                   act_t* __restrict__ out, int S, int d) {
   const int b = blockIdx.y;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
@@ -99,8 +99,8 @@ __global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ xp, const i
 //   y   = bf16( float(w) * float(y1) )          second rounding
 // One warp per row; the row stays in registers between the two passes.
 template <int kMaxVec>  // uint4 vectors per lane: d <= kMaxVec * 256
-__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                               __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
+__global__ void rmsnorm_kernel(const act_t* __restrict__ x, const act_t* __restrict__ w,
+                               act_t* __restrict__ y, int M, int d, float eps) {
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = lane_id();
@@ -126,7 +126,7 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
       const uint32_t wds[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = bf16_lo(wds[j]), b = bf16_hi(wds[j]);
+        const float a = act_lo(wds[j]), b = act_hi(wds[j]);
         ss = fmaf(a, a, ss);
         ss = fmaf(b, b, ss);
       }
@@ -145,9 +145,9 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = bf16_round(bf16_lo(xs[j]) * inv);
-        const float b = bf16_round(bf16_hi(xs[j]) * inv);
-        o[j] = pack_bf16x2(bf16_lo(ws[j]) * a, bf16_hi(ws[j]) * b);
+        const float a = act_round(act_lo(xs[j]) * inv);
+        const float b = act_round(act_hi(xs[j]) * inv);
+        o[j] = pack_act2(act_lo(ws[j]) * a, act_hi(ws[j]) * b);
       }
       yr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -194,8 +194,8 @@ struct DecodeState {
 // Start of generate(): x_dec[b] = E[decoder_start], out[b][0] = decoder_start, flags reset.
 __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished, long long* __restrict__ out_ids,
                                    int* __restrict__ out_len, int out_ld, int B, long long start_tok,
-                                   long long pad_tok, const __nv_bfloat16* __restrict__ E,
-                                   __nv_bfloat16* __restrict__ x, int d) {
+                                   long long pad_tok, const act_t* __restrict__ E,
+                                   act_t* __restrict__ x, int d) {
   const int b = blockIdx.x;
   if (b == 0 && threadIdx.x == 0) {
     st->step = 0;
@@ -219,7 +219,7 @@ __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished
 __global__ void stream_init_kernel(DecodeState* st, int* __restrict__ unfinished, int* __restrict__ pos,
                                    int* __restrict__ live_extent, long long* __restrict__ out_ids,
                                    int* __restrict__ out_len, int out_ld, int N, int B, long long start_tok,
-                                   long long pad_tok, const __nv_bfloat16* __restrict__ E, __nv_bfloat16* __restrict__ x,
+                                   long long pad_tok, const act_t* __restrict__ E, act_t* __restrict__ x,
                                    int d) {
   const int r = blockIdx.x;
   if (r == 0 && threadIdx.x == 0) {
@@ -248,7 +248,7 @@ __global__ void admit_slots_kernel(const int* __restrict__ slots, const int* __r
                                    int* __restrict__ pos, int* __restrict__ out_row, const int* __restrict__ extent,
                                    int* __restrict__ live_extent, const unsigned char* __restrict__ key_ok,
                                    unsigned char* __restrict__ live_key_ok, int S, long long start_tok,
-                                   const __nv_bfloat16* __restrict__ E, __nv_bfloat16* __restrict__ x, int d) {
+                                   const act_t* __restrict__ E, act_t* __restrict__ x, int d) {
   const int b = slots[blockIdx.x];
   if (threadIdx.x == 0) {
     unfinished[b] = 1;
@@ -275,8 +275,8 @@ __global__ void admit_slots_kernel(const int* __restrict__ slots, const int* __r
 __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int n_tiles,
                                      DecodeState* st, int* __restrict__ unfinished,
                                      long long* __restrict__ out_ids, int* __restrict__ out_len, int out_ld,
-                                     long long eos_tok, long long pad_tok, const __nv_bfloat16* __restrict__ E,
-                                     __nv_bfloat16* __restrict__ x, int d, int* __restrict__ live_extent,
+                                     long long eos_tok, long long pad_tok, const act_t* __restrict__ E,
+                                     act_t* __restrict__ x, int d, int* __restrict__ live_extent,
                                      int* __restrict__ pos, const int* __restrict__ out_row, int max_new) {
   pdl_launch_dependents();
   pdl_wait();
@@ -347,8 +347,8 @@ __global__ void advance_step_kernel(DecodeState* st) {
 }
 
 // teacher forcing (test hook): overwrite the next decoder input with a given token
-__global__ void force_token_kernel(const long long* __restrict__ toks, const __nv_bfloat16* __restrict__ E,
-                                   __nv_bfloat16* __restrict__ x, int d) {
+__global__ void force_token_kernel(const long long* __restrict__ toks, const act_t* __restrict__ E,
+                                   act_t* __restrict__ x, int d) {
   const int b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(toks[b]) * d);
   uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);

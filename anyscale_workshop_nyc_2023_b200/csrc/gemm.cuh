@@ -143,7 +143,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_act(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -161,7 +161,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+            umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                          (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
@@ -215,11 +215,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 DEVINL void round_pack_32(const uint32_t (&acc)[32], uint32_t (&out)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+  for (int i = 0; i < 16; ++i) out[i] = pack_act2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
 }
 
 // Store 32 bf16 (64 B) to dst; columns [n0, n0+32) clipped to N in groups of 8.
-DEVINL void store_row_chunk(__nv_bfloat16* dst, const uint32_t (&p)[16], int n0, int N) {
+DEVINL void store_row_chunk(act_t* dst, const uint32_t (&p)[16], int n0, int N) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -258,7 +258,7 @@ DEVINL void run_chunks_from_tmem(const typename Epi::Params& p, uint32_t taddr, 
 // ---- plain store: C = bf16(acc)
 struct EpiStore {
   struct Params {
-    __nv_bfloat16* C;
+    act_t* C;
     int ldc;
   };
   static constexpr bool kPaired = false;
@@ -281,8 +281,8 @@ struct EpiStore {
 // ---- residual: C = bf16( float(R) + float(bf16(acc)) )   (modeling_t5.py:375,406,149)
 struct EpiResidual {
   struct Params {
-    __nv_bfloat16* C;
-    const __nv_bfloat16* R;
+    act_t* C;
+    const act_t* R;
     int ld;
     // optional: sum of squares of the 32 outputs of each (row, chunk) -> ss[m * ss_ld + n0 / 32], for a
     // consumer GEMM that applies the following RMSNorm to its A operand (gemm_splitk.cuh, NormA)
@@ -309,9 +309,9 @@ struct EpiResidual {
       const uint32_t rw[4] = {pre.r[g].x, pre.r[g].y, pre.r[g].z, pre.r[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float y0 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j]));
-        const float y1 = bf16_round(__uint_as_float(acc[g * 8 + 2 * j + 1]));
-        o[g * 4 + j] = pack_bf16x2(bf16_lo(rw[j]) + y0, bf16_hi(rw[j]) + y1);
+        const float y0 = act_round(__uint_as_float(acc[g * 8 + 2 * j]));
+        const float y1 = act_round(__uint_as_float(acc[g * 8 + 2 * j + 1]));
+        o[g * 4 + j] = pack_act2(act_lo(rw[j]) + y0, act_hi(rw[j]) + y1);
       }
     }
     store_row_chunk(p.C + static_cast<size_t>(m) * p.ld + n0, o, n0, N);
@@ -320,7 +320,7 @@ struct EpiResidual {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (n0 + 2 * i + 2 <= N) {
-          const float a = bf16_lo(o[i]), b = bf16_hi(o[i]);
+          const float a = act_lo(o[i]), b = act_hi(o[i]);
           sq = fmaf(a, a, sq);
           sq = fmaf(b, b, sq);
         }
@@ -339,15 +339,15 @@ struct EpiResidual {
 // result to bf16 (transformers/activations.py:59-66). torch.pow(x, 3.0) on
 // a bf16 tensor is x*x*x in bf16 arithmetic (two roundings, pow_mode 0; verified exhaustively
 // against torch on the GPU); pow_mode 1 keeps the single-rounding variant selectable.
-DEVINL float gelu_new_bf16_exact(float x, int pow_mode) {
-  const float half_x = bf16_round(0.5f * x);
-  const float x3 = pow_mode == 0 ? bf16_round(bf16_round(x * x) * x) : bf16_round(x * x * x);
-  const float t1 = bf16_round(0.044715f * x3);
-  const float t2 = bf16_round(x + t1);
-  const float t3 = bf16_round(0.7978845608028654f * t2);
-  const float t4 = bf16_round(tanhf(t3));
-  const float t5 = bf16_round(1.0f + t4);
-  return bf16_round(half_x * t5);
+DEVINL float gelu_new_act_exact(float x, int pow_mode) {
+  const float half_x = act_round(0.5f * x);
+  const float x3 = pow_mode == 0 ? act_round(act_round(x * x) * x) : act_round(x * x * x);
+  const float t1 = act_round(0.044715f * x3);
+  const float t2 = act_round(x + t1);
+  const float t3 = act_round(0.7978845608028654f * t2);
+  const float t4 = act_round(tanhf(t3));
+  const float t5 = act_round(1.0f + t4);
+  return act_round(half_x * t5);
 }
 
 // The input of gelu_new is itself a bf16 value, so the function has only 65536 possible
@@ -369,7 +369,7 @@ DEVINL float gelu_from_lut_sel(float x, const uint16_t* lut, int lo, int n /* = 
   const int rel = mag - lo;
   const int idx = min(max(rel, 0), n - 1) + (neg ? n : 0);
   const float tab = __uint_as_float(static_cast<uint32_t>(lut[idx]) << 16);
-  const float half = bf16_round(0.5f * x);
+  const float half = act_round(0.5f * x);
   float sat = neg ? (mag == 0x7F80 ? __int_as_float(0x7FC00000) : -0.0f) : x;
   sat = mag > 0x7F80 ? x : sat;
   return rel < 0 ? half : (rel >= n ? sat : tab);
@@ -379,7 +379,7 @@ DEVINL float gelu_from_lut(float x, const uint16_t* lut, int lo, int hi) {
   const uint32_t bits = __float_as_uint(x) >> 16;
   const int mag = static_cast<int>(bits & 0x7FFFu);
   const int neg = static_cast<int>(bits >> 15);
-  if (mag < lo) return bf16_round(0.5f * x);  // tanh term rounds away: gelu_new(x) == bf16(0.5*x)
+  if (mag < lo) return act_round(0.5f * x);  // tanh term rounds away: gelu_new(x) == bf16(0.5*x)
   if (mag >= hi) {
     if (mag > 0x7F80) return x;                     // NaN propagates
     if (!neg) return x;                             // tanh saturated: 0.5x * 2
@@ -393,7 +393,7 @@ DEVINL float gelu_from_lut(float x, const uint16_t* lut, int lo, int hi) {
 //   out = bf16( gelu_new(bf16(gate)) * bf16(up) )          (modeling_t5.py:115-118)
 struct EpiGeglu {
   struct Params {
-    __nv_bfloat16* out;  // [M, F]
+    act_t* out;  // [M, F]
     int F;
     GeluLut lut;
   };
@@ -419,11 +419,11 @@ struct EpiGeglu {
       float r[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float x = bf16_round(__uint_as_float(g[2 * i + e]));
-        const float lin = bf16_round(__uint_as_float(u[2 * i + e]));
+        const float x = act_round(__uint_as_float(g[2 * i + e]));
+        const float lin = act_round(__uint_as_float(u[2 * i + e]));
         r[e] = (n > 0 ? gelu_from_lut_sel(x, lut, lo, n) : gelu_from_lut(x, lut, lo, p.lut.hi)) * lin;
       }
-      o[i] = pack_bf16x2(r[0], r[1]);
+      o[i] = pack_act2(r[0], r[1]);
     }
     store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
   }
@@ -449,7 +449,7 @@ struct EpiGeglu {
 // Written straight into the decode arena  [layer][kv][B][H][S][64].
 struct EpiCrossKV {
   struct Params {
-    __nv_bfloat16* arena;
+    act_t* arena;
     int B, H, S;
     const int* row_b = nullptr;  // packed encoder rows: row m is position row_s[m] of prompt row_b[m]
     const int* row_s = nullptr;
@@ -468,7 +468,7 @@ struct EpiCrossKV {
     const int h = rem >> 6, d0 = rem & 63;
     uint32_t o[16];
     round_pack_32(acc, o);
-    __nv_bfloat16* dst = p.arena + ((((static_cast<size_t>(lkv) * p.B + b) * p.H + h) * p.S + s) << 6) + d0;
+    act_t* dst = p.arena + ((((static_cast<size_t>(lkv) * p.B + b) * p.H + h) * p.S + s) << 6) + d0;
     store_row_chunk(dst, o, n0, N);
   }
   template <int BN>
@@ -483,8 +483,8 @@ struct EpiCrossKV {
 // torch.cat regrowth of transformers/cache_utils.py:119-120).
 struct EpiQkvDecode {
   struct Params {
-    __nv_bfloat16* q;      // [B, I]
-    __nv_bfloat16* cache;  // this layer: [2][B][H][Tmax][64]
+    act_t* q;      // [B, I]
+    act_t* cache;  // this layer: [2][B][H][Tmax][64]
     const int* step;       // device scalar: current decode position t
     int B, H, Tmax;
     int step_stride = 0;   // 1 = slot pool: row m appends at its own position step[m]
@@ -498,7 +498,7 @@ struct EpiQkvDecode {
     const int I = p.H * 64;
     uint32_t o[16];
     round_pack_32(acc, o);
-    __nv_bfloat16* dst;
+    act_t* dst;
     if (n0 < I) {
       dst = p.q + static_cast<size_t>(m) * I + n0;
     } else {
@@ -546,7 +546,7 @@ struct EpiArgmax {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int n = n0 + j;
-        float v = bf16_round(__uint_as_float(acc[j]));
+        float v = act_round(__uint_as_float(acc[j]));
         if (n >= N || (block_eos && n == p.eos)) v = -INFINITY;
         if (v > best) {  // ascending scan + strict '>' keeps the lowest index among equal maxima
           best = v;
@@ -579,7 +579,7 @@ struct EpiStoreF32 {
       if (m_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) p.C[static_cast<size_t>(m) * p.ldc + n0 + j] = bf16_round(__uint_as_float(acc[j]));
+          if (n0 + j < N) p.C[static_cast<size_t>(m) * p.ldc + n0 + j] = act_round(__uint_as_float(acc[j]));
       }
     }
   }

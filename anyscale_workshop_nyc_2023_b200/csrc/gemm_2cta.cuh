@@ -42,7 +42,7 @@ DEVINL void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* lea
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
-DEVINL void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+DEVINL void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -143,7 +143,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_act(2 * kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -160,7 +160,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + kBM * kBK * 2);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                               (kb | k) != 0 ? 1u : 0u);
           umma_commit_pair(&empty[stage]);
           if (++stage == k2ctaStages) {

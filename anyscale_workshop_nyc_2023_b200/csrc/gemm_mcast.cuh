@@ -47,7 +47,7 @@ struct McStore {
     uint4* d4 = reinterpret_cast<uint4*>(p.C + static_cast<size_t>(m) * p.ldc + n0);
     uint32_t o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+    for (int i = 0; i < 8; ++i) o[i] = pack_act2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
@@ -70,9 +70,9 @@ struct McResidual {
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float y0 = bf16_round(__uint_as_float(acc[2 * i]));
-      const float y1 = bf16_round(__uint_as_float(acc[2 * i + 1]));
-      o[i] = pack_bf16x2(bf16_lo(rw[i]) + y0, bf16_hi(rw[i]) + y1);
+      const float y0 = act_round(__uint_as_float(acc[2 * i]));
+      const float y1 = act_round(__uint_as_float(acc[2 * i + 1]));
+      o[i] = pack_act2(act_lo(rw[i]) + y0, act_hi(rw[i]) + y1);
     }
     uint4* d4 = reinterpret_cast<uint4*>(p.C + static_cast<size_t>(m) * p.ld + n0);
     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -139,7 +139,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ MMA issuer
     cluster_wait_acquire();
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, kMcBN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_act(kBM, kMcBN, 0, 0);
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[kb], 0);
         tc_fence_after_sync();
@@ -148,7 +148,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + kBM * kBK * 2);
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k)
-          umma_bf16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+          umma_f16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                        (kb | k) != 0 ? 1u : 0u);
       }
       umma_commit(tfull);

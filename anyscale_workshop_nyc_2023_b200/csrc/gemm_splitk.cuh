@@ -77,7 +77,7 @@ DEVINL void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uin
 struct NormA {
   const float* ss;            // [M][ss_ld] partial sums of squares of x
   int ss_ld;                  // = d / 32
-  const __nv_bfloat16* w;     // [K] layer-norm weight
+  const act_t* w;     // [K] layer-norm weight
   float eps;
 };
 
@@ -167,7 +167,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_act(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
@@ -178,7 +178,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + Cfg::kABytes);
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k)
-          umma_bf16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+          umma_f16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
                        (i | k) != 0 ? 1u : 0u);
         umma_commit(&empty[stage]);
         if (++stage == Cfg::kStages) {
@@ -231,9 +231,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint32_t o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float a = bf16_round(bf16_lo(xs[j]) * inv);
-            const float b = bf16_round(bf16_hi(xs[j]) * inv);
-            o[j] = pack_bf16x2(bf16_lo(wsv[j]) * a, bf16_hi(wsv[j]) * b);
+            const float a = act_round(act_lo(xs[j]) * inv);
+            const float b = act_round(act_hi(xs[j]) * inv);
+            o[j] = pack_act2(act_lo(wsv[j]) * a, act_hi(wsv[j]) * b);
           }
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
         }

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -132,7 +133,7 @@ DEVINL void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_
 DEVINL void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate. One thread issues.
-DEVINL void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+DEVINL void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -141,7 +142,7 @@ DEVINL void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
       : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]
-DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -216,23 +217,57 @@ DEVINL uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor, kind::f16, bf16 x bf16 -> fp32:
-//   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)
+// ---------------------------------------------------------------- the numerics contract of this build
+// The library is compiled twice from the same sources. Every "one rounding per eager op" point of the HF contract
+// goes through act_round / pack_act2, and every 2-byte tensor is an act_t:
+//   default            act_t = bf16   (libb200t5.so; torch_dtype=bfloat16)
+//   -DB200T5_F16=1     act_t = fp16   (libb200t5_f16.so; the notebook's literal torch_dtype=float16, NB:882, SURVEY
+//                      Appendix A.7): in addition the residual stream (res_t) and the GeGLU output that feeds `wo`
+//                      (ffh_t) are fp32, and `wo` is an fp32-weight GEMM (two tf32 passes, W = W_hi + W_lo).
+#ifndef B200T5_F16
+#define B200T5_F16 0
+#endif
+#if B200T5_F16
+typedef __half act_t;
+typedef __half2 act2_t;
+typedef float res_t;   // residual stream
+typedef float ffh_t;   // gelu(wi_0 x) * wi_1 x, the A operand of `wo`
+constexpr uint32_t kUmmaActFmt = 0;  // kind::f16 operand format field: 0 = f16
+DEVINL act_t float2act(float x) { return __float2half_rn(x); }
+__host__ __device__ inline float act2float(act_t x) { return __half2float(x); }
+DEVINL act2_t floats2act2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+DEVINL float act_lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu))); }
+DEVINL float act_hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
+#else
+typedef __nv_bfloat16 act_t;
+typedef __nv_bfloat162 act2_t;
+typedef __nv_bfloat16 res_t;
+typedef __nv_bfloat16 ffh_t;
+constexpr uint32_t kUmmaActFmt = 1;  // 1 = bf16
+DEVINL act_t float2act(float x) { return __float2bfloat16_rn(x); }
+__host__ __device__ inline float act2float(act_t x) { return __bfloat162float(x); }
+DEVINL act2_t floats2act2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+DEVINL float act_lo(uint32_t w) { return __uint_as_float(w << 16); }
+DEVINL float act_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+#endif
+DEVINL float act_round(float x) { return act2float(float2act(x)); }
+DEVINL uint32_t pack_act2(float lo, float hi) {
+  act2_t v = floats2act2(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Instruction descriptor, kind::f16 (act x act -> fp32) and kind::tf32 (fmt 2):
+//   [4,6) D fmt (1=f32)  [7,10) A fmt (0=f16, 1=bf16, 2=tf32)  [10,13) B fmt
 //   [15] A major (0=K)   [16] B major (0=K, 1=MN)   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_fmt(uint32_t fmt, int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
-
-// ---------------------------------------------------------------- bf16 helpers
-DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-DEVINL uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+__host__ __device__ constexpr uint32_t make_idesc_act(int M, int N, int a_mn_major, int b_mn_major) {
+  return make_idesc_fmt(kUmmaActFmt, M, N, a_mn_major, b_mn_major);
 }
-DEVINL float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-DEVINL float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) { return make_idesc_fmt(2u, M, N, 0, 0); }
 
 DEVINL uint4 ldg_nc_v4(const void* p) {
   uint4 r;

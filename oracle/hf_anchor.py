@@ -39,6 +39,12 @@ def load_hf_model(ckpt_dir, dtype=torch.float32, device="cpu"):
     model.lm_head.weight = torch.nn.Parameter(lm.clone())  # untie
     assert model.lm_head.weight.data_ptr() != model.shared.weight.data_ptr()
     model = model.to(dtype=dtype, device=device).eval()
+    if dtype == torch.float16:
+        # what from_pretrained(torch_dtype=float16) does for T5 (`_keep_in_fp32_modules = ["wo"]`): the feed-forward
+        # output projection keeps its fp32 checkpoint values
+        for name, mod in model.named_modules():
+            if name.endswith("DenseReluDense.wo"):
+                mod.weight = torch.nn.Parameter(sd[f"{name}.weight"].to(device=device, dtype=torch.float32).clone(), requires_grad=False)
     model.generation_config.decoder_start_token_id = config.decoder_start_token_id
     model.generation_config.eos_token_id = config.eos_token_id
     model.generation_config.pad_token_id = config.pad_token_id

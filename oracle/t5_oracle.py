@@ -27,10 +27,18 @@ tests/golden/make_golden.py and committed as tests/golden/*.npz (token IDs and l
 transformers' T5ForConditionalGeneration.generate on seeded synthetic checkpoints), plus the
 known-answer vectors of SURVEY Appendix B (bucket tables, gelu_new values).
 
-Two numerics modes:
+Three numerics modes:
   emulate_bf16=False  everything in fp32 (matches HF fp32 on CPU)
   emulate_bf16=True   fp32 arithmetic with a round-to-bf16 after every op where HF eager bf16
                       rounds - the contract the CUDA kernels implement.
+  emulate="fp16"      the notebook's literal torch_dtype=torch.float16 (NB:882):
+                      round-to-fp16 at the same points, EXCEPT that `wo` stays an fp32 weight with an fp32
+                      output (`_keep_in_fp32_modules = ["wo"]`, modeling_t5.py; T5DenseGatedActDense.forward
+                      casts its input up), so the residual stream is fp32 from the first feed-forward block
+                      on (type promotion in T5LayerFF / T5LayerSelfAttention / T5LayerCrossAttention) and
+                      T5LayerNorm rounds to fp16 only on its way out. The additive mask is finfo(fp16).min, and
+                      fp16(score + mask) overflows to -inf exactly as in torch. No CUDA path implements this
+                      mode yet; the mode and its goldens are the oracle for that work.
 """
 from __future__ import annotations
 
@@ -40,6 +48,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 BF16_MIN = np.float32(-3.3895313892515355e38)
+FP16_MIN = np.float32(-65504.0)
 FP32_MIN = np.float32(np.finfo(np.float32).min)
 
 
@@ -47,6 +56,11 @@ def _round_bf16(x: np.ndarray) -> np.ndarray:
     u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
     r = (u + (np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1)))) & np.uint32(0xFFFF0000)
     return r.view(np.float32)
+
+
+def _round_fp16(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float32)
 
 
 def relative_bucket(rel: np.ndarray, bidirectional: bool, num_buckets: int = 32, max_distance: int = 128) -> np.ndarray:
@@ -77,20 +91,33 @@ def gelu_new_f32(x: np.ndarray) -> np.ndarray:
 
 
 class T5Oracle:
-    def __init__(self, state_dict: Dict[str, np.ndarray], spec, emulate_bf16: bool = False):
+    def __init__(self, state_dict: Dict[str, np.ndarray], spec, emulate_bf16: bool = False, emulate: Optional[str] = None):
         self.sd = {k: np.asarray(v, dtype=np.float32) for k, v in state_dict.items()}
         self.spec = spec
-        self.bf16 = bool(emulate_bf16)
-        if self.bf16:
-            self.sd = {k: _round_bf16(v) for k, v in self.sd.items()}
+        self.mode = emulate if emulate is not None else ("bf16" if emulate_bf16 else "fp32")
+        if self.mode not in ("fp32", "bf16", "fp16"):
+            raise ValueError(self.mode)
+        self.bf16 = self.mode != "fp32"  # "reduced precision": one rounding per eager op
+        self.fp16 = self.mode == "fp16"
+        self._round = {"fp32": lambda x: np.asarray(x, dtype=np.float32), "bf16": _round_bf16, "fp16": _round_fp16}[self.mode]
+        if self.bf16:  # from_pretrained casts the fp32 checkpoint; in fp16 mode `wo` is kept in fp32
+            self.sd = {k: (v if self.fp16 and k.endswith("DenseReluDense.wo.weight") else self._round(v)) for k, v in self.sd.items()}
         if "lm_head.weight" not in self.sd:  # tied checkpoint
             self.sd["lm_head.weight"] = self.sd["shared.weight"]
         self.H, self.dk = spec.num_heads, spec.d_kv
-        self.mask_min = BF16_MIN if self.bf16 else FP32_MIN
+        self.mask_min = {"fp32": FP32_MIN, "bf16": BF16_MIN, "fp16": FP16_MIN}[self.mode]
 
     # ---- elementary ops with HF's rounding points
     def r(self, x):
-        return _round_bf16(x) if self.bf16 else np.asarray(x, dtype=np.float32)
+        return self._round(x)
+
+    def res_add(self, x, y):
+        """Residual add under torch type promotion. x, y = (values, is_fp32). In fp16 mode the stream turns fp32 at
+        the first feed-forward block (its `wo` output is fp32) and stays fp32; until then it is an fp16 add."""
+        (xv, xf), (yv, yf) = x, y
+        if self.fp16 and (xf or yf):
+            return (xv.astype(np.float32) + yv.astype(np.float32)).astype(np.float32), True
+        return self.r(xv + yv), False
 
     def linear(self, x, name):
         return self.r(x @ self.sd[name].T)
@@ -106,7 +133,9 @@ class T5Oracle:
             return gelu_new_f32(x)
         r = self.r  # one rounding per eager op; torch.pow(x, 3.0) on bf16 is x*x*x in bf16 arithmetic
         half_x = r(np.float32(0.5) * x)
-        x3 = r(r(x * x) * x)
+        # torch.pow(x, 3.0): bf16 -> x*x*x in bf16 arithmetic (two roundings); fp16 -> computed in fp32, one rounding
+        # (measured against torch 2.11 on CPU: 0 mismatches over a 20001-point grid for the single rounding)
+        x3 = r(x * x * x) if self.fp16 else r(r(x * x) * x)
         t = r(np.float32(0.044715) * x3)
         t = r(x + t)
         t = r(np.float32(math.sqrt(2.0 / math.pi)) * t)
@@ -117,7 +146,10 @@ class T5Oracle:
     def ff(self, x, prefix):
         g = self.gelu_new(self.linear(x, f"{prefix}.DenseReluDense.wi_0.weight"))
         u = self.linear(x, f"{prefix}.DenseReluDense.wi_1.weight")
-        return self.linear(self.r(g * u), f"{prefix}.DenseReluDense.wo.weight")
+        h = self.r(g * u)
+        if self.fp16:  # fp32 weight, input cast up, fp32 output (no rounding)
+            return (h @ self.sd[f"{prefix}.DenseReluDense.wo.weight"].T).astype(np.float32)
+        return self.linear(h, f"{prefix}.DenseReluDense.wo.weight")
 
     def _heads(self, x):  # [B,T,I] -> [B,H,T,dk]
         B, T, _ = x.shape
@@ -150,6 +182,7 @@ class T5Oracle:
         x = self.sd["shared.weight"][input_ids]
         add_mask = np.where(mask[:, None, None, :] != 0, np.float32(0), self.mask_min).astype(np.float32)
         pb = self.r(self._bias("encoder", np.arange(S), S) + add_mask)  # position_bias + mask (:323-325)
+        xf = False  # is the residual stream fp32 (fp16 mode only)
         for i in range(self.spec.num_layers):
             p = f"encoder.block.{i}.layer"
             n = self.rms_norm(x, f"{p}.0.layer_norm.weight")
@@ -157,9 +190,9 @@ class T5Oracle:
             k = self._heads(self.linear(n, f"{p}.0.SelfAttention.k.weight"))
             v = self._heads(self.linear(n, f"{p}.0.SelfAttention.v.weight"))
             a = self.linear(self._attend(q, k, v, pb), f"{p}.0.SelfAttention.o.weight")
-            x = self.r(x + a)
+            x, xf = self.res_add((x, xf), (a, False))
             n = self.rms_norm(x, f"{p}.1.layer_norm.weight")
-            x = self.r(x + self.ff(n, f"{p}.1"))
+            x, xf = self.res_add((x, xf), (self.ff(n, f"{p}.1"), self.fp16))
         return self.rms_norm(x, "encoder.final_layer_norm.weight")
 
     # ---- decoder with KV cache
@@ -178,6 +211,7 @@ class T5Oracle:
         t = cache["t"]
         x = self.sd["shared.weight"][tokens][:, None, :]  # [B,1,d]
         self_bias = self.r(self._bias("decoder", np.array([t]), t + 1))  # + causal mask of zeros
+        xf = False
         for i in range(self.spec.num_decoder_layers):
             p = f"decoder.block.{i}.layer"
             n = self.rms_norm(x, f"{p}.0.layer_norm.weight")
@@ -190,13 +224,13 @@ class T5Oracle:
                 cache["self_k"][i] = np.concatenate([cache["self_k"][i], k], axis=2)
                 cache["self_v"][i] = np.concatenate([cache["self_v"][i], v], axis=2)
             a = self._attend(q, cache["self_k"][i], cache["self_v"][i], self_bias)
-            x = self.r(x + self.linear(a, f"{p}.0.SelfAttention.o.weight"))
+            x, xf = self.res_add((x, xf), (self.linear(a, f"{p}.0.SelfAttention.o.weight"), False))
             n = self.rms_norm(x, f"{p}.1.layer_norm.weight")
             q = self._heads(self.linear(n, f"{p}.1.EncDecAttention.q.weight"))
             a = self._attend(q, cache["cross_k"][i], cache["cross_v"][i], cache["cross_bias"])
-            x = self.r(x + self.linear(a, f"{p}.1.EncDecAttention.o.weight"))
+            x, xf = self.res_add((x, xf), (self.linear(a, f"{p}.1.EncDecAttention.o.weight"), False))
             n = self.rms_norm(x, f"{p}.2.layer_norm.weight")
-            x = self.r(x + self.ff(n, f"{p}.2"))
+            x, xf = self.res_add((x, xf), (self.ff(n, f"{p}.2"), self.fp16))
         x = self.rms_norm(x, "decoder.final_layer_norm.weight")
         cache["t"] = t + 1
         return self.linear(x[:, 0, :], "lm_head.weight")

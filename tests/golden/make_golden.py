@@ -1,6 +1,6 @@
 """Generates tests/golden/*.npz by running the reference's own dependency (transformers'
 T5ForConditionalGeneration.generate, eager attention) on seeded synthetic checkpoints, in the
-build container (CPU). Re-run with:  python tests/golden/make_golden.py
+build container (CPU). Re-run with:  python tests/golden/make_golden.py   (--fp16: only the *_fp16.npz files)
 The fixtures pin oracle/t5_oracle.py; they are environment-stamped (torch / transformers versions).
 """
 import sys
@@ -21,6 +21,30 @@ CASES = [  # name, spec, weight seed, B, S, max_new, input seed, lengths
     ("tiny_full", "tiny", 1, 4, 16, 10, 102, "full"),
     ("mini_a", "mini", 2, 5, 40, 16, 103, "uniform"),
 ]
+
+
+def main_fp16():
+    """fp16 goldens (the notebook's literal torch_dtype, NB:882) in their own files, so that the fp32/bf16 fixtures
+    above stay byte-identical: tests/golden/<case>_fp16.npz."""
+    import tempfile
+
+    out_dir = Path(__file__).resolve().parent
+    for name, spec_name, wseed, B, S, T, iseed, lengths in CASES:
+        spec = SPECS[spec_name]
+        ids, mask = synthetic_token_batch(B, S, spec.vocab_size, iseed, lengths)
+        with tempfile.TemporaryDirectory() as d:
+            save_checkpoint(d, spec, seed=wseed)
+            m = load_hf_model(d, dtype=torch.float16)
+            assert m.encoder.block[0].layer[1].DenseReluDense.wo.weight.dtype == torch.float32
+            toks = hf_generate(m, ids, mask, T)
+            res = {"ids": ids, "mask": mask, "tokens_fp16": toks, "forced_fp16": hf_generate(m, ids, mask, T, min_new_tokens=T),
+                   "logits_fp16": hf_teacher_forced_logits(m, ids, mask, toks[:, :-1]).astype(np.float32)}
+            with torch.no_grad():
+                enc = m.encoder(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask)).last_hidden_state
+            res["enc_fp16"] = enc.float().numpy()
+        res["meta"] = np.array([f"spec={spec_name} wseed={wseed} max_new={T} torch={torch.__version__} transformers={transformers.__version__} wo=fp32"])
+        np.savez_compressed(out_dir / f"{name}_fp16.npz", **res)
+        print(name + "_fp16", {k: v.shape for k, v in res.items() if k != "meta"})
 
 
 def main():
@@ -50,4 +74,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--fp16" in sys.argv:
+        main_fp16()
+    else:
+        main()
+        main_fp16()
