@@ -1,7 +1,9 @@
 """ctypes binding of libb200t5.so (the C ABI declared in include/b200t5.h).
 
 The library is built in-tree (``csrc/Makefile`` -> ``libb200t5.so`` next to this file) so it
-travels with the repository snapshot. There is no fallback: if the shared object is missing or a
+travels with the repository snapshot. The same sources are compiled a second time into
+``libb200t5_f16.so``: identical entry points, the fp16 numerics contract (torch_dtype=float16 with
+transformers' fp32 `wo`) instead of the bf16 one - ``load("fp16")``. There is no fallback: if the shared object is missing or a
 symbol cannot be resolved, importing callers get a loud ``RuntimeError``.
 """
 from __future__ import annotations
@@ -13,6 +15,7 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libb200t5.so"
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": _HERE / "libb200t5_f16.so"}
 CSRC = _HERE / "csrc"
 
 OK, EINVAL, ENODEV, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -88,43 +91,46 @@ SIGNATURES = {
     "b200t5_version": (C.c_char_p, []),
 }
 
-_lib = None
+_libs = {}
 
 
 def build(force: bool = False) -> Path:
-    """Compile libb200t5.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    if force and LIB_PATH.exists():
-        LIB_PATH.unlink()
-    proc = subprocess.run(["make", "-C", str(CSRC)], capture_output=True, text=True)
-    if proc.returncode != 0 or not LIB_PATH.exists():
-        raise RuntimeError(f"building libb200t5.so failed:\n{proc.stdout}\n{proc.stderr}")
+    """Compile libb200t5.so and libb200t5_f16.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    for path in LIB_PATHS.values():
+        if force and path.exists():
+            path.unlink()
+    proc = subprocess.run(["make", "-j2", "-C", str(CSRC)], capture_output=True, text=True)
+    if proc.returncode != 0 or not all(path.exists() for path in LIB_PATHS.values()):
+        raise RuntimeError(f"building libb200t5.so / libb200t5_f16.so failed:\n{proc.stdout}\n{proc.stderr}")
     return LIB_PATH
 
 
-def load() -> C.CDLL:
-    """Load the shared library and bind every declared entry point (raises if anything is missing)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+def load(flavour: str = "bf16") -> C.CDLL:
+    """Load the shared library of one numerics contract ("bf16" | "fp16") and bind every declared entry point
+    (raises if anything is missing)."""
+    if flavour in _libs:
+        return _libs[flavour]
+    path = LIB_PATHS[flavour]
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: run `make -C {CSRC}` (or __graft_entry__.build()). "
+            f"{path} is missing: run `make -C {CSRC}` (or __graft_entry__.build()). "
             "There is no CPU or PyTorch fallback for the B200 path."
         )
-    lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    # RTLD_LOCAL (the ctypes default): both flavours export the same names and must not see each other
+    lib = C.CDLL(str(path), mode=getattr(os, "RTLD_NOW", 2))
     for name, (res, args) in SIGNATURES.items():
         try:
             fn = getattr(lib, name)
         except AttributeError as e:  # pragma: no cover
-            raise RuntimeError(f"libb200t5.so does not export {name}") from e
+            raise RuntimeError(f"{path.name} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[flavour] = lib
     return lib
 
 
-def last_error(handle=None) -> str:
-    lib = load()
+def last_error(handle=None, lib=None) -> str:
+    lib = lib or load()
     msg = lib.b200t5_last_error(handle) if handle else lib.b200t5_last_global_error()
     return (msg or b"").decode("utf-8", "replace")
 
@@ -135,6 +141,6 @@ class B200T5Error(RuntimeError):
         self.code = code
 
 
-def check(rc: int, handle=None) -> None:
+def check(rc: int, handle=None, lib=None) -> None:
     if rc != OK:
-        raise B200T5Error(rc, last_error(handle))
+        raise B200T5Error(rc, last_error(handle, lib))

@@ -67,18 +67,21 @@ static PFN_encodeTiled get_encode_fn() {
   }
   return fn;
 }
-// bf16 row-major [rows, cols] (cols contiguous); box = 64 cols x box_rows rows, 128-B swizzle.
-static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// row-major [rows, cols] (cols contiguous) of 2-byte activations / weights, or (f32) of fp32 values for the tf32
+// products of the fp16 build; box = 128 bytes of columns x box_rows rows, 128-B swizzle.
+static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32 = false) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_gerr("cuTensorMapEncodeTiled entry point not available");
     return false;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {cols * (f32 ? 4u : 2u)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                     : (B200T5_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -90,16 +93,42 @@ static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
 }
 
 // ================================================================== small device helpers
+DEVINL float load_as_float(const void* src, int dtype, size_t i) {
+  if (dtype == B200T5_DTYPE_F32) return reinterpret_cast<const float*>(src)[i];
+  if (dtype == B200T5_DTYPE_F16) return __half2float(reinterpret_cast<const __half*>(src)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+}
 __global__ void convert_to_act_kernel(const void* src, int dtype, act_t* dst, size_t n) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) {
-    float v;
-    if (dtype == B200T5_DTYPE_F32) v = reinterpret_cast<const float*>(src)[i];
-    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
-    dst[i] = float2act(v);
-  }
+  for (; i < n; i += stride) dst[i] = float2act(load_as_float(src, dtype, i));
 }
+#if B200T5_F16
+// `wo` stays an fp32 weight (transformers' _keep_in_fp32_modules = ["wo"] under torch_dtype=float16)
+__global__ void convert_to_f32_kernel(const void* src, int dtype, float* dst, size_t n) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) dst[i] = load_as_float(src, dtype, i);
+}
+// W [rows, K] fp32 -> W' [rows, 2*Kp] = [W_hi | W_lo], Kp = K rounded up to the 32-element k-block, both pieces
+// exactly representable in tf32 (low 13 mantissa bits clear): W_hi = tf32_rn(W), W_lo = tf32_rn(W - W_hi) (the
+// subtraction is exact), so A . W_hi^T + A . W_lo^T with fp32 accumulation carries ~22 of W's 24 significand bits.
+DEVINL float tf32_rn(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x0FFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int K, int Kp) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t n = static_cast<size_t>(rows) * Kp;
+  if (i >= n) return;
+  const int r = static_cast<int>(i / Kp), k = static_cast<int>(i % Kp);
+  const float v = k < K ? w[static_cast<size_t>(r) * K + k] : 0.f;
+  const float hi = tf32_rn(v);
+  out[static_cast<size_t>(r) * 2 * Kp + k] = hi;
+  out[static_cast<size_t>(r) * 2 * Kp + Kp + k] = tf32_rn(v - hi);
+}
+#endif
 // mode 0: the engine's path (table lookup); 1/2: op-by-op arithmetic with pow_mode 1/0
 __global__ void geglu_elementwise_kernel(const act_t* gate, const act_t* up, act_t* out, long long n, int mode, GeluLut lut) {
   long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -260,8 +289,10 @@ struct b200t5_ctx {
   int device = 0;
   int num_sms = 148;
   bool finalized = false;
+  int ffo_k = 0;  // K extent of the feed-forward output weight as stored (F, or 2 * round_up(F, 32) in the fp16 build)
   char err[512] = "";
-  std::map<std::string, std::unique_ptr<DevBuf>> raw;  // HF name -> bf16 copy (until finalize)
+  std::map<std::string, std::unique_ptr<DevBuf>> raw;  // HF name -> act_t copy (until finalize)
+  std::map<std::string, std::unique_ptr<DevBuf>> raw_f32;  // fp16 build: fp32 copies of the `wo` weights
   std::map<std::string, std::vector<int64_t>> raw_shape;
   DevBuf shared, lm_head, enc_final_ln, dec_final_ln, enc_relbias, dec_relbias, wcrosskv;
   CUtensorMap tm_lm, tm_crosskv, tm2_crosskv;
@@ -417,7 +448,25 @@ static cudaError_t run_gemm_sk_norm(b200t5_ctx* h, const b200t5_ctx::SkChoice& c
   return launch_gemm_splitk<64, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
 }
 
-static cudaError_t run_rmsnorm(b200t5_ctx* h, const act_t* x, const act_t* w, act_t* y, int M, int d, float eps,
+// Feed-forward output projection + residual. bf16 build: an ordinary 2-byte product. fp16 build: fp32 weight and
+// fp32 output (HF keeps `wo` in fp32), computed as two tf32 passes over W' = [W_hi | W_lo] with the fp32 A operand
+// (the GeGLU output) walked twice.
+static cudaError_t run_ffo_2cta(b200t5_ctx* h, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
+                                const EpiResidual::Params& ep, cudaStream_t s) {
+  h->launches++;
+  return launch_gemm_2cta<EpiResidual, B200T5_F16 != 0>(tmA, tmB, M, N, h->ffo_k, ep, h->num_sms, s, B200T5_F16 ? h->ffo_k / 64 : 0);
+}
+static cudaError_t run_ffo_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                              int M, int N, const EpiResidual::Params& ep, cudaStream_t s, bool pdl) {
+  h->launches++;
+  constexpr bool tf = B200T5_F16 != 0;
+  const int split = splitk_factor(h->ffo_k, ch.split, tf ? kBK / 2 : kBK);
+  const int akb = tf ? h->ffo_k / 64 : 0;
+  if (ch.bn == 128) return launch_gemm_splitk<128, EpiResidual, false, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, NormA{}, akb);
+  return launch_gemm_splitk<64, EpiResidual, false, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, NormA{}, akb);
+}
+
+static cudaError_t run_rmsnorm(b200t5_ctx* h, const res_t* x, const act_t* w, act_t* y, int M, int d, float eps,
                                cudaStream_t s, bool pdl = false) {
   if (h) h->launches++;
   const int wpb = 8;
@@ -446,6 +495,9 @@ static cudaError_t init_kernel_attrs() {
   PREPSK(64, EpiStore) PREPSK(128, EpiStore) PREPSK(64, EpiResidual) PREPSK(128, EpiResidual)
   PREPSK(64, EpiQkvDecode) PREPSK(128, EpiQkvDecode) PREPSK(64, EpiGeglu) PREPSK(128, EpiGeglu)
 #undef PREPSK
+  if ((e = prepare_gemm_2cta<EpiResidual, B200T5_F16 != 0>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_splitk<64, EpiResidual, false, B200T5_F16 != 0>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_splitk<128, EpiResidual, false, B200T5_F16 != 0>()) != cudaSuccess) return e;
 #define PREPSKN(BN, EPI) \
   if ((e = prepare_gemm_splitk<BN, EPI, true>()) != cudaSuccess) return e;
   PREPSKN(64, EpiStore) PREPSKN(128, EpiStore) PREPSKN(64, EpiQkvDecode) PREPSKN(128, EpiQkvDecode)
@@ -511,7 +563,9 @@ static int ensure_gelu_lut(b200t5_ctx* h, int pow_mode, GeluLut* out) {
 }
 
 // ================================================================== lifecycle
-extern "C" const char* b200t5_version(void) { return "b200t5 0.1 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* b200t5_version(void) {
+  return B200T5_F16 ? "b200t5 0.1 fp16 (sm_100a, tcgen05/TMA)" : "b200t5 0.1 (sm_100a, tcgen05/TMA)";
+}
 extern "C" const char* b200t5_last_global_error(void) { return g_err; }
 extern "C" const char* b200t5_last_error(b200t5_handle h) { return h ? h->err : g_err; }
 
@@ -577,6 +631,16 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   }
   const char* ch_env = getenv("B200T5_CHAINS");
   h->chains_override = ch_env ? atoi(ch_env) : 0;
+#if B200T5_F16
+  // the fp16 build implements the default kernel set only (the measured-slower experiments and the fallbacks
+  // they replace assume the bf16 contract: 2-byte residual stream, table-driven gelu)
+  h->mega_on = h->mcast = h->fuse_norm = h->xattn_tc = h->l2_prefetch = false;
+  h->use_2cta = h->pack_rows = h->enc_attn_tc = true;
+  if (!h->sk_on) {
+    delete h;
+    return fail(nullptr, B200T5_EINVAL, "B200T5_SK=0 is not available in the fp16 build");
+  }
+#endif
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->exec_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
@@ -589,6 +653,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
       return fail(nullptr, B200T5_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(ke));
     }
   }
+#if !B200T5_F16  // (the fp16 build evaluates gelu_new directly; the table indexes bf16 bit patterns)
   {
     int lrc = ensure_gelu_lut(nullptr, h->pow_mode, &h->gelu_lut);
     if (lrc != B200T5_OK) {
@@ -596,6 +661,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
       return lrc;
     }
   }
+#endif
   {
     cudaError_t ce = cudaSuccess;
     for (int i = 0; i < 4 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
@@ -643,7 +709,7 @@ extern "C" int b200t5_set_weight(b200t5_handle h, const char* name, const void* 
   }
   std::unique_ptr<DevBuf> buf(new DevBuf());
   CU_OK(h, buf->alloc(n * sizeof(act_t)));
-  if (dtype == B200T5_DTYPE_BF16) {
+  if (dtype == (B200T5_F16 ? B200T5_DTYPE_F16 : B200T5_DTYPE_BF16)) {
     CU_OK(h, cudaMemcpy(buf->p, dev_ptr, n * sizeof(act_t), cudaMemcpyDeviceToDevice));
   } else {
     convert_to_act_kernel<<<1024, 256>>>(dev_ptr, dtype, buf->as<act_t>(), n);
@@ -652,6 +718,20 @@ extern "C" int b200t5_set_weight(b200t5_handle h, const char* name, const void* 
   }
   h->raw[name] = std::move(buf);
   h->raw_shape[name] = shp;
+#if B200T5_F16
+  {
+    const std::string nm(name);
+    const std::string suffix = "DenseReluDense.wo.weight";
+    if (nm.size() >= suffix.size() && nm.compare(nm.size() - suffix.size(), suffix.size(), suffix) == 0) {
+      std::unique_ptr<DevBuf> f(new DevBuf());
+      CU_OK(h, f->alloc(n * 4));
+      convert_to_f32_kernel<<<1024, 256>>>(dev_ptr, dtype, f->as<float>(), n);
+      CU_OK(h, cudaGetLastError());
+      CU_OK(h, cudaDeviceSynchronize());
+      h->raw_f32[nm] = std::move(f);
+    }
+  }
+#endif
   return B200T5_OK;
 }
 
@@ -688,6 +768,29 @@ static int interleave_geglu(b200t5_ctx* h, const act_t* wi0, const act_t* wi1, D
   return B200T5_OK;
 }
 
+// Feed-forward output projection weight [d, F] as the GEMM kernels read it: a 2-byte copy (bf16 build) or the
+// two tf32 pieces side by side, [d, 2 * round_up(F, 32)] fp32 (fp16 build).
+static int build_ffo(b200t5_ctx* h, DevBuf& dst, const std::string& name, const act_t* src2, int d, int F, int* k_cols) {
+#if B200T5_F16
+  auto it = h->raw_f32.find(name);
+  if (it == h->raw_f32.end()) return fail(h, B200T5_ESTATE, "finalize: missing fp32 copy of '%s'", name.c_str());
+  const int Fp = (F + 31) / 32 * 32;
+  CU_OK(h, dst.alloc(static_cast<size_t>(d) * 2 * Fp * 4));
+  const size_t n = static_cast<size_t>(d) * Fp;
+  split_tf32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(it->second->as<float>(), dst.as<float>(), d, F, Fp);
+  CU_OK(h, cudaGetLastError());
+  CU_OK(h, cudaDeviceSynchronize());
+  *k_cols = 2 * Fp;
+  (void)src2;
+  return B200T5_OK;
+#else
+  *k_cols = F;
+  CU_OK(h, dst.alloc(static_cast<size_t>(d) * F * sizeof(act_t)));
+  CU_OK(h, cudaMemcpy(dst.p, src2, static_cast<size_t>(d) * F * sizeof(act_t), cudaMemcpyDeviceToDevice));
+  return B200T5_OK;
+#endif
+}
+
 static int clone_buf(b200t5_ctx* h, DevBuf& dst, const act_t* src, size_t n) {
   CU_OK(h, dst.alloc(n * sizeof(act_t)));
   CU_OK(h, cudaMemcpy(dst.p, src, n * sizeof(act_t), cudaMemcpyDeviceToDevice));
@@ -702,6 +805,11 @@ static int clone_buf(b200t5_ctx* h, DevBuf& dst, const act_t* src, size_t n) {
 #define TMAP(h, tm, base, rows, cols, box) \
   do {                                     \
     if (!make_tmap(tm, base, rows, cols, box)) return fail(h, B200T5_ECUDA, "%s", g_err); \
+  } while (0)
+// the operands of the feed-forward output projection: 2-byte in the bf16 build, fp32 (tf32 MMA) in the fp16 build
+#define TMAP_FFO(h, tm, base, rows, cols, box) \
+  do {                                         \
+    if (!make_tmap(tm, base, rows, cols, box, B200T5_F16 != 0)) return fail(h, B200T5_ECUDA, "%s", g_err); \
   } while (0)
 
 extern "C" int b200t5_finalize(b200t5_handle h) {
@@ -766,15 +874,15 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     int wi_rows = 0;
     TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, 256, &wi_rows));
     if (!(p = take(h, key("layer.1.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
-    TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
+    TRY(build_ffo(h, w.wff_o, key("layer.1.DenseReluDense.wo.weight"), p, d, F, &h->ffo_k));
     TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, 256);
     TMAP(h, &w.tm_o, w.wo.p, d, I, 256);
     TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, 256);
-    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, 256);
+    TMAP_FFO(h, &w.tm_ffo, w.wff_o.p, d, h->ffo_k, 256);
     TMAP(h, &w.tm2_qkv, w.wqkv.p, 3 * I, d, 128);
     TMAP(h, &w.tm2_o, w.wo.p, d, I, 128);
     TMAP(h, &w.tm2_wi, w.wi.p, wi_rows, d, 128);
-    TMAP(h, &w.tm2_ffo, w.wff_o.p, d, F, 128);
+    TMAP_FFO(h, &w.tm2_ffo, w.wff_o.p, d, h->ffo_k, 128);
   }
 
   CU_OK(h, h->wcrosskv.alloc(static_cast<size_t>(c.Ld) * 2 * I * d * sizeof(act_t)));
@@ -831,13 +939,13 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
       w.mega_wi_bn = mbn;
     }
     if (!(p = take(h, key("layer.2.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
-    TRY(clone_buf(h, w.wff_o, p, static_cast<size_t>(d) * F));
+    TRY(build_ffo(h, w.wff_o, key("layer.2.DenseReluDense.wo.weight"), p, d, F, &h->ffo_k));
     TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, bn_qkv);
     TMAP(h, &w.tm_o, w.wo.p, d, I, bn_proj);
     TMAP(h, &w.tm_cq, w.wcq.p, I, d, bn_proj);
     TMAP(h, &w.tm_co, w.wco.p, d, I, bn_proj);
     TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, bn_wi);
-    TMAP(h, &w.tm_ffo, w.wff_o.p, d, F, bn_ffo);
+    TMAP_FFO(h, &w.tm_ffo, w.wff_o.p, d, h->ffo_k, bn_ffo);
     TMAP(h, &w.tm16_o, w.wo.p, d, I, 16);
     TMAP(h, &w.tm16_cq, w.wcq.p, I, d, 16);
     TMAP(h, &w.tm16_co, w.wco.p, d, I, 16);
@@ -846,6 +954,7 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
   TMAP(h, &h->tm2_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 128);
 
   h->raw.clear();
+  h->raw_f32.clear();
   h->raw_shape.clear();
   h->finalized = true;
   return B200T5_OK;
@@ -969,11 +1078,11 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   pl->Tmax = Tmax;
   const size_t M = static_cast<size_t>(B) * S;
   const int d = c.d, I = c.I, F = c.F, H = c.H;
-  CU_OK(h, pl->x.alloc(M * d * 2));
+  CU_OK(h, pl->x.alloc(M * d * sizeof(res_t)));
   CU_OK(h, pl->xn.alloc(M * d * 2));
   CU_OK(h, pl->qkv.alloc(M * 3 * I * 2));
   CU_OK(h, pl->ctx.alloc(M * I * 2));
-  CU_OK(h, pl->hff.alloc(M * F * 2));
+  CU_OK(h, pl->hff.alloc(M * F * sizeof(ffh_t)));
   CU_OK(h, pl->key_ok.alloc(M));
   CU_OK(h, pl->extent.alloc(static_cast<size_t>(B) * 4));
   CU_OK(h, pl->cu.alloc(static_cast<size_t>(B + 1) * 4));
@@ -984,11 +1093,11 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   // finite everywhere: keys beyond a prompt's extent are never written, and the tensor-core decode attention
   // multiplies them by p = 0
   CU_OK(h, cudaMemset(pl->cross_kv.p, 0, pl->cross_kv.bytes));
-  CU_OK(h, pl->dx.alloc(static_cast<size_t>(B) * d * 2));
+  CU_OK(h, pl->dx.alloc(static_cast<size_t>(B) * d * sizeof(res_t)));
   CU_OK(h, pl->dxn.alloc(static_cast<size_t>(B) * d * 2));
   CU_OK(h, pl->dq.alloc(static_cast<size_t>(B) * I * 2));
   CU_OK(h, pl->dctx.alloc(static_cast<size_t>(B) * I * 2));
-  CU_OK(h, pl->dh.alloc(static_cast<size_t>(B) * F * 2));
+  CU_OK(h, pl->dh.alloc(static_cast<size_t>(B) * F * sizeof(ffh_t)));
   CU_OK(h, pl->dss.alloc(static_cast<size_t>(B) * ((d + 31) / 32) * 4));
   CU_OK(h, pl->self_kv.alloc(static_cast<size_t>(c.Ld) * 2 * B * I * Tmax * 2));
   pl->n_vtiles = (c.V + 127) / 128;
@@ -1034,7 +1143,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   }
   TMAP(h, &pl->tm_xn, pl->xn.p, M, d, 128);
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
-  TMAP(h, &pl->tm_hff, pl->hff.p, M, F, 128);
+  TMAP_FFO(h, &pl->tm_hff, pl->hff.p, M, F, 128);
   TMAP(h, &pl->tm_qkv_attn, pl->qkv.p, M, 3 * I, 128);
   TMAP(h, &pl->tm_cross_kv, pl->cross_kv.p, static_cast<uint64_t>(c.Ld) * 2 * B * H * S, 64, 128);
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
@@ -1050,9 +1159,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
       ch.b0 = static_cast<int>(static_cast<long long>(B) * i / nc);
       ch.nb = static_cast<int>(static_cast<long long>(B) * (i + 1) / nc) - ch.b0;
       TMAP(h, &ch.tm_dxn, pl->dxn.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
-      TMAP(h, &ch.tm_dx, pl->dx.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
+      if (!B200T5_F16)  // A operand of the fused-RMSNorm experiment (bf16 build only)
+        TMAP(h, &ch.tm_dx, pl->dx.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
       TMAP(h, &ch.tm_dctx, pl->dctx.as<act_t>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
-      TMAP(h, &ch.tm_dh, pl->dh.as<act_t>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
+      TMAP_FFO(h, &ch.tm_dh, pl->dh.as<ffh_t>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
     }
   }
   TRY(build_mega(h, *pl));
@@ -1099,11 +1209,11 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     CU_OK(h, cudaStreamSynchronize(s));
     M = *p.h_cu;
     cu = p.cu.as<int>();
-    embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<act_t>(), cu, p.row_b.as<int>(),
+    embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<res_t>(), cu, p.row_b.as<int>(),
                                                                p.row_s.as<int>(), S, d, c.V);
     h->launches += 2;
   } else {
-    embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<act_t>(), M, d, c.V);
+    embed_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<res_t>(), M, d, c.V);
     h->launches++;
   }
   p.packed_rows = M;
@@ -1113,7 +1223,7 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
   const int wi_tiles = (F + 127) / 128;
   for (int l = 0; l < c.Le; ++l) {
     EncLayerW& w = h->enc[l];
-    CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), w.ln0.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, p.x.as<res_t>(), w.ln0.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
     {
       EpiStore::Params ep{p.qkv.as<act_t>(), 3 * I};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiStore>(h, p.tm_xn, w.tm2_qkv, M, 3 * I, d, ep, s));
@@ -1129,23 +1239,26 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     h->launches++;
     CU_OK(h, cudaGetLastError());
     {
-      EpiResidual::Params ep{p.x.as<act_t>(), p.x.as<act_t>(), d};
+      EpiResidual::Params ep{p.x.as<res_t>(), p.x.as<res_t>(), d};
+      ep.round_out = l == 0;  // (fp16 build) the stream is still fp16 before the first feed-forward block
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_ctx, w.tm2_o, M, d, I, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_ctx, w.tm_o, M, d, I, G_RES256, 0), &ep, s));
     }
-    CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), w.ln1.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
+    CU_OK(h, run_rmsnorm(h, p.x.as<res_t>(), w.ln1.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
     {
-      EpiGeglu::Params ep{p.hff.as<act_t>(), F, h->gelu_lut};
+      EpiGeglu::Params ep{p.hff.as<ffh_t>(), F, h->gelu_lut};
       if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiGeglu>(h, p.tm_xn, w.tm2_wi, M, wi_tiles * 256, d, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_wi, M, wi_tiles * 256, d, G_GEGLU256, 0), &ep, s));
     }
     {
-      EpiResidual::Params ep{p.x.as<act_t>(), p.x.as<act_t>(), d};
-      if (h->use_2cta) CU_OK(h, run_gemm_2cta<EpiResidual>(h, p.tm_hff, w.tm2_ffo, M, d, F, ep, s));
+      EpiResidual::Params ep{p.x.as<res_t>(), p.x.as<res_t>(), d};
+      ep.round_acc = B200T5_F16 ? 0 : 1;  // fp16 build: `wo` is an fp32 Linear, its output is not rounded
+      ep.round_out = B200T5_F16 ? 0 : 1;
+      if (h->use_2cta) CU_OK(h, run_ffo_2cta(h, p.tm_hff, w.tm2_ffo, M, d, ep, s));
       else CU_OK(h, run_gemm(h, mk(p.tm_hff, w.tm_ffo, M, d, F, G_RES256, 0), &ep, s));
     }
   }
-  CU_OK(h, run_rmsnorm(h, p.x.as<act_t>(), h->enc_final_ln.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
+  CU_OK(h, run_rmsnorm(h, p.x.as<res_t>(), h->enc_final_ln.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
   return B200T5_OK;
 }
 
@@ -1169,7 +1282,9 @@ static int run_cross_kv(b200t5_ctx* h, cudaStream_t s) {
 // step counter) and write disjoint row ranges of the same buffers.
 struct ChainView {
   int b0, nb;
-  act_t *dx, *dxn, *dq, *dctx, *dh;
+  res_t* dx;
+  ffh_t* dh;
+  act_t *dxn, *dq, *dctx;
   const Plan::Chain* ch;
 };
 static ChainView chain_view(b200t5_ctx* h, const Plan::Chain& ch) {
@@ -1178,11 +1293,11 @@ static ChainView chain_view(b200t5_ctx* h, const Plan::Chain& ch) {
   ChainView v;
   v.b0 = ch.b0;
   v.nb = ch.nb;
-  v.dx = p.dx.as<act_t>() + static_cast<size_t>(ch.b0) * c.d;
+  v.dx = p.dx.as<res_t>() + static_cast<size_t>(ch.b0) * c.d;
   v.dxn = p.dxn.as<act_t>() + static_cast<size_t>(ch.b0) * c.d;
   v.dq = p.dq.as<act_t>() + static_cast<size_t>(ch.b0) * c.I;
   v.dctx = p.dctx.as<act_t>() + static_cast<size_t>(ch.b0) * c.I;
-  v.dh = p.dh.as<act_t>() + static_cast<size_t>(ch.b0) * c.F;
+  v.dh = p.dh.as<ffh_t>() + static_cast<size_t>(ch.b0) * c.F;
   v.ch = &ch;
   return v;
 }
@@ -1225,6 +1340,7 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   h->launches++;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
+    ep.round_out = l == 0;  // (fp16 build) the stream is still fp16 before the first feed-forward block
     if (fuse) {
       ep.ss = ss;
       ep.ss_ld = ss_ld;
@@ -1307,6 +1423,7 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
   float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
+    ep.round_out = l == 0;
     if (fuse) {
       ep.ss = ss;
       ep.ss_ld = ss_ld;
@@ -1332,7 +1449,9 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
       ep.ss = ss;
       ep.ss_ld = ss_ld;
     }
-    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_ffo, v.ch->tm_dh, w.tm_ffo, v.nb, d, F, ep, s, pdl));
+    ep.round_acc = B200T5_F16 ? 0 : 1;  // fp16 build: `wo` is an fp32 Linear, its output is not rounded
+    ep.round_out = B200T5_F16 ? 0 : 1;
+    if (h->sk_on) CU_OK(h, run_ffo_sk(h, h->sk_ffo, v.ch->tm_dh, w.tm_ffo, v.nb, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dh, w.tm_ffo, v.nb, d, F, G_RES32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
@@ -1520,7 +1639,7 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
   CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   decode_init_kernel<<<B, 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.out_ids.as<long long>(),
-                                       p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
+                                       p.out_len.as<int>(), T + 1, B, start, pad, h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
   h->launches++;
   CU_OK(h, cudaGetLastError());
   CU_OK(h, cudaEventRecord(h->ev[1], s));
@@ -1656,7 +1775,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     stream_init_kernel<<<static_cast<unsigned>(rows), 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.pos.as<int>(),
                                                                   p.live_extent.as<int>(), p.stream_out.as<long long>(),
                                                                   p.stream_len.as<int>(), T + 1, static_cast<int>(N), B, start, pad,
-                                                                  h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
+                                                                  h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
     h->launches++;
     CU_OK(h, cudaGetLastError());
   }
@@ -1699,7 +1818,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
       admit_slots_kernel<<<k, 128, 0, s>>>(p.admit.as<int>() + B, p.admit.as<int>() + 2 * B, p.unfinished.as<int>(), p.pos.as<int>(),
                                            p.out_row.as<int>(), p.extent.as<int>(), p.live_extent.as<int>(),
                                            p.key_ok.as<unsigned char>(), p.live_key_ok.as<unsigned char>(), S, start,
-                                           h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
+                                           h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
       h->launches++;
       CU_OK(h, cudaGetLastError());
       fill_stats_model(h, 0);
@@ -1853,7 +1972,7 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
   CU_OK(h, col.alloc(static_cast<size_t>(B) * 8));
   for (int t = 0; t < T; ++t) {
     CU_OK(h, cudaMemcpy2DAsync(col.p, 8, reinterpret_cast<const long long*>(decoder_input_ids) + t, static_cast<size_t>(T) * 8, 8, B, cudaMemcpyDeviceToDevice, s));
-    force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<act_t>(), p.dx.as<act_t>(), c.d);
+    force_token_kernel<<<B, 128, 0, s>>>(col.as<long long>(), h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
     TRY(run_decode_step(h, s, false, logits + static_cast<size_t>(t) * c.V, T * c.V, c.eos, c.pad, 0));
   }
   CU_OK(h, cudaStreamSynchronize(s));
@@ -1871,6 +1990,9 @@ static int hook_device(int device) {
 
 extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
                                 int pow_mode, void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
@@ -1921,10 +2043,14 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
   }
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm(bn=%d, mode=%d): %s", bn, mode, cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }
 
 extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn,
                                        int split, int mode, int pow_mode, void* aux, int Tmax, int step, void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
@@ -1984,19 +2110,27 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
   }
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm_splitk(bn=%d, split=%d, mode=%d): %s", bn, split, mode, cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }
 
 extern "C" int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   cudaError_t e = run_rmsnorm(nullptr, static_cast<const act_t*>(x), static_cast<const act_t*>(w), static_cast<act_t*>(y), M, d, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "rmsnorm: %s", cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }
 
 extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx,
                                        int B, int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
                                        const float* dist_bias, void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -2025,11 +2159,15 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "attn_decode: %s", cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }
 
 extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, const float* rel_bias,
                                         const uint8_t* key_ok, const int32_t* extent, int B, int S, int H, int impl,
                                         void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   if (impl == 1) {
@@ -2051,9 +2189,13 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
   }
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn: %s", cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }
 
 extern "C" int b200t5_test_geglu(int device, const void* gate, const void* up, void* out, int64_t n, int pow_mode, void* stream) {
+#if B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");
+#else
   const int sms = hook_device(device);
   if (sms < 0) return sms;
   GeluLut lut;
@@ -2064,4 +2206,5 @@ extern "C" int b200t5_test_geglu(int device, const void* gate, const void* up, v
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "geglu: %s", cudaGetErrorString(e));
   return B200T5_OK;
+#endif
 }

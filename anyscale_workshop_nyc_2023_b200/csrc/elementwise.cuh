@@ -5,17 +5,39 @@
 
 namespace b200 {
 
+// 8 consecutive residual-stream elements as floats (bf16 build: one 16-byte load; fp16 build: the stream is fp32)
+DEVINL void load_res8(const res_t* p, float (&f)[8]) {
+#if B200T5_F16
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+#else
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  f[0] = act_lo(v.x); f[1] = act_hi(v.x); f[2] = act_lo(v.y); f[3] = act_hi(v.y);
+  f[4] = act_lo(v.z); f[5] = act_hi(v.z); f[6] = act_lo(v.w); f[7] = act_hi(v.w);
+#endif
+}
+// the same 8 elements written from a row of the embedding table (act_t values widen exactly)
+DEVINL void store_res8_from_act(res_t* dst, const uint4& e) {
+#if B200T5_F16
+  reinterpret_cast<float4*>(dst)[0] = make_float4(act_lo(e.x), act_hi(e.x), act_lo(e.y), act_hi(e.y));
+  reinterpret_cast<float4*>(dst)[1] = make_float4(act_lo(e.z), act_hi(e.z), act_lo(e.w), act_hi(e.w));
+#else
+  *reinterpret_cast<uint4*>(dst) = e;
+#endif
+}
+
+
 // ---------------------------------------------------------------- embedding gather
 // x[m, :] = E[ids[m], :]   (modeling_t5.py:682).  One warp per row, 16-B vectors.
 __global__ void embed_rows_kernel(const long long* __restrict__ ids, const act_t* __restrict__ E,
-                                  act_t* __restrict__ x, int M, int d, int vocab) {
+                                  res_t* __restrict__ x, int M, int d, int vocab) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   long long id = ids[row];
   if (id < 0 || id >= vocab) id = 0;  // HF would raise an index error; ids are validated on the host
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(id) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * d);
-  for (int i = lane_id(); i < d / 8; i += 32) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(row) * d;
+  for (int i = lane_id(); i < d / 8; i += 32) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 // ---------------------------------------------------------------- packed (variable-length) encoder rows
@@ -62,7 +84,7 @@ __global__ void pack_offsets_kernel(const int* __restrict__ extent, int* __restr
 
 // row tables for the packed layout + embedding gather: x[cu[b] + s, :] = E[ids[b, s], :]
 __global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, const act_t* __restrict__ E,
-                                         act_t* __restrict__ x, const int* __restrict__ cu,
+                                         res_t* __restrict__ x, const int* __restrict__ cu,
                                          int* __restrict__ row_b, int* __restrict__ row_s, int S, int d, int vocab) {
   const int b = blockIdx.y;
   const int n = cu[b + 1] - cu[b];
@@ -76,8 +98,8 @@ __global__ void embed_rows_packed_kernel(const long long* __restrict__ ids, cons
   long long id = ids[static_cast<size_t>(b) * S + s];
   if (id < 0 || id >= vocab) id = 0;
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(id) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * d);
-  for (int i = lane_id(); i < d / 8; i += 32) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(row) * d;
+  for (int i = lane_id(); i < d / 8; i += 32) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 // test hook: packed rows back to the padded [B*S, d] layout (rows beyond extent[b] are zero)
@@ -98,8 +120,8 @@ __global__ void unpack_rows_kernel(const act_t* __restrict__ xp, const int* __re
 //   y1  = bf16( float(x) * rsqrt(var + eps) )   first rounding
 //   y   = bf16( float(w) * float(y1) )          second rounding
 // One warp per row; the row stays in registers between the two passes.
-template <int kMaxVec>  // uint4 vectors per lane: d <= kMaxVec * 256
-__global__ void rmsnorm_kernel(const act_t* __restrict__ x, const act_t* __restrict__ w,
+template <int kMaxVec>  // 8-element vectors per lane: d <= kMaxVec * 256
+__global__ void rmsnorm_kernel(const res_t* __restrict__ x, const act_t* __restrict__ w,
                                act_t* __restrict__ y, int M, int d, float eps) {
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -115,21 +137,16 @@ __global__ void rmsnorm_kernel(const act_t* __restrict__ x, const act_t* __restr
   }
   pdl_wait();
   if (row >= M) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
-  uint4 v[kMaxVec];
+  const res_t* xr = x + static_cast<size_t>(row) * d;
+  float v[kMaxVec][8];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      v[i] = xr[idx];
-      const uint32_t wds[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      load_res8(xr + idx * 8, v[i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = act_lo(wds[j]), b = act_hi(wds[j]);
-        ss = fmaf(a, a, ss);
-        ss = fmaf(b, b, ss);
-      }
+      for (int j = 0; j < 8; ++j) ss = fmaf(v[i][j], v[i][j], ss);
     }
   }
 #pragma unroll
@@ -140,13 +157,12 @@ __global__ void rmsnorm_kernel(const act_t* __restrict__ x, const act_t* __restr
   for (int i = 0; i < kMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      const uint32_t xs[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
       const uint32_t ws[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = act_round(act_lo(xs[j]) * inv);
-        const float b = act_round(act_hi(xs[j]) * inv);
+        const float a = act_round(v[i][2 * j] * inv);
+        const float b = act_round(v[i][2 * j + 1] * inv);
         o[j] = pack_act2(act_lo(ws[j]) * a, act_hi(ws[j]) * b);
       }
       yr[idx] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -195,7 +211,7 @@ struct DecodeState {
 __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished, long long* __restrict__ out_ids,
                                    int* __restrict__ out_len, int out_ld, int B, long long start_tok,
                                    long long pad_tok, const act_t* __restrict__ E,
-                                   act_t* __restrict__ x, int d) {
+                                   res_t* __restrict__ x, int d) {
   const int b = blockIdx.x;
   if (b == 0 && threadIdx.x == 0) {
     st->step = 0;
@@ -209,8 +225,8 @@ __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished
     out_len[b] = 0;
   }
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(start_tok) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(b) * d;
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 // ---------------------------------------------------------------- slot pool (b200t5_generate_stream)
@@ -219,7 +235,7 @@ __global__ void decode_init_kernel(DecodeState* st, int* __restrict__ unfinished
 __global__ void stream_init_kernel(DecodeState* st, int* __restrict__ unfinished, int* __restrict__ pos,
                                    int* __restrict__ live_extent, long long* __restrict__ out_ids,
                                    int* __restrict__ out_len, int out_ld, int N, int B, long long start_tok,
-                                   long long pad_tok, const act_t* __restrict__ E, act_t* __restrict__ x,
+                                   long long pad_tok, const act_t* __restrict__ E, res_t* __restrict__ x,
                                    int d) {
   const int r = blockIdx.x;
   if (r == 0 && threadIdx.x == 0) {
@@ -238,8 +254,8 @@ __global__ void stream_init_kernel(DecodeState* st, int* __restrict__ unfinished
       live_extent[r] = 0;
     }
     const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(pad_tok) * d);
-    uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(r) * d);
-    for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+    res_t* dst = x + static_cast<size_t>(r) * d;
+    for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
   }
 }
 
@@ -248,7 +264,7 @@ __global__ void admit_slots_kernel(const int* __restrict__ slots, const int* __r
                                    int* __restrict__ pos, int* __restrict__ out_row, const int* __restrict__ extent,
                                    int* __restrict__ live_extent, const unsigned char* __restrict__ key_ok,
                                    unsigned char* __restrict__ live_key_ok, int S, long long start_tok,
-                                   const act_t* __restrict__ E, act_t* __restrict__ x, int d) {
+                                   const act_t* __restrict__ E, res_t* __restrict__ x, int d) {
   const int b = slots[blockIdx.x];
   if (threadIdx.x == 0) {
     unfinished[b] = 1;
@@ -258,8 +274,8 @@ __global__ void admit_slots_kernel(const int* __restrict__ slots, const int* __r
   }
   for (int j = threadIdx.x; j < S; j += blockDim.x) live_key_ok[static_cast<size_t>(b) * S + j] = key_ok[static_cast<size_t>(b) * S + j];
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(start_tok) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(b) * d;
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 // One CTA per row: reduce the per-tile (max, index) partials of the fused lm_head
@@ -276,7 +292,7 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
                                      DecodeState* st, int* __restrict__ unfinished,
                                      long long* __restrict__ out_ids, int* __restrict__ out_len, int out_ld,
                                      long long eos_tok, long long pad_tok, const act_t* __restrict__ E,
-                                     act_t* __restrict__ x, int d, int* __restrict__ live_extent,
+                                     res_t* __restrict__ x, int d, int* __restrict__ live_extent,
                                      int* __restrict__ pos, const int* __restrict__ out_row, int max_new) {
   pdl_launch_dependents();
   pdl_wait();
@@ -336,8 +352,8 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
   }
   __syncthreads();
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(s_tok) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(b) * d;
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 __global__ void advance_step_kernel(DecodeState* st) {
@@ -348,11 +364,11 @@ __global__ void advance_step_kernel(DecodeState* st) {
 
 // teacher forcing (test hook): overwrite the next decoder input with a given token
 __global__ void force_token_kernel(const long long* __restrict__ toks, const act_t* __restrict__ E,
-                                   act_t* __restrict__ x, int d) {
+                                   res_t* __restrict__ x, int d) {
   const int b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(toks[b]) * d);
-  uint4* dst = reinterpret_cast<uint4*>(x + static_cast<size_t>(b) * d);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+  res_t* dst = x + static_cast<size_t>(b) * d;
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
 }
 
 }  // namespace b200

@@ -227,6 +227,15 @@ DEVINL void store_row_chunk(act_t* dst, const uint32_t (&p)[16], int n0, int N) 
   }
 }
 
+// Store 32 fp32 (128 B) to dst, clipped to N in groups of 4.
+DEVINL void store_row_chunk_f32(float* dst, const float (&v)[32], int n0, int N) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (n0 + g * 4 + 4 <= N) d4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  }
+}
+
 struct NoPre {};
 
 // Drives an unpaired functor over the BN columns of this thread's TMEM row, fetching the
@@ -278,6 +287,56 @@ struct EpiStore {
   }
 };
 
+#if B200T5_F16
+// ---- residual, fp16 build: the stream is fp32 (res_t = float) and torch's type promotion decides the arithmetic
+// (modeling_t5.py T5LayerSelfAttention / T5LayerCrossAttention / T5LayerFF.forward):
+//   attention output projection (fp16 Linear):  C = R + float(fp16(acc))            round_acc = 1
+//     ... while the stream is still fp16, i.e. before the first feed-forward block:  C = fp16(R + fp16(acc))   round_out = 1
+//   feed-forward `wo` (fp32 weight, fp32 output; _keep_in_fp32_modules): C = R + acc   round_acc = 0
+struct EpiResidual {
+  struct Params {
+    res_t* C;
+    const res_t* R;
+    int ld;
+    float* ss = nullptr;  // (fused RMSNorm is a bf16-build experiment)
+    int ss_ld = 0;
+    int round_acc = 1;
+    int round_out = 0;
+  };
+  static constexpr bool kPaired = false;
+  struct ChunkPre {
+    float4 r[8];
+  };
+  static DEVINL void prologue(const Params&, uint8_t*, int, int = 128) {}
+  static DEVINL void chunk_pre(const Params& p, int m, int n0, int N, ChunkPre& pre) {
+    const float4* r4 = reinterpret_cast<const float4*>(p.R + static_cast<size_t>(m) * p.ld + n0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) pre.r[g] = (n0 + g * 4 + 4 <= N) ? r4[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  static DEVINL void chunk(const Params& p, const uint32_t (&acc)[32], int m, int n0, int N, const uint8_t*,
+                           const ChunkPre& pre) {
+    float o[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float rw[4] = {pre.r[g].x, pre.r[g].y, pre.r[g].z, pre.r[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = __uint_as_float(acc[g * 4 + j]);
+        if (p.round_acc) y = act_round(y);
+        float v = rw[j] + y;
+        if (p.round_out) v = act_round(v);
+        o[g * 4 + j] = v;
+      }
+    }
+    store_row_chunk_f32(p.C + static_cast<size_t>(m) * p.ld + n0, o, n0, N);
+  }
+  template <int BN>
+  static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int N, const uint8_t* es,
+                         int part, int parts) {
+    run_chunks_from_tmem<BN, EpiResidual>(p, taddr, m, m_ok, n_tile, N, es, part, parts);
+  }
+};
+#else
 // ---- residual: C = bf16( float(R) + float(bf16(acc)) )   (modeling_t5.py:375,406,149)
 struct EpiResidual {
   struct Params {
@@ -288,6 +347,7 @@ struct EpiResidual {
     // consumer GEMM that applies the following RMSNorm to its A operand (gemm_splitk.cuh, NormA)
     float* ss = nullptr;
     int ss_ld = 0;
+    int round_acc = 1, round_out = 1;  // (fp16 build only; this build always rounds both)
   };
   static constexpr bool kPaired = false;
   struct ChunkPre {
@@ -335,13 +395,16 @@ struct EpiResidual {
   }
 };
 
+#endif
+
 // gelu_new exactly as HF eager evaluates it on bf16 tensors: every elementwise op rounds its
 // result to bf16 (transformers/activations.py:59-66). torch.pow(x, 3.0) on
 // a bf16 tensor is x*x*x in bf16 arithmetic (two roundings, pow_mode 0; verified exhaustively
 // against torch on the GPU); pow_mode 1 keeps the single-rounding variant selectable.
 DEVINL float gelu_new_act_exact(float x, int pow_mode) {
   const float half_x = act_round(0.5f * x);
-  const float x3 = pow_mode == 0 ? act_round(act_round(x * x) * x) : act_round(x * x * x);
+  // (torch.pow on an fp16 tensor computes in fp32 and rounds once: oracle/t5_oracle.py gelu_new)
+  const float x3 = (pow_mode == 0 && !B200T5_F16) ? act_round(act_round(x * x) * x) : act_round(x * x * x);
   const float t1 = act_round(0.044715f * x3);
   const float t2 = act_round(x + t1);
   const float t3 = act_round(0.7978845608028654f * t2);
@@ -393,7 +456,7 @@ DEVINL float gelu_from_lut(float x, const uint16_t* lut, int lo, int hi) {
 //   out = bf16( gelu_new(bf16(gate)) * bf16(up) )          (modeling_t5.py:115-118)
 struct EpiGeglu {
   struct Params {
-    act_t* out;  // [M, F]
+    ffh_t* out;  // [M, F]
     int F;
     GeluLut lut;
   };
@@ -402,6 +465,9 @@ struct EpiGeglu {
   // stage the gelu table (a few KB) with 16-byte loads; `nthreads` epilogue threads take part
   // (named barrier 2 is reserved for them)
   static DEVINL void prologue(const Params& p, uint8_t* epi_smem, int tid, int nthreads = 128) {
+#if B200T5_F16
+    return;  // fp16 build: gelu_new is evaluated directly (the table trick below indexes bf16 bit patterns)
+#endif
     const int nvec = (2 * (p.lut.hi - p.lut.lo) * 2 + 15) / 16;
     const uint4* src = reinterpret_cast<const uint4*>(p.lut.table);
     uint4* dst = reinterpret_cast<uint4*>(epi_smem);
@@ -411,6 +477,17 @@ struct EpiGeglu {
   // g/u: gate and up accumulators of features [f0, f0+32)
   static DEVINL void chunk2(const Params& p, const uint32_t (&g)[32], const uint32_t (&u)[32], int m, int f0,
                             const uint8_t* epi_smem) {
+#if B200T5_F16
+    // out = float(fp16(gelu_new(fp16 gate) * fp16 up)): the fp16 product cast up for the fp32 `wo` GEMM
+    float o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float x = act_round(__uint_as_float(g[i]));
+      const float lin = act_round(__uint_as_float(u[i]));
+      o[i] = act_round(gelu_new_act_exact(x, 1) * lin);
+    }
+    store_row_chunk_f32(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
+#else
     const uint16_t* lut = reinterpret_cast<const uint16_t*>(epi_smem);
     const int lo = p.lut.lo, n = p.lut.hi - p.lut.lo;
     uint32_t o[16];
@@ -426,6 +503,7 @@ struct EpiGeglu {
       o[i] = pack_act2(r[0], r[1]);
     }
     store_row_chunk(p.out + static_cast<size_t>(m) * p.F + f0, o, f0, p.F);
+#endif
   }
   template <int BN>
   static DEVINL void run(const Params& p, uint32_t taddr, int m, bool m_ok, int n_tile, int /*N*/, const uint8_t* epi_smem,

@@ -50,6 +50,14 @@ DEVINL void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, 
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+DEVINL void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // All MMAs issued so far by this thread: arrive on the barrier at this offset in BOTH CTAs of the pair.
 DEVINL void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -68,11 +76,16 @@ DEVINL void tmem_dealloc_pair_512(uint32_t taddr) {
 }
 
 // tmA: box 64 x 128 rows of A; tmB: box 64 x 128 rows of W. grid = 2 * pairs (persistent), cluster (2,1,1).
-template <class Epi>
+// kTf32 (fp16 build, the fp32-weight `wo` product): both operands are fp32 in memory and consumed as tf32, a
+// k-block is 32 elements (the same 128-byte rows) and K counts the columns of W' = [W_hi | W_lo], the two
+// tf32 pieces of the fp32 weight side by side; A has only a_kblocks k-blocks and is walked twice (kb % a_kblocks),
+// so the accumulator receives A . W_hi^T + A . W_lo^T.
+template <class Epi, bool kTf32 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairEpi<Epi>::kThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                         int K, typename Epi::Params ep) {
+                         int K, typename Epi::Params ep, int a_kblocks) {
   constexpr int BN = k2ctaBN;
+  constexpr int kbk = kTf32 ? kBK / 2 : kBK;  // elements per k-block (128 bytes)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2ctaStages * k2ctaStageBytes);
@@ -91,7 +104,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int tiles_m = (M + 2 * kBM - 1) / (2 * kBM);
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
-  const int kblocks = (K + kBK - 1) / kBK;
+  const int kblocks = (K + kbk - 1) / kbk;
+  if (a_kblocks <= 0) a_kblocks = kblocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -131,8 +145,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sA = smem + stage * k2ctaStageBytes;
           if (leader) mbar_arrive_expect_tx(&full[stage], 2u * k2ctaStageBytes);
-          tma_load_2d_pair(sA, &tmA, &full[stage], kb * kBK, m0);
-          tma_load_2d_pair(sA + kBM * kBK * 2, &tmB, &full[stage], kb * kBK, n0);
+          tma_load_2d_pair(sA, &tmA, &full[stage], (kb % a_kblocks) * kbk, m0);
+          tma_load_2d_pair(sA + kBM * kBK * 2, &tmB, &full[stage], kb * kbk, n0);
           if (++stage == k2ctaStages) {
             stage = 0;
             phase ^= 1u;
@@ -143,7 +157,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_act(2 * kBM, BN, 0, 0);
+      constexpr uint32_t idesc = kTf32 ? make_idesc_tf32(2 * kBM, BN) : make_idesc_act(2 * kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -159,9 +173,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
           const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + kBM * kBK * 2);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {  // 32 bytes of K per instruction in either kind
+            if constexpr (kTf32)
+              umma_tf32_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit_pair(&empty[stage]);
           if (++stage == k2ctaStages) {
             stage = 0;
@@ -205,18 +224,19 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <class Epi>
+template <class Epi, bool kTf32 = false>
 cudaError_t prepare_gemm_2cta() {
-  return cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2ctaSmemBytes);
+  return cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<Epi, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2ctaSmemBytes);
 }
 
-template <class Epi>
+// a_kblocks: see kTf32 above (0 = A spans all of K)
+template <class Epi, bool kTf32 = false>
 cudaError_t launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
-                             const typename Epi::Params& ep, int num_sms, cudaStream_t stream) {
+                             const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int a_kblocks = 0) {
   const int tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * ((N + k2ctaBN - 1) / k2ctaBN);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm_bf16_tn_2cta_kernel<Epi><<<dim3(2 * pairs), dim3(PairEpi<Epi>::kThreads), k2ctaSmemBytes, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_bf16_tn_2cta_kernel<Epi, kTf32><<<dim3(2 * pairs), dim3(PairEpi<Epi>::kThreads), k2ctaSmemBytes, stream>>>(tmA, tmB, M, N, K, ep, a_kblocks);
   return cudaGetLastError();
 }
 

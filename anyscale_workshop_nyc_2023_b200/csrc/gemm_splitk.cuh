@@ -82,11 +82,14 @@ struct NormA {
 };
 
 // grid = (S, tiles_n, tiles_m), cluster = (S, 1, 1); S in {1,2,4,8} divides 128.
-template <int BN, class Epi, bool kNormA = false>
+// kTf32 / a_kblocks: as in gemm_2cta.cuh (fp32 operands consumed as tf32, W' = [W_hi | W_lo], A walked twice).
+template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
 __global__ void __launch_bounds__(kSkThreads, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                   int K, typename Epi::Params ep, const NormA na) {
+                   int K, typename Epi::Params ep, const NormA na, int a_kblocks) {
   using Cfg = SkCfg<BN>;
+  constexpr int kbk = kTf32 ? kBK / 2 : kBK;  // elements per k-block (128 bytes)
+  static_assert(!(kNormA && kTf32), "the fused RMSNorm transforms 2-byte A tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -103,7 +106,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int S = static_cast<int>(cluster_nctarank());
   const int rank = static_cast<int>(cluster_ctarank());
   const int n_tile = blockIdx.y, m_tile = blockIdx.z;
-  const int kblocks = (K + kBK - 1) / kBK;
+  const int kblocks = (K + kbk - 1) / kbk;
+  if (a_kblocks <= 0) a_kblocks = kblocks;
   const int kb_per = (kblocks + S - 1) / S;
   const int kb0 = rank * kb_per;
   const int kb1 = (kb0 + kb_per) < kblocks ? (kb0 + kb_per) : kblocks;
@@ -142,18 +146,18 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int i = 0; i < first; ++i) {
         uint8_t* sA = smem + i * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[i], Cfg::kStageBytes);
-        tma_load_2d(sA + Cfg::kABytes, &tmB, &full[i], (kb0 + i) * kBK, n0t);
+        tma_load_2d(sA + Cfg::kABytes, &tmB, &full[i], (kb0 + i) * kbk, n0t);
       }
       pdl_wait();
-      for (int i = 0; i < first; ++i) tma_load_2d(smem + i * Cfg::kStageBytes, &tmA, &full[i], (kb0 + i) * kBK, m0);
+      for (int i = 0; i < first; ++i) tma_load_2d(smem + i * Cfg::kStageBytes, &tmA, &full[i], ((kb0 + i) % a_kblocks) * kbk, m0);
       int stage = first == Cfg::kStages ? 0 : first;
       uint32_t phase = first == Cfg::kStages ? 1u : 0u;
       for (int i = first; i < nkb; ++i) {
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-        tma_load_2d(sA, &tmA, &full[stage], (kb0 + i) * kBK, m0);
-        tma_load_2d(sA + Cfg::kABytes, &tmB, &full[stage], (kb0 + i) * kBK, n0t);
+        tma_load_2d(sA, &tmA, &full[stage], ((kb0 + i) % a_kblocks) * kbk, m0);
+        tma_load_2d(sA + Cfg::kABytes, &tmB, &full[stage], (kb0 + i) * kbk, n0t);
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1u;
@@ -167,7 +171,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_act(kBM, BN, 0, 0);
+      constexpr uint32_t idesc = kTf32 ? make_idesc_tf32(kBM, BN) : make_idesc_act(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
@@ -177,9 +181,14 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
         const uint64_t b_desc = make_desc_sw128_kmajor(a_addr + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)
-          umma_f16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
-                       (i | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBK / 16; ++k) {  // 32 bytes of K per instruction in either kind
+          if constexpr (kTf32)
+            umma_tf32_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                         (i | k) != 0 ? 1u : 0u);
+          else
+            umma_f16_ss(tmem_base, a_desc + static_cast<uint64_t>(2 * k), b_desc + static_cast<uint64_t>(2 * k), idesc,
+                        (i | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&empty[stage]);
         if (++stage == Cfg::kStages) {
           stage = 0;
@@ -330,17 +339,17 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-template <int BN, class Epi, bool kNormA = false>
+template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
 cudaError_t prepare_gemm_splitk() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SkCfg<BN>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 // Largest split in {8,4,2,1} not above `want` that leaves every rank at least one k-block.
-inline int splitk_factor(int K, int want) {
-  const int kblocks = (K + kBK - 1) / kBK;
+inline int splitk_factor(int K, int want, int kbk = kBK) {
+  const int kblocks = (K + kbk - 1) / kbk;
   for (int s = want; s > 1; s >>= 1) {
     const int per = (kblocks + s - 1) / s;
     if ((s - 1) * per < kblocks) return s;
@@ -348,9 +357,10 @@ inline int splitk_factor(int K, int want) {
   return 1;
 }
 
-template <int BN, class Epi, bool kNormA = false>
+template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
 cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int split,
-                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl, const NormA& norm = NormA{}) {
+                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl, const NormA& norm = NormA{},
+                               int a_kblocks = 0) {
   using Cfg = SkCfg<BN>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(split, (N + BN - 1) / BN, (M + kBM - 1) / kBM);
@@ -376,7 +386,7 @@ cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, i
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi, kNormA>, tmA, tmB, M, N, K, ep, norm);
+  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, tmA, tmB, M, N, K, ep, norm, a_kblocks);
 }
 
 }  // namespace b200

@@ -33,6 +33,10 @@ _IGNORED_WEIGHTS = ("decoder.block.0.layer.1.EncDecAttention.relative_attention_
 _ALIASES = ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight")
 
 
+def _chk(model, rc: int, handle=None) -> None:
+    _lib.check(rc, handle, model._lib)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -43,10 +47,15 @@ class B200T5ForConditionalGeneration:
 
     main_input_name = "input_ids"
 
-    def __init__(self, config: Dict[str, Any], device: torch.device):
+    def __init__(self, config: Dict[str, Any], device: torch.device, compute_dtype: torch.dtype = torch.bfloat16):
         if device.type != "cuda":
             raise RuntimeError("B200T5ForConditionalGeneration runs on a B200 only; there is no CPU fallback")
-        self._lib = _lib.load()
+        if compute_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError(f"compute dtype must be bfloat16 or float16, got {compute_dtype}")
+        # one shared library per numerics contract: bf16 everywhere, or the notebook's literal torch_dtype=float16
+        # (NB:882) with transformers' fp32 `wo` / fp32 residual stream
+        self._dtype = compute_dtype
+        self._lib = _lib.load("fp16" if compute_dtype == torch.float16 else "bf16")
         self._device = device
         self.config = SimpleNamespace(**config)
         self.generation_config = SimpleNamespace(
@@ -72,7 +81,7 @@ class B200T5ForConditionalGeneration:
         )
         h = C.c_void_p()
         index = device.index if device.index is not None else torch.cuda.current_device()
-        _lib.check(self._lib.b200t5_create(C.byref(cfg), index, C.byref(h)))
+        _chk(self, self._lib.b200t5_create(C.byref(cfg), index, C.byref(h)))
         self._h = h
         self._index = index
         self.last_lengths: Optional[torch.Tensor] = None
@@ -85,18 +94,21 @@ class B200T5ForConditionalGeneration:
                         dtype=None, device=None, **kwargs) -> "B200T5ForConditionalGeneration":
         """Load a Hugging Face T5 directory (config.json + model.safetensors | pytorch_model.bin).
 
-        `device_map="auto"` / `torch_dtype=` are accepted as the notebook passes them
-        (NB:881-882). Compute is bf16; a request for float16/float32 is honoured as "load and
-        round the weights to bf16" with a warning (the fp16 + fp32-`wo` mode is SURVEY 8f rank 1).
+        `device_map="auto"` / `torch_dtype=` are accepted as the notebook passes them (NB:881-882).
+        torch_dtype=bfloat16 (default) and torch_dtype=float16 select the two numerics contracts the library
+        implements; float16 is transformers' mode for T5: fp16 weights and activations, `wo` kept in fp32, fp32
+        residual stream from the first feed-forward block on. float32 is honoured as "load and round to
+        bfloat16" with a warning.
         """
         path = Path(pretrained_model_name_or_path)
         if not (path / "config.json").exists():
             raise FileNotFoundError(f"{path} is not a Hugging Face checkpoint directory (no config.json); "
                                     "hub downloads are not available offline")
         want = dtype if dtype is not None else torch_dtype
-        if want not in (None, torch.bfloat16, "bfloat16", "auto"):
-            warnings.warn(f"B200T5ForConditionalGeneration computes in bfloat16; requested {want} weights are "
-                          "rounded to bfloat16 on load", stacklevel=2)
+        compute = torch.float16 if want in (torch.float16, "float16", "half") else torch.bfloat16
+        if want not in (None, torch.bfloat16, "bfloat16", "auto", torch.float16, "float16", "half"):
+            warnings.warn(f"B200T5ForConditionalGeneration computes in bfloat16 or float16; requested {want} weights "
+                          "are rounded to bfloat16 on load", stacklevel=2)
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: B200T5ForConditionalGeneration has no CPU fallback")
         if device is None:
@@ -110,7 +122,7 @@ class B200T5ForConditionalGeneration:
             device = torch.device("cuda", torch.cuda.current_device())
         device = torch.device(device)
         config = json.loads((path / "config.json").read_text())
-        model = cls(config, device)
+        model = cls(config, device, compute)
         model._load_weights(path)
         return model
 
@@ -141,10 +153,10 @@ class B200T5ForConditionalGeneration:
                     t = t.float()
                 dev = t.to(self._device).contiguous()
                 shape = (C.c_int64 * dev.dim())(*dev.shape)
-                _lib.check(self._lib.b200t5_set_weight(self._h, name.encode(), _ptr(dev), codes[dev.dtype], shape,
+                _chk(self, self._lib.b200t5_set_weight(self._h, name.encode(), _ptr(dev), codes[dev.dtype], shape,
                                                        dev.dim()), self._h)
                 del dev
-            _lib.check(self._lib.b200t5_finalize(self._h), self._h)
+            _chk(self, self._lib.b200t5_finalize(self._h), self._h)
         return SimpleNamespace(missing_keys=[], unexpected_keys=[])
 
     # ------------------------------------------------------------------ nn.Module-ish surface
@@ -154,7 +166,7 @@ class B200T5ForConditionalGeneration:
 
     @property
     def dtype(self) -> torch.dtype:
-        return torch.bfloat16
+        return self._dtype
 
     def eval(self):
         return self
@@ -239,7 +251,7 @@ class B200T5ForConditionalGeneration:
             out = torch.empty((B, T + 1), dtype=torch.long, device=self._device)
             lens = torch.empty((B,), dtype=torch.int32, device=self._device)
             stream = torch.cuda.current_stream(self._device)
-            _lib.check(self._lib.b200t5_generate(self._h, _ptr(ids), _ptr(mask), B, S, C.byref(gp), _ptr(out),
+            _chk(self, self._lib.b200t5_generate(self._h, _ptr(ids), _ptr(mask), B, S, C.byref(gp), _ptr(out),
                                                  _ptr(lens), C.c_void_p(stream.cuda_stream)), self._h)
             self.last_lengths = lens
             steps = int(lens.max().item())  # synchronises; HF returns exactly the steps it ran
@@ -256,7 +268,7 @@ class B200T5ForConditionalGeneration:
         mask = None if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
         out = np.empty((B, gp.max_new_tokens + 1), dtype=np.int64)
         lens = np.empty((B,), dtype=np.int32)
-        _lib.check(self._lib.b200t5_generate_host(
+        _chk(self, self._lib.b200t5_generate_host(
             self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), B, S,
             C.byref(gp), out.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)), self._h)
         return out[:, : int(lens.max()) + 1], lens
@@ -282,7 +294,7 @@ class B200T5ForConditionalGeneration:
             raise ValueError("attention_mask shape must match input_ids")
         out = np.empty((N, gp.max_new_tokens + 1), dtype=np.int64)
         lens = np.empty((N,), dtype=np.int32)
-        _lib.check(self._lib.b200t5_generate_stream(
+        _chk(self, self._lib.b200t5_generate_stream(
             self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), N, S,
             C.byref(gp), int(pool or self.pool_size), int(admit_min), out.ctypes.data_as(C.c_void_p),
             lens.ctypes.data_as(C.c_void_p)), self._h)
@@ -291,7 +303,7 @@ class B200T5ForConditionalGeneration:
 
     def stats(self) -> Dict[str, float]:
         s = _lib.Stats()
-        _lib.check(self._lib.b200t5_get_stats(self._h, C.byref(s)), self._h)
+        _chk(self, self._lib.b200t5_get_stats(self._h, C.byref(s)), self._h)
         return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
 
     def bench_cross_attention(self, reps: int = 5) -> Dict[str, float]:
@@ -299,7 +311,7 @@ class B200T5ForConditionalGeneration:
         ms, nbytes = C.c_float(), C.c_double()
         with torch.cuda.device(self._index):
             stream = torch.cuda.current_stream(self._device)
-            _lib.check(self._lib.b200t5_bench_cross_attn(self._h, reps, C.byref(ms), C.byref(nbytes),
+            _chk(self, self._lib.b200t5_bench_cross_attn(self._h, reps, C.byref(ms), C.byref(nbytes),
                                                          C.c_void_p(stream.cuda_stream)), self._h)
         return {"ms_per_launch": ms.value, "bytes_per_launch": nbytes.value}
 
@@ -309,10 +321,10 @@ class B200T5ForConditionalGeneration:
         ids = torch.as_tensor(input_ids).to(self._device, torch.long).contiguous()
         mask = None if attention_mask is None else torch.as_tensor(attention_mask).to(self._device, torch.long).contiguous()
         B, S = ids.shape
-        out = torch.empty((B, S, self.config.d_model), dtype=torch.bfloat16, device=self._device)
+        out = torch.empty((B, S, self.config.d_model), dtype=self._dtype, device=self._device)
         with torch.cuda.device(self._index):
             stream = torch.cuda.current_stream(self._device)
-            _lib.check(self._lib.b200t5_encode(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(out),
+            _chk(self, self._lib.b200t5_encode(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(out),
                                                C.c_void_p(stream.cuda_stream)), self._h)
             torch.cuda.synchronize(self._device)
         return out
@@ -327,6 +339,6 @@ class B200T5ForConditionalGeneration:
         out = torch.empty((B, T, self.config.vocab_size), dtype=torch.float32, device=self._device)
         with torch.cuda.device(self._index):
             stream = torch.cuda.current_stream(self._device)
-            _lib.check(self._lib.b200t5_decode_logits(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(dec), T, _ptr(out),
+            _chk(self, self._lib.b200t5_decode_logits(self._h, _ptr(ids), _ptr(mask), B, S, _ptr(dec), T, _ptr(out),
                                                       C.c_void_p(stream.cuda_stream)), self._h)
         return out

@@ -384,3 +384,96 @@ def test_finished_rows_are_retired_in_static_batches(models):
         solo, sl = model.generate_host(ids[b:b + 1], mask[b:b + 1], max_new_tokens=24)
         assert int(sl[0]) == int(lens[b])
         assert (out[b, : solo.shape[1]] == solo[0]).all() and (out[b, solo.shape[1]:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16 contract (libb200t5_f16.so): the notebook's literal torch_dtype=torch.float16 (NB:882) with transformers'
+# fp32 `wo` and fp32 residual stream. Anchors: HF fp16 goldens (tests/golden/*_fp16.npz) and the oracle's fp16
+# mode, which the CPU suite pins to those goldens. fp16 has 3 more mantissa bits than bf16, so the logit
+# tolerances are tighter than the bf16 ones (ulp 0.0039-0.0078 at |logit| in [4, 16)).
+TAU_FP16 = 0.03
+LOGIT_ATOL_FP16 = 0.08
+LOGIT_MEAN_FP16 = 0.008
+
+
+@pytest.fixture(scope="module")
+def models_fp16(tmp_path_factory):
+    from anyscale_workshop_nyc_2023_b200.modeling import B200T5ForConditionalGeneration
+
+    cache = {}
+
+    def get(spec_name, seed):
+        key = (spec_name, seed)
+        if key not in cache:
+            d = tmp_path_factory.mktemp(f"ckpt16_{spec_name}_{seed}")
+            save_checkpoint(d, SPECS[spec_name], seed=seed)
+            cache[key] = B200T5ForConditionalGeneration.from_pretrained(d, device_map="auto", torch_dtype=torch.float16)
+        return cache[key]
+
+    return get
+
+
+def oracle_fp16(spec_name, seed):
+    from oracle.t5_oracle import T5Oracle
+
+    return T5Oracle(make_state_dict(SPECS[spec_name], seed), SPECS[spec_name], emulate="fp16")
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp16_golden_generate(models_fp16, case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}_fp16.npz")
+    model = models_fp16(spec_name, seed)
+    assert model.dtype == torch.float16
+    out = model.generate(input_ids=torch.from_numpy(g["ids"]), attention_mask=torch.from_numpy(g["mask"]),
+                         labels=torch.from_numpy(g["ids"]), max_new_tokens=T).cpu().numpy()
+    orc = oracle_fp16(spec_name, seed)
+    otoks, margins = orc.generate(g["ids"], g["mask"], max_new_tokens=T, return_margins=True)
+    gated_o, full_o = gated_prefix_match(out, otoks, margins, tau=TAU_FP16)
+    gated_h, full_h = gated_prefix_match(out, g["tokens_fp16"], margins, tau=TAU_FP16)
+    print(f"{case} fp16: vs oracle gated={gated_o:.2f} full={full_o:.2f} | vs HF-fp16 golden gated={gated_h:.2f} full={full_h:.2f}")
+    assert gated_o == 1.0 and gated_h == 1.0
+    forced = model.generate(input_ids=torch.from_numpy(g["ids"]), attention_mask=torch.from_numpy(g["mask"]),
+                            max_new_tokens=T, min_new_tokens=T).cpu().numpy()
+    assert forced.shape == (g["ids"].shape[0], T + 1)
+    ftoks, fm = orc.generate(g["ids"], g["mask"], max_new_tokens=T, min_new_tokens=T, return_margins=True)
+    gated_f, full_f = gated_prefix_match(forced, ftoks, fm, tau=TAU_FP16)
+    gated_fh, full_fh = gated_prefix_match(forced, g["forced_fp16"], fm, tau=TAU_FP16)
+    print(f"{case} fp16 forced: vs oracle gated={gated_f:.2f} full={full_f:.2f} | vs golden gated={gated_fh:.2f} full={full_fh:.2f}")
+    assert gated_f == 1.0 and gated_fh == 1.0
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp16_golden_logits_and_encoder(models_fp16, case):
+    spec_name, seed, T = CASES[case]
+    g = np.load(GOLD / f"{case}_fp16.npz")
+    model = models_fp16(spec_name, seed)
+    valid = g["mask"].astype(bool)
+    enc_t = model.encode(g["ids"], g["mask"])
+    assert enc_t.dtype == torch.float16
+    enc = enc_t.float().cpu().numpy()
+    e_err = np.abs(enc - g["enc_fp16"])[valid]
+    print(f"{case} fp16: encoder max err {e_err.max():.4f} mean {e_err.mean():.5f} (scale {np.abs(g['enc_fp16'])[valid].max():.2f})")
+    assert e_err.max() <= 0.03 and e_err.mean() <= 0.002
+    dec_in = g["tokens_fp16"][:, :-1]
+    logits = model.decode_logits(g["ids"], g["mask"], dec_in).cpu().numpy()
+    err = np.abs(logits - g["logits_fp16"])
+    print(f"{case} fp16: logits max err {err.max():.4f} mean {err.mean():.5f} (scale {np.abs(g['logits_fp16']).max():.2f})")
+    assert err.max() <= LOGIT_ATOL_FP16 and err.mean() <= LOGIT_MEAN_FP16
+    assert (logits == logits.astype(np.float16).astype(np.float32)).all()  # fp16-rounded outputs
+
+
+def test_fp16_and_bf16_models_coexist_and_pool(models, models_fp16):
+    """Both libraries loaded in one process (separate handles); the slot pool in the fp16 build equals its static
+    batches bit for bit, like the bf16 one."""
+    spec = SPECS["tiny"]
+    m16 = models_fp16("tiny", 1)
+    mb, _ = models("tiny", 1)
+    ids, mask = synthetic_token_batch(40, 20, spec.vocab_size, seed=31, lengths="uniform")
+    kw = dict(max_new_tokens=12)
+    ref, ref_len = _static_rows(m16, ids, mask, 16, **kw)
+    out, lens = m16.generate_stream(ids, mask, pool=16, **kw)
+    assert (lens == ref_len).all() and (out == ref[:, : out.shape[1]]).all()
+    ob, _ = mb.generate_host(ids[:16], mask[:16], **kw)
+    o16, _ = m16.generate_host(ids[:16], mask[:16], **kw)
+    assert ob.shape[0] == o16.shape[0] == 16  # different contracts, both alive; tokens may legitimately differ
