@@ -1598,7 +1598,8 @@ static void fill_stats_model(b200t5_ctx* h, int steps) {
   const Cfg& c = h->c;
   const Plan& p = *h->plan;
   // weights once per step + cross-KV + self-KV read/write, bf16.
-  const double wstep = static_cast<double>(c.Ld) * (6.0 * c.d * c.I + 3.0 * c.d * c.F) + static_cast<double>(c.V) * c.d;
+  // (element count; the fp16 build's `wo` weights are fp32: counted twice)
+  const double wstep = static_cast<double>(c.Ld) * (6.0 * c.d * c.I + (B200T5_F16 ? 4.0 : 3.0) * c.d * c.F) + static_cast<double>(c.V) * c.d;
   std::vector<int> ext(p.B, p.S);
   if (cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
     ext.assign(p.B, p.S);  // statistics only: fall back to the padded length

@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--lengths", default="full", choices=["full", "alpaca", "uniform"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="numerics contract: bf16 (headline) or the notebook's literal torch_dtype=float16 (fp32 wo, fp32 residual stream)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="prompts in the CPU-baseline sample")
     ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the in-run CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,7 +225,7 @@ def main_b200(a):
     ckpt = checkpoint_dir(a.model, seed=0)
 
     log(f"rank {rank}/{world}: checkpoint at {ckpt}; loading the model")
-    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.bfloat16)
+    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.float16 if a.dtype == "fp16" else torch.bfloat16)
     from anyscale_workshop_nyc_2023_b200.rayshim.train import _ScoringWorker
 
     worker = _ScoringWorker(bp._checkpoint, bp._predictor_cls, {**bp._predictor_kwargs, "use_gpu": True}, False)
@@ -317,7 +319,7 @@ def main_b200(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": world * B, "prompts_per_rank_step": B,
                        "parallelism": f"dataset sharded over {world} replica(s), no collective",
                        "l2": f"inputs exceed L2 (cross-KV arena {kv_gb:.1f} GB and {w_gb:.2f} GB of decoder weights "

@@ -477,3 +477,37 @@ def test_fp16_and_bf16_models_coexist_and_pool(models, models_fp16):
     ob, _ = mb.generate_host(ids[:16], mask[:16], **kw)
     o16, _ = m16.generate_host(ids[:16], mask[:16], **kw)
     assert ob.shape[0] == o16.shape[0] == 16  # different contracts, both alive; tokens may legitimately differ
+
+
+def test_fp16_flan_t5_small_vs_hf_gpu(models_fp16, tmp_path):
+    """Real FLAN-T5-small architecture in the notebook's literal dtype; anchor = HF eager fp16 (fp32 `wo`) on this GPU.
+    HF's fp32 `wo` Linear runs through cuBLAS fp32 there; ours through two tf32 passes over W_hi + W_lo."""
+    pytest.importorskip("transformers")
+    from oracle.hf_anchor import hf_generate, hf_teacher_forced_logits, load_hf_model
+
+    spec = SPECS["flan-t5-small"]
+    model = models_fp16("flan-t5-small", 3)
+    ckpt = tmp_path / "ckpt"
+    save_checkpoint(ckpt, spec, seed=3)
+    B, S, T = 16, 96, 24
+    ids, mask = synthetic_token_batch(B, S, spec.vocab_size, seed=21, lengths="uniform")
+    hf = load_hf_model(ckpt, dtype=torch.float16, device="cuda")
+    assert hf.encoder.block[0].layer[1].DenseReluDense.wo.weight.dtype == torch.float32
+    ref = hf_generate(hf, ids, mask, T, min_new_tokens=T)
+    out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=T, min_new_tokens=T).cpu().numpy()
+    assert out.shape == ref.shape
+    lg = hf_teacher_forced_logits(hf, ids, mask, ref[:, :-1])
+    lg[:, :, spec.eos_token_id] = -np.inf
+    top2 = np.partition(lg, -2, axis=-1)[:, :, -2:]
+    margins = top2[:, :, 1] - top2[:, :, 0]
+    gated, full = gated_prefix_match(out, ref, margins, tau=TAU_FP16)
+    print(f"flan-t5-small fp16 vs HF-fp16-GPU: gated rows={gated:.2f} ungated rows={full:.2f} token agreement={(out == ref).mean():.3f}")
+    ours_lg = model.decode_logits(ids, mask, ref[:, :-1]).cpu().numpy()
+    gpu_lg = hf_teacher_forced_logits(hf, ids, mask, ref[:, :-1])
+    cpu_lg = hf_teacher_forced_logits(load_hf_model(ckpt, dtype=torch.float16, device="cpu"), ids, mask, ref[:, :-1])
+    err = np.abs(ours_lg - gpu_lg)
+    floor = np.abs(gpu_lg - cpu_lg)
+    print(f"flan-t5-small fp16 teacher-forced logits: ours vs HF-fp16-GPU max {err.max():.4f} mean {err.mean():.5f} | "
+          f"noise floor HF-fp16-GPU vs HF-fp16-CPU max {floor.max():.4f} mean {floor.mean():.5f}")
+    assert gated == 1.0
+    assert err.mean() <= 1.0 * floor.mean() and err.max() <= 2.0 * floor.max()
