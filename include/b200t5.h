@@ -12,6 +12,15 @@
  * transformers==4.27.2 (requirements.txt:168): T5ForConditionalGeneration + greedy search.
  * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
  *
+ * Two builds export this same ABI (csrc/Makefile), one per numerics contract of the dependency:
+ *   libb200t5.so      torch_dtype=bfloat16: every eager op rounds to bf16
+ *   libb200t5_f16.so  torch_dtype=float16, the notebook's literal setting (Text_generation_with_FLAN_T5.ipynb,
+ *                     BatchPredictor.from_checkpoint(..., torch_dtype=torch.float16)): fp16 roundings, the
+ *                     feed-forward `wo` kept as an fp32 weight with an fp32 output (transformers'
+ *                     _keep_in_fp32_modules = ["wo"]) and therefore an fp32 residual stream (Appendix A.7).
+ * b200t5_set_weight converts whatever dtype it is given to the build's own types; b200t5_encode returns the
+ * encoder output in the build's 2-byte type; the single-kernel test hooks exist in the bf16 build only.
+ *
  * Conventions
  *   - every function returns 0 on success, a negative B200T5_E* code otherwise; the message
  *     is available from b200t5_last_error(handle) (or b200t5_last_global_error() when no

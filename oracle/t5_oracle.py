@@ -37,8 +37,8 @@ Three numerics modes:
                       casts its input up), so the residual stream is fp32 from the first feed-forward block
                       on (type promotion in T5LayerFF / T5LayerSelfAttention / T5LayerCrossAttention) and
                       T5LayerNorm rounds to fp16 only on its way out. The additive mask is finfo(fp16).min, and
-                      fp16(score + mask) overflows to -inf exactly as in torch. No CUDA path implements this
-                      mode yet; the mode and its goldens are the oracle for that work.
+                      fp16(score + mask) overflows to -inf exactly as in torch. The contract of
+                      libb200t5_f16.so.
 """
 from __future__ import annotations
 

@@ -18,20 +18,24 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(b200t5_[a-z0-9_]+)\s*\(", text)))
 
 
-def test_every_declared_symbol_is_exported_and_bound():
-    lib = _lib.load()
+@pytest.mark.parametrize("flavour", ["bf16", "fp16"])
+def test_every_declared_symbol_is_exported_and_bound(flavour):
+    """Both builds of the library (bf16 contract, fp16 contract) export the whole C ABI."""
+    lib = _lib.load(flavour)
     names = declared_symbols()
     assert len(names) >= 18
-    exported = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATHS[flavour])], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", exported), f"{n} not exported"
         assert n in _lib.SIGNATURES, f"{n} declared in the header but not bound in _lib.py"
         getattr(lib, n)
     assert sorted(_lib.SIGNATURES) == names
+    assert ("fp16" in lib.b200t5_version().decode()) == (flavour == "fp16")
 
 
-def test_library_is_sm100a_tcgen05():
-    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+@pytest.mark.parametrize("flavour", ["bf16", "fp16"])
+def test_library_is_sm100a_tcgen05(flavour):
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATHS[flavour])], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100" in sass.upper()
     for needle in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
         assert needle in sass

@@ -46,7 +46,7 @@ def test_bf16_emulation_tracks_hf_bf16(case):
 @pytest.mark.parametrize("case", list(CASES))
 def test_fp16_mode_tracks_hf_fp16_with_fp32_wo(case):
     """The notebook's literal torch_dtype=float16 (NB:882): fp16 roundings, `wo` kept in fp32, fp32 residual stream
-    after the first feed-forward block. Oracle for SURVEY 8f row 1 (no CUDA path yet). The residual stream being
+    after the first feed-forward block: the contract of libb200t5_f16.so. The residual stream being
     fp32, accumulation order perturbs it at the 1e-4 level and about one fp16 rounding in five flips downstream:
     tokens are exact on these fixtures, logits agree within ~4 fp16 ulps (0.0039 at |logit| in [4, 8))."""
     spec_name, seed, T = CASES[case]
