@@ -14,7 +14,8 @@ from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir  # noqa: E40
 model_name = os.environ.get("TRACE_MODEL", "flan-t5-base")
 B, S = int(os.environ.get("TRACE_B", 256)), int(os.environ.get("TRACE_S", 512))
 spec = SPECS[model_name]
-model = B200T5ForConditionalGeneration.from_pretrained(checkpoint_dir(model_name, 0))
+dtype = torch.float16 if os.environ.get("TRACE_DTYPE", "bf16") == "fp16" else torch.bfloat16
+model = B200T5ForConditionalGeneration.from_pretrained(checkpoint_dir(model_name, 0), torch_dtype=dtype)
 ids, mask = synthetic_token_batch(B, S, spec.vocab_size, seed=1, lengths="full")
 for _ in range(int(os.environ.get("TRACE_REPS", 2))):
     out = model.encode(ids, mask)
