@@ -2114,6 +2114,44 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
 #endif
 }
 
+// fp16 build only: the fp32-weight feed-forward output projection, R += A . W^T, through the tf32 two-pass product
+// (A [M,F] fp32 holding fp16 values, W [N,F] fp32, R [M,N] fp32 in/out). kernel 0: CTA-pair encoder kernel,
+// 1: cluster split-K decode kernel (bn in {64,128}, split in {1,2,4,8}).
+extern "C" int b200t5_test_ffo(int device, const void* A, const void* W, void* R, int M, int N, int F, int kernel, int bn,
+                               int split, void* stream) {
+#if !B200T5_F16
+  return fail(nullptr, B200T5_EINVAL, "b200t5_test_ffo exists in the fp16 build only (libb200t5_f16.so)");
+#else
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  if (F % 4 || N % 4) return fail(nullptr, B200T5_EINVAL, "F and N must be multiples of 4");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Fp = (F + 31) / 32 * 32;
+  DevBuf wsplit;
+  if (wsplit.alloc(static_cast<size_t>(N) * 2 * Fp * 4) != cudaSuccess) return fail(nullptr, B200T5_ENOMEM, "alloc failed");
+  const size_t n = static_cast<size_t>(N) * Fp;
+  split_tf32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(W), wsplit.as<float>(), N, F, Fp);
+  CUtensorMap ta, tb;
+  const int box_b = kernel == 0 ? 128 : bn;
+  if (!make_tmap(&ta, A, M, F, 128, true) || !make_tmap(&tb, wsplit.p, N, 2 * Fp, box_b, true))
+    return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+  EpiResidual::Params ep{static_cast<float*>(R), static_cast<const float*>(R), N};
+  ep.round_acc = 0;
+  ep.round_out = 0;
+  cudaError_t e;
+  if (kernel == 0) {
+    e = launch_gemm_2cta<EpiResidual, true>(ta, tb, M, N, 2 * Fp, ep, sms, s, Fp / 32);
+  } else {
+    const int sp = splitk_factor(2 * Fp, split, kBK / 2);
+    e = bn == 128 ? launch_gemm_splitk<128, EpiResidual, false, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, NormA{}, Fp / 32)
+                  : launch_gemm_splitk<64, EpiResidual, false, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, NormA{}, Fp / 32);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_ffo: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+#endif
+}
+
 extern "C" int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream) {
 #if B200T5_F16
   return fail(nullptr, B200T5_EINVAL, "the single-kernel test hooks exist in the bf16 build only (libb200t5.so)");

@@ -166,6 +166,12 @@ int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, i
  * with the T5 RMSNorm of A fused in: `aux` = float ss[M][ceil(K/32)] followed by the bf16 norm weight [K]. */
 int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int split,
                             int mode, int pow_mode, void* aux, int Tmax, int step, void* stream);
+/* fp16 build (libb200t5_f16.so) only: the fp32-weight feed-forward output projection (transformers keeps T5's `wo`
+ * in fp32 under torch_dtype=float16), R += A . W^T computed as two tf32 tensor-core passes over W = W_hi + W_lo.
+ * A [M,F] fp32 (fp16-representable values), W [N,F] fp32, R [M,N] fp32 in/out; kernel 0 = CTA-pair (encoder),
+ * 1 = cluster split-K (decode; bn 64|128, split 1|2|4|8). The bf16 build returns B200T5_EINVAL. */
+int b200t5_test_ffo(int device, const void* A, const void* W, void* R, int M, int N, int F, int kernel, int bn, int split,
+                    void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);
 /* self == 1: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk];
  * self == 2: as 0 through the tensor-core kernel (csrc/attention_decode_tc.cuh, Tk <= 512; K and V must be finite

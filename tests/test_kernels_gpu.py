@@ -402,3 +402,38 @@ def test_encoder_attn(lib, B, S, H, impl):
     err = (out.float() - refv.float()).abs()
     assert (err <= 2 * 2.0 ** -7 * refv.float().abs() + 3e-3).all(), err.max().item()
     assert (out == refv).float().mean().item() > 0.95
+
+
+# ------------------------------------------------------------------------------------------------ fp16 build
+@pytest.mark.parametrize("M,N,F,kernel,bn,split", [
+    (512, 768, 2048, 0, 0, 0),      # encoder shape, CTA-pair kernel
+    (300, 520, 1000, 0, 0, 0),      # ragged everything; F not a multiple of the 32-element k-block
+    (256, 768, 2048, 1, 64, 4),     # decode shape, cluster split-K
+    (128, 512, 1024, 1, 128, 2),
+    (37, 136, 96, 1, 64, 8),        # more ranks than k-blocks allow -> the factor is reduced
+])
+def test_fp32_weight_ffo_via_two_tf32_passes(M, N, F, kernel, bn, split):
+    """`wo` under torch_dtype=float16 is an fp32 Linear (transformers keeps it in fp32): R += A . W^T with fp32 W.
+    The tensor cores only offer tf32 (10 mantissa bits); the library multiplies by W_hi and W_lo, both tf32-exact,
+    in one K-loop. Error metric: max |err| / sum_k |a||w| against an fp64 product. Measured on B200: 2e-7 .. 2.4e-6
+    (growing with K: the tensor core's fp32 accumulation truncates, unlike cuBLAS SGEMM's FMA chain at 2e-7 .. 4e-7),
+    35x .. 1000x below a single tf32 pass (8e-5 .. 2.5e-4) and far below the fp16 rounding (4.9e-4) that follows it
+    in T5LayerNorm."""
+    lib16 = _lib.load("fp16")
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * F)
+    A = (torch.randn(M, F, device="cuda", generator=g)).half().float()          # fp16 values, as the GeGLU epilogue writes them
+    W = torch.randn(N, F, device="cuda", generator=g) * 0.05                     # full fp32 mantissas
+    R0 = torch.randn(M, N, device="cuda", generator=g)
+    R = R0.clone()
+    _lib.check(lib16.b200t5_test_ffo(DEV, P(A), P(W), P(R), M, N, F, kernel, bn, split, None), None, lib16)
+    ref = R0.double() + A.double() @ W.double().t()
+    scale = (A.double().abs() @ W.double().abs().t()).clamp_min(1e-30)  # sum |a||w|: the natural error scale of a dot product
+    err = ((R.double() - ref).abs() / scale).max().item()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fp32_err = (((R0 + A @ W.t()).double() - ref).abs() / scale).max().item()
+    w_tf32 = (W.view(torch.int32) & -8192).view(torch.float32)  # one tf32 pass: W truncated to 10 mantissa bits
+    one_pass_err = (((R0.double() + A.double() @ w_tf32.double().t()) - ref).abs() / scale).max().item()
+    print(f"ffo M={M} N={N} F={F} kernel={kernel}: rel err two-pass {err:.2e} | torch fp32 {fp32_err:.2e} | single tf32 pass {one_pass_err:.2e}")
+    assert err <= 5e-6 and err <= 0.05 * one_pass_err, (err, fp32_err, one_pass_err)
+    # and the bf16 build refuses the hook loudly
+    assert _lib.load().b200t5_test_ffo(DEV, P(A), P(W), P(R), M, N, F, kernel, bn, split, None) == _lib.EINVAL
