@@ -140,6 +140,54 @@ class _ScoringWorker:
         return out
 
 
+def _visible_gpus() -> int:
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _prefetch(items: List[Any], fn, depth: int = 2):
+    """Yield fn(item) in order while a producer thread works `depth` items ahead (the consumer spends its time inside
+    the GPU library with the GIL released, so the two overlap). Exceptions of the producer are re-raised here."""
+    import queue
+    import threading
+
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+
+    def put(x) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(x, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def run():
+        try:
+            for it in items:
+                if not put(("ok", fn(it))):
+                    return
+            put(("end", None))
+        except BaseException as e:  # noqa: BLE001 - handed to the consumer
+            put(("err", e))
+
+    t = threading.Thread(target=run, name="b200t5-cpu-stage", daemon=True)
+    t.start()
+    try:
+        while True:
+            kind, val = q.get()
+            if kind == "end":
+                return
+            if kind == "err":
+                raise val
+            yield val
+    finally:
+        stop.set()
+        t.join(timeout=5)
+
+
 class BatchPredictor:
     def __init__(self, checkpoint: Any, predictor_cls: Type[Predictor], **predictor_kwargs: Any):
         self._checkpoint = checkpoint
@@ -162,7 +210,8 @@ class BatchPredictor:
                 keep_columns: Optional[List[str]] = None, batch_size: int = 4096, min_scoring_workers: int = 1,
                 max_scoring_workers: Optional[int] = None, num_cpus_per_worker: Optional[int] = None,
                 num_gpus_per_worker: Optional[int] = None, separate_gpu_stage: bool = True,
-                ray_remote_args: Optional[Dict[str, Any]] = None, **predict_kwargs) -> Dataset:
+                ray_remote_args: Optional[Dict[str, Any]] = None, pipeline_cpu_stage: bool = True,
+                **predict_kwargs) -> Dataset:
         num_gpus = int(num_gpus_per_worker or 0)
         kwargs = dict(self._predictor_kwargs)
         sig = inspect.signature(self._predictor_cls.from_checkpoint)
@@ -170,9 +219,17 @@ class BatchPredictor:
             kwargs["use_gpu"] = True
         prep = self.get_preprocessor()
         override_prep = False
+        stream_prep = None
         if prep is not None and num_gpus > 0 and separate_gpu_stage:
-            data = prep.transform(data)  # CPU stage of its own, as AIR does before a GPU stage
+            # CPU stage of its own, as AIR does before a GPU stage. With one scoring worker it is STREAMED: a
+            # producer thread tokenises block i+1 while the GPU generates block i (the library call releases the
+            # GIL), instead of materialising the whole tokenised dataset first. Tokenisation is row-wise, so the
+            # results are the same whichever way the rows are blocked.
             override_prep = True
+            if pipeline_cpu_stage and (max_scoring_workers == 1 or _visible_gpus() <= 1):
+                stream_prep = prep
+            else:
+                data = prep.transform(data)
         batches = list(data.iter_batches(batch_size=batch_size, batch_format="pandas"))
         n_workers = 1
         if num_gpus > 0:
@@ -186,7 +243,11 @@ class BatchPredictor:
             if self._worker is None or self._worker_key != (id(self._checkpoint), override_prep, repr(sorted(kwargs))):
                 self._worker = _ScoringWorker(self._checkpoint, self._predictor_cls, kwargs, override_prep)
                 self._worker_key = (id(self._checkpoint), override_prep, repr(sorted(kwargs)))
-            outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs) for b in batches]
+            if stream_prep is not None:
+                outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs)
+                        for b in _prefetch(batches, lambda raw: _to_pandas(_to_block(stream_prep.transform_batch(raw))))]
+            else:
+                outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs) for b in batches]
         else:
             from .pool import GpuWorkerPool
 

@@ -130,3 +130,43 @@ def test_lean_preprocess_equals_reference_style_tokenisation():
         assert lean[k].dtype == ref[k].dtype == np.int64 and lean[k].shape == ref[k].shape
         assert np.array_equal(lean[k], ref[k]), k
     assert lean["attention_mask"][-3].sum() == lean["input_ids"].shape[1]  # a truncated pair fills the row
+
+
+def test_streamed_cpu_stage_prefetch_keeps_order_and_propagates_errors():
+    """rayshim.train._prefetch: the tokenisation of block i+1 runs on a producer thread while block i is being
+    scored; results arrive in order, a producer exception surfaces in the consumer, an abandoned consumer does not
+    leave the producer blocked."""
+    import threading
+    import time
+
+    from anyscale_workshop_nyc_2023_b200.rayshim.train import _prefetch
+
+    seen_threads = set()
+
+    def slow_square(x):
+        seen_threads.add(threading.current_thread().name)
+        time.sleep(0.01)
+        return x * x
+
+    t0 = time.perf_counter()
+    got = []
+    for v in _prefetch(list(range(12)), slow_square):
+        time.sleep(0.01)  # the "GPU" stage
+        got.append(v)
+    dt = time.perf_counter() - t0
+    assert got == [i * i for i in range(12)]
+    assert seen_threads == {"b200t5-cpu-stage"}
+    assert dt < 0.22  # overlapped: ~12 x 0.01 + one stage of latency, not 12 x 0.02
+
+    def boom(x):
+        if x == 3:
+            raise ValueError("tokeniser failed")
+        return x
+
+    with pytest.raises(ValueError, match="tokeniser failed"):
+        list(_prefetch(list(range(6)), boom))
+    it = _prefetch(list(range(100)), slow_square)
+    assert next(it) == 0
+    it.close()  # consumer walks away: the producer must stop instead of blocking on a full queue
+    time.sleep(0.3)
+    assert not any(t.name == "b200t5-cpu-stage" and t.is_alive() for t in threading.enumerate())
