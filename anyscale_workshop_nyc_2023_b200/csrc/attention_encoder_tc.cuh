@@ -41,6 +41,16 @@ DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
       "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// exp(t) for t <= 0 as ex2.approx(t * log2(e)) with the product carried in two pieces (hi by FMA, lo by a multiply):
+// 4 instructions per score where expf costs ~10, max error ~2-3 ulp like expf's documented 2 ulp (the naive
+// ex2(t * log2e) would lose |t| * 2^-24 relative accuracy in the single rounding of the product). Results below
+// 2^-126 flush to zero; such a probability is < 1e-38 of the row maximum's and vanishes in the fp32 P.V sum anyway.
+DEVINL float exp_fast(float t) {
+  const float y = fmaf(t, 1.4426950216293335f, t * 1.925963033500258e-8f);
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return r;
+}
 DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -65,8 +75,11 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
                        const unsigned char* __restrict__ key_ok,   // [B][S]
                        const int* __restrict__ extent,             // [B]
                        const int* __restrict__ cu,                 // packed rows: prompt b starts at row cu[b] (NULL: b * S)
-                       int S, int H) {
+                       int S, int H,
+                       long long* __restrict__ prof = nullptr) {  // diagnostic: SM-clock stamps of CTA (0, 0), B200T5_ENC_PROF
   extern __shared__ uint8_t enc_tc_raw[];
+  const bool pr = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32;
+  if (pr) prof[0] = clock64();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(enc_tc_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + EncTcSmem::kQ;
   uint8_t* sK = smem + EncTcSmem::kK;
@@ -107,6 +120,16 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       mbar_init(&bar_pfree[1], 1);
       mbar_init(bar_o, 1);
       mbar_fence_init();
+      // Q tile, K and V chunks of this (b,h): issued before anything else so that the ~3k clocks of TMA latency run
+      // under the bias-table build and the TMEM allocation instead of after them (the loads need nothing but
+      // extent[b] / cu[b]; the issuing thread initialised and fenced the barrier itself)
+      const int row0 = cu ? cu[b] : b * S;
+      mbar_arrive_expect_tx(bar_load, 16384u * (1 + 2 * nchunks));
+      tma_load_2d(sQ, &tmQKV, bar_load, h * 64, row0 + i0);
+      for (int c = 0; c < nchunks; ++c) {
+        tma_load_2d(sK + c * 16384, &tmQKV, bar_load, I + h * 64, row0 + c * kEncTcChunk);
+        tma_load_2d(sV + c * 16384, &tmQKV, bar_load, 2 * I + h * 64, row0 + c * kEncTcChunk);
+      }
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
@@ -136,18 +159,11 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (pr) prof[1] = clock64();  // prologue done (bias tables, barriers, TMEM)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- loads: Q tile, K and V chunks of this (b,h)
-      const int row0 = cu ? cu[b] : b * S;
-      mbar_arrive_expect_tx(bar_load, 16384u * (1 + 2 * nchunks));
-      tma_load_2d(sQ, &tmQKV, bar_load, h * 64, row0 + i0);
-      for (int c = 0; c < nchunks; ++c) {
-        tma_load_2d(sK + c * 16384, &tmQKV, bar_load, I + h * 64, row0 + c * kEncTcChunk);
-        tma_load_2d(sV + c * 16384, &tmQKV, bar_load, 2 * I + h * 64, row0 + c * kEncTcChunk);
-      }
-      mbar_wait(bar_load, 0);
+      mbar_wait(bar_load, 0);  // (the loads were issued at the top of the kernel)
       tc_fence_after_sync();
       // ---------------- S[:, 128c : 128c+128] = Q K_c^T
       constexpr uint32_t idesc_s = make_idesc_act(128, 128, 0, 0);
@@ -185,6 +201,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     constexpr int P = kEncTcParts;
     mbar_wait(bar_s, 0);
     tc_fence_after_sync();
+    if (pr) prof[2] = clock64();  // TMA loads + Q K^T done
 
     // ---- pass A: s = bf16(bf16(acc) + bias) (+ mask), two keys per instruction: the fp32 accumulators are
     // packed to bf16x2 (one F2FP), the bias pair comes from the packed table, add.rn.bf16x2 rounds
@@ -239,6 +256,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     float mx = fmaxf(__low2float(mx2), __high2float(mx2));
     sStat[part * 128 + il] = mx;
     named_bar_sync(1, kEncTcCompute);
+    if (pr) prof[3] = clock64();  // pass A (bias, max) done
 #pragma unroll
     for (int k = 0; k < P; ++k) mx = fmaxf(mx, sStat[k * 128 + il]);
 
@@ -253,8 +271,8 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       uint32_t v[32];
 #pragma unroll
       for (int t = 0; t < 16; ++t) {
-        const float e0 = expf(act_lo(pk[t]) - mx);
-        const float e1 = expf(act_hi(pk[t]) - mx);
+        const float e0 = exp_fast(act_lo(pk[t]) - mx);
+        const float e1 = exp_fast(act_hi(pk[t]) - mx);
         sum += e0;
         sum += e1;
         v[2 * t] = __float_as_uint(e0);
@@ -265,6 +283,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     tmem_st_wait();
     sStat[(P + part) * 128 + il] = sum;
     named_bar_sync(1, kEncTcCompute);
+    if (pr) prof[4] = clock64();  // pass B (exp, sum) done
     sum = 0.f;
 #pragma unroll
     for (int k = 0; k < P; ++k) sum += sStat[(P + k) * 128 + il];  // fixed order: deterministic
@@ -301,8 +320,10 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
     }
 
     // ---- epilogue: O (TMEM cols 0..63) -> bf16 -> ctx[b*S + i, h*64 + d]; 16 columns per warp
+    if (pr) prof[5] = clock64();  // pass C (normalise, stage P) done
     mbar_wait(bar_o, 0);
     tc_fence_after_sync();
+    if (pr) prof[6] = clock64();  // last P.V MMA done
     {
       uint32_t o[16];
       tmem_ld_32x16(trow + part * 16, o);
@@ -318,6 +339,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       }
     }
     tc_fence_before_sync();
+    if (pr) prof[7] = clock64();  // output written
   }
   __syncthreads();
   if (warp == 0) {

@@ -1221,6 +1221,13 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
   const size_t attn_smem = encoder_attn_smem_bytes(S);
   if (attn_smem > 96 * 1024) return fail(h, B200T5_EINVAL, "encoder length S=%d too long for the attention kernel", S);
   const int wi_tiles = (F + 127) / 128;
+  // diagnostic (B200T5_ENC_PROF=1): phase timeline of the first CTA of layer 0's attention kernel
+  std::unique_ptr<DevBuf> enc_prof;
+  if (getenv("B200T5_ENC_PROF")) {
+    enc_prof.reset(new DevBuf());
+    CU_OK(h, enc_prof->alloc(64));
+    CU_OK(h, cudaMemsetAsync(enc_prof->p, 0, 64, s));
+  }
   for (int l = 0; l < c.Le; ++l) {
     EncLayerW& w = h->enc[l];
     CU_OK(h, run_rmsnorm(h, p.x.as<res_t>(), w.ln0.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
@@ -1231,7 +1238,8 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     }
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
       encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
-          p.tm_qkv_attn, p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H);
+          p.tm_qkv_attn, p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H,
+          enc_prof && l == 0 ? enc_prof->as<long long>() : nullptr);
     } else {
       encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
           p.qkv.as<act_t>(), p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
@@ -1259,6 +1267,14 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     }
   }
   CU_OK(h, run_rmsnorm(h, p.x.as<res_t>(), h->enc_final_ln.as<act_t>(), p.xn.as<act_t>(), M, d, c.eps, s));
+  if (enc_prof) {
+    long long st[8];
+    CU_OK(h, cudaStreamSynchronize(s));
+    CU_OK(h, cudaMemcpy(st, enc_prof->p, 64, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "ENC_PROF (SM clocks, CTA 0 of layer 0's attention; prologue, loads+QK^T, pass A, pass B, pass C, P.V tail, store):");
+    for (int i = 1; i < 8; ++i) fprintf(stderr, " %lld", st[i] - st[i - 1]);
+    fprintf(stderr, " | total %lld\n", st[7] - st[0]);
+  }
   return B200T5_OK;
 }
 
