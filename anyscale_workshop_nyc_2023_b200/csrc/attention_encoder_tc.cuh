@@ -65,7 +65,9 @@ struct EncTcSmem {
   // (S + 128) / 2 + 16 words each (the +16 staggers T1 by half the banks)
   static constexpr int kBias = kStat + 2 * kEncTcParts * 128 * 4;
   __host__ __device__ static int table_words(int S) { return (S + 128) / 2 + 16; }
-  static size_t bytes(int S) { return static_cast<size_t>(kBias) + 2 * table_words(S) * 4 + S + 16 + 1024; }
+  // the same rounded up to whole 16-byte vectors (layout of the precomputed tables and of sT0 / sT1 in shared memory)
+  __host__ __device__ static int table_words_padded(int S) { return (table_words(S) + 3) & ~3; }
+  static size_t bytes(int S) { return static_cast<size_t>(kBias) + 2 * table_words_padded(S) * 4 + S + 16 + 1024; }
 };
 
 __global__ void __launch_bounds__(kEncTcThreads, 1)
@@ -76,7 +78,8 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
                        const int* __restrict__ extent,             // [B]
                        const int* __restrict__ cu,                 // packed rows: prompt b starts at row cu[b] (NULL: b * S)
                        int S, int H,
-                       long long* __restrict__ prof = nullptr) {  // diagnostic: SM-clock stamps of CTA (0, 0), B200T5_ENC_PROF
+                       long long* __restrict__ prof = nullptr,     // diagnostic: SM-clock stamps of CTA (0, 0), B200T5_ENC_PROF
+                       const uint32_t* __restrict__ packed_bias = nullptr) {  // [H][q tiles][2][table_words_padded(S)]: sT0|sT1 ready-made
   extern __shared__ uint8_t enc_tc_raw[];
   const bool pr = prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32;
   if (pr) prof[0] = clock64();
@@ -93,8 +96,8 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* sStat = reinterpret_cast<float*>(smem + EncTcSmem::kStat);
   uint32_t* sT0 = reinterpret_cast<uint32_t*>(smem + EncTcSmem::kBias);
-  uint32_t* sT1 = sT0 + EncTcSmem::table_words(S);
-  unsigned char* sOk = reinterpret_cast<unsigned char*>(sT1 + EncTcSmem::table_words(S));
+  uint32_t* sT1 = sT0 + EncTcSmem::table_words_padded(S);
+  unsigned char* sOk = reinterpret_cast<unsigned char*>(sT1 + EncTcSmem::table_words_padded(S));
   int* sHoles = reinterpret_cast<int*>(bars + 10);
   if (threadIdx.x == 0) *sHoles = 0;
   __syncthreads();
@@ -142,10 +145,19 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,  // [B*S, 3I] 
       const int idx = lo + x;
       return (x < S + 127 && idx >= 0 && idx < 2 * S - 1) ? rel_bias[static_cast<size_t>(h) * (2 * S - 1) + idx] : 0.f;
     };
-    for (int k = t; k < (S + 128) / 2; k += kEncTcCompute) {
-      const float b0 = bias_at(2 * k), b1 = bias_at(2 * k + 1), b2 = bias_at(2 * k + 2);
-      sT0[k] = pack_act2(b0, b1);
-      sT1[k] = pack_act2(b1, b2);
+    if (packed_bias != nullptr) {
+      // the two packed tables of this (head, query tile) were built once per plan on the host (b200t5.cu
+      // build_packed_bias): a 16-byte-vector copy instead of ~1k dependent global reads per CTA
+      const int tw = EncTcSmem::table_words_padded(S);
+      const uint4* src = reinterpret_cast<const uint4*>(packed_bias + (static_cast<size_t>(h) * gridDim.x + blockIdx.x) * 2 * tw);
+      uint4* d0 = reinterpret_cast<uint4*>(sT0);
+      for (int k = t; k < 2 * tw / 4; k += kEncTcCompute) d0[k] = src[k];  // sT1 = sT0 + tw follows contiguously
+    } else {
+      for (int k = t; k < (S + 128) / 2; k += kEncTcCompute) {
+        const float b0 = bias_at(2 * k), b1 = bias_at(2 * k + 1), b2 = bias_at(2 * k + 2);
+        sT0[k] = pack_act2(b0, b1);
+        sT1[k] = pack_act2(b1, b2);
+      }
     }
     int holes = 0;
     for (int x = t; x < S; x += kEncTcCompute) {

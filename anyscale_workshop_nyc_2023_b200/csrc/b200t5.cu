@@ -213,6 +213,7 @@ struct Plan {
   // encoder workspace
   DevBuf x, xn, qkv, ctx, hff;          // [B*S, d], [B*S, d], [B*S, 3I], [B*S, I], [B*S, F]
   DevBuf key_ok, extent, enc_bias;      // uint8 [B,S], int [B], float [H][2S-1]
+  DevBuf enc_bias_packed;               // [H][q tiles][2][table_words_padded(S)] act2 words: the attention kernel's smem tables
   DevBuf cu, row_b, row_s;              // packed encoder rows: int [B+1] offsets, int [B*S] row -> (prompt, position)
   int* h_cu = nullptr;                  // pinned copy of cu[B] (number of packed rows)
   int packed_rows = 0;                  // rows the last encoder pass ran on
@@ -1133,6 +1134,35 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
     }
     CU_OK(h, pl->enc_bias.alloc(eb.size() * 4));
     CU_OK(h, cudaMemcpy(pl->enc_bias.p, eb.data(), eb.size() * 4, cudaMemcpyHostToDevice));
+    if (S <= kEncTcMaxS) {
+      // The attention kernel's two packed tables per (head, 128-query tile): T0[k] = (bias[2k], bias[2k+1]),
+      // T1[k] = (bias[2k+1], bias[2k+2]) with bias[x] = rel_bias[h][S - 1 - i0 - 127 + x] (0 outside), exactly
+      // what the kernel used to build per CTA (attention_encoder_tc.cuh, bias_at).
+      const int tw = EncTcSmem::table_words_padded(S), ntiles = (S + kEncTcQ - 1) / kEncTcQ;
+      std::vector<uint32_t> pk(static_cast<size_t>(H) * ntiles * 2 * tw, 0u);
+      auto bits = [](float v) -> uint32_t {
+        const act_t a = B200T5_F16 ? act_t(__float2half_rn(v)) : act_t(__float2bfloat16_rn(v));
+        uint16_t u;
+        memcpy(&u, &a, 2);
+        return u;
+      };
+      for (int hh = 0; hh < H; ++hh)
+        for (int ti = 0; ti < ntiles; ++ti) {
+          const int lo = S - 1 - ti * kEncTcQ - 127;
+          auto at = [&](int x) -> float {
+            const int idx = lo + x;
+            return (x < S + 127 && idx >= 0 && idx < 2 * S - 1) ? eb[static_cast<size_t>(hh) * (2 * S - 1) + idx] : 0.f;
+          };
+          uint32_t* t0 = pk.data() + (static_cast<size_t>(hh) * ntiles + ti) * 2 * tw;
+          uint32_t* t1 = t0 + tw;
+          for (int k = 0; k < (S + 128) / 2; ++k) {
+            t0[k] = bits(at(2 * k)) | (bits(at(2 * k + 1)) << 16);
+            t1[k] = bits(at(2 * k + 1)) | (bits(at(2 * k + 2)) << 16);
+          }
+        }
+      CU_OK(h, pl->enc_bias_packed.alloc(pk.size() * 4));
+      CU_OK(h, cudaMemcpy(pl->enc_bias_packed.p, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    }
     std::vector<float> db(static_cast<size_t>(H) * Tmax);
     for (int n = 0; n < Tmax; ++n) {
       const int bk = b200t5_relative_bucket(-n, 0, c.nb, c.maxdist);
@@ -1239,7 +1269,7 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
       encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
           p.tm_qkv_attn, p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H,
-          enc_prof && l == 0 ? enc_prof->as<long long>() : nullptr);
+          enc_prof && l == 0 ? enc_prof->as<long long>() : nullptr, p.enc_bias_packed.as<uint32_t>());
     } else {
       encoder_attn_kernel<<<dim3((S + kEncQ - 1) / kEncQ, B * H), kEncThreads, attn_smem, s>>>(
           p.qkv.as<act_t>(), p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), S, H);
