@@ -1800,6 +1800,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
   const int min_new = gp->min_new_tokens > 0 ? gp->min_new_tokens : 0;
   const int B = pool;
   if (admit_min < 1) admit_min = B >= 8 ? B / 8 : 1;
+  const int poll = gp->poll_interval > 0 ? (gp->poll_interval > 64 ? 64 : gp->poll_interval) : kStepsPerGraph;
   TRY(ensure_plan(h, B, S, T));
   Plan& p = *h->plan;
   cudaStream_t s = h->exec_stream;
@@ -1873,10 +1874,14 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
       next += k;
       active += k;
     }
-    // ---- eight decode steps for every slot, then see which slots have finished
-    CU_OK(h, cudaGraphLaunch(p.gexec8, s));
-    h->launches += static_cast<int64_t>(p.graph_nodes) * kStepsPerGraph;
-    steps += kStepsPerGraph;
+    // ---- `poll` decode steps for every slot (eight = one graph launch), then see which slots have finished
+    if (poll % kStepsPerGraph == 0) {
+      for (int r = 0; r < poll / kStepsPerGraph; ++r) CU_OK(h, cudaGraphLaunch(p.gexec8, s));
+    } else {
+      for (int r = 0; r < poll; ++r) CU_OK(h, cudaGraphLaunch(p.gexec, s));
+    }
+    h->launches += static_cast<int64_t>(p.graph_nodes) * poll;
+    steps += poll;
     CU_OK(h, cudaMemcpyAsync(p.h_unf, p.unfinished.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
     CU_OK(h, cudaStreamSynchronize(s));
     for (int b = 0; b < B; ++b) {

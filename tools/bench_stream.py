@@ -43,12 +43,14 @@ def main():
     ap.add_argument("--lengths", default="alpaca")
     ap.add_argument("--admit", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--poll", type=int, default=8, help="decode steps between two looks at the finished flags")
+    ap.add_argument("--only-pool", action="store_true")
     a = ap.parse_args()
     spec = SPECS[a.model]
     model = B200T5ForConditionalGeneration.from_pretrained(checkpoint_dir(a.model, 0))
     ids, mask = synthetic_token_batch(a.n, a.seq, spec.vocab_size, seed=3, lengths=a.lengths)
     res = {}
-    for name in ("static", "pool"):
+    for name in (("pool",) if a.only_pool else ("static", "pool")):
         best = None
         for rep in range(a.reps + 1):  # rep 0 = warm-up (plan, graphs)
             torch.cuda.synchronize()
@@ -56,7 +58,7 @@ def main():
             if name == "static":
                 out, lens, steps = static_batches(model, ids, mask, a.pool, a.new)
             else:
-                out, lens = model.generate_stream(ids, mask, pool=a.pool, admit_min=a.admit, max_new_tokens=a.new)
+                out, lens = model.generate_stream(ids, mask, pool=a.pool, admit_min=a.admit, max_new_tokens=a.new, poll_interval=a.poll)
                 out = np.pad(out, ((0, 0), (0, a.new + 1 - out.shape[1])))
                 steps = int(model.stats()["decode_steps"])
             torch.cuda.synchronize()
@@ -64,6 +66,11 @@ def main():
             if rep and (best is None or dt < best):
                 best = dt
         res[name] = dict(seconds=best, out=out, lens=lens, steps=steps)
+    if a.only_pool:
+        r = res["pool"]
+        print(json.dumps({"admit": a.admit, "poll": a.poll, "seconds": round(r["seconds"], 4), "decode_steps": r["steps"],
+                          "tokens_per_s": round(int(r["lens"].sum()) / r["seconds"], 1)}))
+        return
     same = bool((res["static"]["out"] == res["pool"]["out"]).all() and (res["static"]["lens"] == res["pool"]["lens"]).all())
     lens = res["static"]["lens"]
     toks = int(lens.sum())
