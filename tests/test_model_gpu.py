@@ -361,12 +361,15 @@ def test_slot_pool_forced_length_and_generate_dispatch(models):
     kw = dict(max_new_tokens=9, min_new_tokens=9)
     ref, ref_len = _static_rows(model, ids, mask, 16, **kw)
     assert (ref_len == 9).all()
-    old = model.pool_size
+    old = model.pool_size, model.pool_slots
     try:
-        model.pool_size = 16
+        model.pool_size, model.pool_slots = 16, 16
         out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), **kw).cpu().numpy()
+        model.pool_slots = 64  # more slots than the static batches have rows: still the same tokens
+        out64 = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), **kw).cpu().numpy()
+        assert (out64 == out).all()
     finally:
-        model.pool_size = old
+        model.pool_size, model.pool_slots = old
     assert out.shape == (70, 10) and (out == ref).all()
     again, _ = model.generate_host(ids[:16], mask[:16], **kw)
     assert (again == ref[:16]).all()

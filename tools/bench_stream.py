@@ -37,7 +37,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="flan-t5-base")
     ap.add_argument("--n", type=int, default=2048)
-    ap.add_argument("--pool", type=int, default=256)
+    ap.add_argument("--pool", type=int, default=512, help="decode slots of the pool")
+    ap.add_argument("--batch", type=int, default=256, help="rows per static batch (the notebook's batch_size)")
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--lengths", default="alpaca")
@@ -56,7 +57,7 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if name == "static":
-                out, lens, steps = static_batches(model, ids, mask, a.pool, a.new)
+                out, lens, steps = static_batches(model, ids, mask, a.batch, a.new)
             else:
                 out, lens = model.generate_stream(ids, mask, pool=a.pool, admit_min=a.admit, max_new_tokens=a.new, poll_interval=a.poll)
                 out = np.pad(out, ((0, 0), (0, a.new + 1 - out.shape[1])))
@@ -75,7 +76,7 @@ def main():
     lens = res["static"]["lens"]
     toks = int(lens.sum())
     line = {
-        "workload": f"{a.model}, {a.n} prompts, S={a.seq} lengths={a.lengths}, max_new_tokens={a.new}, natural EOS, pool/batch {a.pool}",
+        "workload": f"{a.model}, {a.n} prompts, S={a.seq} lengths={a.lengths}, max_new_tokens={a.new}, natural EOS, static batches of {a.batch}, pool of {a.pool} slots",
         "generated_tokens": toks,
         "len_mean": float(lens.mean()), "len_p50": float(np.median(lens)), "len_p90": float(np.percentile(lens, 90)), "len_max": int(lens.max()),
         "identical_tokens": same,
