@@ -231,6 +231,9 @@ def main_b200(a):
     worker = _ScoringWorker(bp._checkpoint, bp._predictor_cls, {**bp._predictor_kwargs, "use_gpu": True}, False)
     predictor = worker.predictor
     model = predictor.model
+    # the bench times the named configuration: one static batch per step, whatever its size (larger batches would
+    # otherwise be routed through the slot pool, whose occupancy-dependent work is measured by tools/bench_stream.py)
+    model.pool_size = max(model.pool_size, a.batch)
 
     # every rank owns its own shard of batches (dataset sharded by block index, no collective)
     def host_batch(step):
