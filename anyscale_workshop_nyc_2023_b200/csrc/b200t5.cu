@@ -524,7 +524,7 @@ struct GeluLutOwner {
 };
 static GeluLutOwner g_gelu;  // one process drives one GPU
 
-static int ensure_gelu_lut(b200t5_ctx* h, int pow_mode, GeluLut* out) {
+[[maybe_unused]] static int ensure_gelu_lut(b200t5_ctx* h, int pow_mode, GeluLut* out) {
   if (g_gelu.lut.table && g_gelu.pow_mode == pow_mode) {
     *out = g_gelu.lut;
     return B200T5_OK;
@@ -2032,7 +2032,7 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
 }
 
 // ================================================================== single-kernel hooks
-static int hook_device(int device) {
+[[maybe_unused]] static int hook_device(int device) {
   int sms = check_device(nullptr, device);
   if (sms < 0) return sms;
   cudaError_t e = init_kernel_attrs();

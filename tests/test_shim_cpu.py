@@ -170,3 +170,44 @@ def test_streamed_cpu_stage_prefetch_keeps_order_and_propagates_errors():
     it.close()  # consumer walks away: the producer must stop instead of blocking on a full queue
     time.sleep(0.3)
     assert not any(t.name == "b200t5-cpu-stage" and t.is_alive() for t in threading.enumerate())
+
+
+def test_batch_predictor_streamed_and_materialised_cpu_stage_agree():
+    """BatchPredictor.predict with a GPU stage requested: the tokenisation runs either as a materialised CPU stage
+    (AIR's behaviour) or streamed block by block under the scoring loop; same rows, same order, and the predictor
+    never sees a preprocessor of its own in either case."""
+    from anyscale_workshop_nyc_2023_b200.rayshim.train import BatchPredictor, Predictor
+
+    calls = []
+
+    class UpperPredictor(Predictor):
+        @classmethod
+        def from_checkpoint(cls, checkpoint, use_gpu=False, **kw):
+            p = cls(preprocessor=checkpoint.get_preprocessor())
+            p.use_gpu = use_gpu
+            return p
+
+        def _predict_pandas(self, data, **kw):
+            calls.append(len(data))
+            assert self.get_preprocessor() is None  # the CPU stage ran outside the predictor
+            return pd.DataFrame({"generated_output": [f"{a}|{b}".upper() for a, b in zip(data["a"], data["n"])]})
+
+    class Ckpt:
+        def __init__(self, prep):
+            self._prep = prep
+
+        def get_preprocessor(self):
+            return self._prep
+
+    prep = rayshim.data.BatchMapper(lambda b: pd.DataFrame({"a": b["instruction"].str[:5], "n": b["instruction"].str.len()}),
+                                    batch_format="pandas")
+    ds = rayshim.data.from_huggingface(synthetic_alpaca_rows(37))
+    bp = BatchPredictor.from_checkpoint(Ckpt(prep), UpperPredictor)
+    outs = {}
+    for streamed in (False, True):
+        calls.clear()
+        outs[streamed] = bp.predict(ds, batch_size=8, num_gpus_per_worker=1, pipeline_cpu_stage=streamed).to_pandas()
+        assert calls == [8, 8, 8, 8, 5]
+    assert outs[True]["generated_output"].tolist() == outs[False]["generated_output"].tolist()
+    want = [f"{s[:5]}|{len(s)}".upper() for s in synthetic_alpaca_rows(37)["instruction"]]
+    assert outs[True]["generated_output"].tolist() == want
