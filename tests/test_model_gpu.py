@@ -514,3 +514,29 @@ def test_fp16_flan_t5_small_vs_hf_gpu(models_fp16, tmp_path):
           f"noise floor HF-fp16-GPU vs HF-fp16-CPU max {floor.max():.4f} mean {floor.mean():.5f}")
     assert gated == 1.0
     assert err.mean() <= 1.0 * floor.mean() and err.max() <= 2.0 * floor.max()
+
+
+def test_fp16_mask_holes_and_edge_shapes_vs_oracle(models_fp16):
+    """fp16 build: a non-prefix mask (HF adds finfo(fp16).min, which can overflow to -inf; the kernels replace the
+    score - both give probability 0 after the fp32 softmax), ragged lengths and a 1-token prompt against the oracle's
+    fp16 mode. (A fully masked row is NaN in HF fp16 and is not part of the contract.)"""
+    spec = SPECS["tiny"]
+    model = models_fp16("tiny", 1)
+    orc = oracle_fp16("tiny", 1)
+    ids, mask = synthetic_token_batch(4, 20, spec.vocab_size, seed=77, lengths="full")
+    mask[1, 3:7] = 0
+    mask[3, 9:] = 0
+    T = 6
+    dec = np.zeros((4, T), dtype=np.int64)
+    dec[:, 1:] = np.random.default_rng(0).integers(3, spec.vocab_size, size=(4, T - 1))
+    ref = orc.decode_logits(ids, mask, dec)
+    got = model.decode_logits(ids, mask, dec).cpu().numpy()
+    err = np.abs(got - ref)
+    print(f"fp16 mask holes: logits max err {err.max():.4f} mean {err.mean():.5f}")
+    assert np.isfinite(got).all() and err.max() <= LOGIT_ATOL_FP16 and err.mean() <= LOGIT_MEAN_FP16
+    for B, S, lengths in [(1, 1, "full"), (9, 130, "uniform")]:
+        ids, mask = synthetic_token_batch(B, S, spec.vocab_size, seed=5 + B, lengths=lengths)
+        out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=8).cpu().numpy()
+        otoks, margins = orc.generate(ids, mask, max_new_tokens=8, return_margins=True)
+        gated, _ = gated_prefix_match(out, otoks, margins, tau=TAU_FP16)
+        assert gated == 1.0, (B, S)
