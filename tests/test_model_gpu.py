@@ -540,3 +540,26 @@ def test_fp16_mask_holes_and_edge_shapes_vs_oracle(models_fp16):
         otoks, margins = orc.generate(ids, mask, max_new_tokens=8, return_margins=True)
         gated, _ = gated_prefix_match(out, otoks, margins, tau=TAU_FP16)
         assert gated == 1.0, (B, S)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_long_prompts_beyond_the_tcgen05_attention_tile(models, models_fp16, dtype):
+    """S = 640 > 512: the encoder falls back to the mma.sync attention kernel and unpacked rows (the tcgen05 kernel
+    keeps a 128 x 512 score tile in TMEM); the slot pool, which needs the packed encoder, refuses such prompts loudly."""
+    spec = SPECS["tiny"]
+    model = models("tiny", 1)[0] if dtype == "bf16" else models_fp16("tiny", 1)
+    orc = oracle_for("tiny", 1) if dtype == "bf16" else oracle_fp16("tiny", 1)
+    tau = TAU if dtype == "bf16" else TAU_FP16
+    ids, mask = synthetic_token_batch(3, 640, spec.vocab_size, seed=41, lengths="uniform", min_len=520)
+    out = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=8).cpu().numpy()
+    otoks, margins = orc.generate(ids, mask, max_new_tokens=8, return_margins=True)
+    gated, full = gated_prefix_match(out, otoks, margins, tau=tau)
+    print(f"S=640 {dtype}: gated={gated:.2f} full={full:.2f}")
+    assert gated == 1.0
+    from anyscale_workshop_nyc_2023_b200._lib import B200T5Error
+
+    with pytest.raises(B200T5Error, match="packed encoder"):
+        model.generate_stream(np.repeat(ids, 4, 0), np.repeat(mask, 4, 0), pool=4, max_new_tokens=4)
+    # the handle is still usable afterwards
+    again = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=8).cpu().numpy()
+    assert (again == out).all()
