@@ -68,3 +68,18 @@ def test_config_validation_is_host_side():
     h = C.c_void_p()
     assert lib.b200t5_create(C.byref(bad), 0, C.byref(h)) == _lib.EINVAL
     assert "d_kv" in _lib.last_error()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/b200t5.h is the whole boundary: it must compile as C99 and as C++ with nothing but the standard
+    headers (no torch, no CUDA types in the signatures)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200t5.h"\nint main(void) { return sizeof(b200t5_config) == 0; }\n')
+    inc = str(ROOT / "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)]):
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stderr
+    code = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "b200t5.h").read_text(), flags=re.S)  # declarations without comments
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "at::" not in code
+    assert re.findall(r"#include\s*[<\"]([^>\"]+)", code) == ["stdint.h"]
