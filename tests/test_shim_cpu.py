@@ -211,3 +211,17 @@ def test_batch_predictor_streamed_and_materialised_cpu_stage_agree():
     assert outs[True]["generated_output"].tolist() == outs[False]["generated_output"].tolist()
     want = [f"{s[:5]}|{len(s)}".upper() for s in synthetic_alpaca_rows(37)["instruction"]]
     assert outs[True]["generated_output"].tolist() == want
+
+
+def test_example_script_reference_leg_runs_on_cpu():
+    """examples/batch_inference.py is the notebook's flow as a script; its `--model-cls hf` leg (the dependency's own
+    model through the same shim, predictor and preprocess function) must run without a GPU."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    proc = subprocess.run([sys.executable, str(root / "examples" / "batch_inference.py"), "--model-cls", "hf", "--n", "5",
+                           "--max-new-tokens", "4", "--batch-size", "2"], capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert "5 prompts in" in proc.stdout and "model_cls=HFModelOnCpu" in proc.stdout
