@@ -563,3 +563,22 @@ def test_long_prompts_beyond_the_tcgen05_attention_tile(models, models_fp16, dty
     # the handle is still usable afterwards
     again = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=8).cpu().numpy()
     assert (again == out).all()
+
+
+def test_library_counters_equal_the_python_roofline_model(models, models_fp16):
+    """b200t5_get_stats' decode_algo_bytes / encoder_flops (what bench.py divides by its CUDA-event times) are the
+    SURVEY 8(d) model: the Python restatement (roofline.py, pinned to SURVEY's table on CPU) gives the same numbers
+    for ragged prompts, in both builds."""
+    from anyscale_workshop_nyc_2023_b200 import roofline
+
+    spec = SPECS["mini"]
+    ids, mask = synthetic_token_batch(7, 48, spec.vocab_size, seed=51, lengths="uniform")
+    ext = mask.sum(axis=1).tolist()
+    for model, fp32_wo in ((models("mini", 2)[0], False), (models_fp16("mini", 2), True)):
+        model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=9, min_new_tokens=9)
+        st = model.stats()
+        assert int(st["decode_steps"]) == 9
+        assert st["decode_algo_bytes"] == pytest.approx(roofline.decode_bytes(spec, 7, 9, extents=ext, fp32_wo=fp32_wo), rel=1e-9)
+        assert st["encoder_flops"] == pytest.approx(roofline.encoder_flops(spec, 7, extents=ext), rel=1e-9)
+        ca = model.bench_cross_attention(reps=1)
+        assert ca["bytes_per_launch"] == pytest.approx(roofline.cross_attention_bytes_per_launch(spec, ext), rel=1e-9)
