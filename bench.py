@@ -311,9 +311,10 @@ def main_b200(a):
     tf = ROOT / "profiles" / "cross_attn_traffic.json"
     if tf.exists() and a.model == "flan-t5-base" and (B, S, a.lengths) == (256, 512, "full"):
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-    kv_gb = 2.0 * spec.num_decoder_layers * 2 * B * S * spec.inner_dim / 1e9
-    w_gb = 2.0 * (spec.num_decoder_layers * (6 * spec.d_model * spec.inner_dim + 3 * spec.d_model * spec.d_ff)
-                  + spec.vocab_size * spec.d_model) / 1e9
+    from anyscale_workshop_nyc_2023_b200 import roofline  # SURVEY 8(d)'s byte model (tests/test_roofline_cpu.py)
+
+    kv_gb = roofline.cross_attention_bytes_per_launch(spec, [S] * B) * spec.num_decoder_layers / 1e9
+    w_gb = 2.0 * roofline.step_weight_elements(spec) / 1e9
 
     if rank == 0:
         tokens = world * K * B * T
