@@ -40,14 +40,12 @@ DEVINL float dot8(const uint4& kv, const float (&qf)[8]) {
   return s;
 }
 
-// Weights the kernels AFTER the cross-attention will need (this layer's cross-O / wi / FF-out, the next layer's
-// QKV / O / cross-Q). Decoder weights (198 MB for base) do not survive in L2 across a step once 4.8 GB of KV
-// has streamed through, so every skinny GEMM used to start with an HBM round trip on its critical path. The
-// streaming kernel has 64 us and ~4 % of spare bandwidth: each CTA requests one slice of every buffer into L2
-// (evict-last) while the K/V stream itself is marked evict-first.
-struct L2Prefetch {
-  const void* ptr[6];
-  unsigned int bytes[6];
+// In-situ timing of the cross-attention launches inside the step graph (bench.py's roofline.frac): when `slots` is
+// non-null every CTA folds its start / end %globaltimer into slot `slot` (min start, max end) and
+// advance_step_kernel turns the slots into per-launch durations once per step. Null in the timed region.
+struct XsStamps {
+  unsigned long long* slots;  // [n_slots][2] = {min start, max end}
+  int slot;
 };
 
 template <bool kSelf>
@@ -61,27 +59,16 @@ attn_decode_kernel(const act_t* __restrict__ q,    // [B, H*64]
                    const unsigned char* __restrict__ key_ok,  // cross: [B][Tk] 1 = attended
                    const int* __restrict__ step,              // self: device scalar t (or per-row positions)
                    const float* __restrict__ dist_bias,       // self: [H][Tk] bias by distance t-j
-                   const L2Prefetch pf,                       // cross: weight slices to pull into L2 (bytes 0 = none)
+                   const XsStamps stamps,                     // cross: in-situ launch timing (slots == nullptr: off)
                    const int step_stride = 0) {               // self: 1 = slot pool, row b is at position step[b]
   extern __shared__ float s_scores[];  // Tk floats
   __shared__ float s_red[4][64];
   __shared__ float s_stat[8];
 
   pdl_launch_dependents();
-  if (!kSelf && threadIdx.x == 0) {
-    // constant data: no need to wait for the previous kernel
-    const uint64_t keep = l2_policy_evict_last();
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const unsigned int per = ((pf.bytes[k] + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
-      const unsigned long long off = static_cast<unsigned long long>(blockIdx.x) * per;
-      if (off < pf.bytes[k]) {
-        const unsigned int n = pf.bytes[k] - off < per ? static_cast<unsigned int>(pf.bytes[k] - off) & ~15u : per;
-        if (n) prefetch_l2_bulk(static_cast<const char*>(pf.ptr[k]) + off, n, keep);
-      }
-    }
-  }
   pdl_wait();
+  unsigned long long t_start = 0;
+  if (!kSelf && stamps.slots != nullptr && threadIdx.x == 0) t_start = global_timer_ns();
   const uint64_t stream_policy = l2_policy_evict_first();
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,6 +183,10 @@ attn_decode_kernel(const act_t* __restrict__ q,    // [B, H*64]
     const float o0 = (s_red[0][d0] + s_red[1][d0]) + (s_red[2][d0] + s_red[3][d0]);
     const float o1 = (s_red[0][d0 + 1] + s_red[1][d0 + 1]) + (s_red[2][d0 + 1] + s_red[3][d0 + 1]);
     *reinterpret_cast<uint32_t*>(ctx + (static_cast<size_t>(b) * H + h) * 64 + d0) = pack_act2(o0, o1);
+  }
+  if (!kSelf && stamps.slots != nullptr && threadIdx.x == 0) {
+    atomicMin(&stamps.slots[2 * stamps.slot], t_start);
+    atomicMax(&stamps.slots[2 * stamps.slot + 1], static_cast<unsigned long long>(global_timer_ns()));
   }
 }
 

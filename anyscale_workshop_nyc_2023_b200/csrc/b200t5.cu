@@ -21,15 +21,13 @@
 
 #include "../../include/b200t5.h"
 #include "attention_decode.cuh"
-#include "attention_decode_tc.cuh"
+#include "attention_cross_stream.cuh"
 #include "attention_encoder.cuh"
 #include "attention_encoder_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm_splitk.cuh"
 #include "gemm_2cta.cuh"
-#include "gemm_mcast.cuh"
-#include "decode_mega.cuh"
 
 using namespace b200;
 
@@ -198,11 +196,7 @@ struct EncLayerW {
 struct DecLayerW {
   DevBuf ln0, ln1, ln2, wqkv, wo, wcq, wco, wi, wff_o;  // wi interleaved per N-tile of the decode wi GEMM
   CUtensorMap tm_qkv, tm_o, tm_cq, tm_co, tm_wi, tm_ffo;
-  CUtensorMap tm16_o, tm16_cq, tm16_co;  // box of 16 weight rows: gemm_mcast.cuh
   int wi_rows = 0;
-  DevBuf mega_wi_own;  // wi interleaved for the persistent kernel's tile when it differs from `wi`
-  void* mega_wi = nullptr;
-  int mega_wi_rows = 0, mega_wi_bn = 0;
 };
 
 constexpr int kMaxChains = 8;
@@ -221,7 +215,6 @@ struct Plan {
   DevBuf cross_kv;                      // [Ld][2][B][H][S][64]
   // decoder workspace
   DevBuf dx, dxn, dq, dctx, dh;         // [B,d], [B,d], [B,I], [B,I], [B,F]
-  DevBuf dss;                           // float [B][ceil(d/32)]: sums of squares of x per 32-column chunk (fused RMSNorm)
   DevBuf self_kv;                       // [Ld][2][B][H][Tmax][64]
   DevBuf dec_bias;                      // float [H][Tmax]
   DevBuf pval, pidx;                    // [B][n_tiles]
@@ -230,6 +223,7 @@ struct Plan {
   // (retired: its K/V are no longer streamed). In slot-pool mode they describe the slots' CURRENT prompts while
   // extent / key_ok describe the prompts of the encoder pass being admitted.
   DevBuf live_extent, live_key_ok;
+  DevBuf xs_stamps, xs_acc;  // in-situ profile of the cross-attention launches: [Ld * chains][2] stamps / {ns, launches}
   // slot pool (b200t5_generate_stream): per-slot position and result row, admission lists, [N, Tmax+1] results
   DevBuf pos, out_row, admit;
   DevBuf stream_out, stream_len;
@@ -241,19 +235,14 @@ struct Plan {
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
   CUtensorMap tm_xn, tm_ctx, tm_hff, tm_qkv_attn;
-  CUtensorMap tm_cross_kv;  // [Ld*2*B*H*S, 64] view of the cross-KV arena, box 64 x 128 keys (attention_decode_tc.cuh)
   // decode chains: the batch is cut into independent row ranges that run concurrently (one
   // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
   struct Chain {
     int b0 = 0, nb = 0;
-    CUtensorMap tm_dxn, tm_dctx, tm_dh, tm_dx;
+    CUtensorMap tm_dxn, tm_dctx, tm_dh;
   };
   int n_chains = 1;
   Chain chains[kMaxChains];
-  // persistent decode kernel (decode_mega.cuh): device-resident tensor maps, layer table, split-K workspace
-  bool mega_ok = false;
-  DevBuf mega_maps, mega_layers, mega_ws, mega_bar, mega_prof;
-  MegaParams mega{};
   // decode-step graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -307,8 +296,6 @@ struct b200t5_ctx {
   int pow_mode = 0;
   bool use_pdl = true;
   bool enc_attn_tc = true;
-  bool serialize_xattn = false;  // measured slower on B200 (300 vs 261 ms/batch): kept as an env knob only
-  std::vector<cudaEvent_t> xattn_ev;
   GeluLut gelu_lut{nullptr, 0, 0};
   // decode GEMMs: cluster split-K tiles (gemm_splitk.cuh). {BN, wanted split} per product;
   // B200T5_SK=0 selects the persistent kernel instead, B200T5_SK="bn,s,bn,s,bn,s,bn,s" overrides
@@ -316,24 +303,20 @@ struct b200t5_ctx {
   struct SkChoice {
     int bn, split;
   };
-  // Persistent decode kernel (decode_mega.cuh). Bit-identical to the step graph but, as measured on B200
-  // (profiles/mega_phases_r1.md), not yet faster: it is opt-in. B200T5_MEGA=1 enables it,
-  // "a,b,c,d,e,f,g" enables it with tile choices (bn_qkv, bn_proj, ks_proj, bn_cq, bn_wi, bn_ffo, ks_ffo).
-  bool mega_on = false;
-  int mega_cfg[7] = {32, 64, 6, 32, 64, 128, 8};
-  bool xattn_tc = false;  // B200T5_XATTN=tc: decode cross-attention on the tensor cores (attention_decode_tc.cuh), S <= 512
   bool pack_rows = true;  // encoder on the valid rows only (variable-length packing); B200T5_PACK=0: all B*S rows as the reference does
-  bool mcast = false;  // B200T5_MCAST=1: decode O / cross-Q / cross-O products through the A-multicast kernel (gemm_mcast.cuh).
-                      // Correct (tests) but slower than split-K (201.4 vs 191.0 ms per batch): multicast saves L2 reads, not the
-                      // bytes each SM has to take in (196 KB of A per CTA), and that ingest rate is what bounds these kernels
-  bool fuse_norm = false;  // B200T5_FUSENORM=1: RMSNorm applied to the A tile inside the consumer split-K GEMM. Correct (tests) but
-                          // measured slower than the separate, PDL-overlapped norm kernels: 201.1 vs 189.1 ms per batch
-  bool use_2cta = true;  // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
-  bool l2_prefetch = false;  // measured: no gain (189.4 vs 188.1 ms/batch), the weight fetch is not on the critical path. B200T5_L2PF=1: pull the next kernels' weights into L2 from the cross-attention kernel
+  bool use_2cta = true;   // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
   bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
                            // (measured: decode 201.5 -> 188.3 ms per batch); B200T5_SELF=warp selects one warp per (row, head)
+  // Cross-attention of the decode step: the bulk-copy stream kernel (attention_cross_stream.cuh; bandwidth independent
+  // of the warps resident per SM, so it survives sharing the SMs with the other chain's GEMM CTAs) or, B200T5_XATTN=ldg,
+  // the per-thread-load kernel of round 1 (attention_decode.cuh). Bit-identical results.
+  bool xattn_stream = true;
+  int xs_stages = 5;        // 8 KB ring stages per CTA (two CTAs per SM): B200T5_XS_STAGES
+  bool xs_late_pdl = true;  // release the dependent GEMM when a CTA starts its last item instead of at once: B200T5_XS_LATE_PDL
+  bool profile_xattn = false;  // b200t5_set_option("profile_xattn"): stamp every cross-attention launch inside the step graph
   int small_prio = 0;  // B200T5_PRIO: launch priority of the latency-bound decode kernels (see launch_priority())
   bool sk_on = true;
+  int sk_stages64 = 0, sk_stages128 = 0;  // pipeline stages of the split-K tiles (0 = default 4 / 3): B200T5_SK_STAGES="a,b"
   SkChoice sk_qkv{64, 2}, sk_proj{64, 4}, sk_wi{128, 2}, sk_ffo{64, 4};  // best of the B200 sweep (tools/sweep_decode.sh)
   int chains_override = 0;
   cudaStream_t chain_streams[kMaxChains] = {};
@@ -434,19 +417,8 @@ static cudaError_t run_gemm_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, co
                                cudaStream_t s, bool pdl) {
   h->launches++;
   const int split = splitk_factor(K, ch.split);
-  if (ch.bn == 128) return launch_gemm_splitk<128, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl);
-  return launch_gemm_splitk<64, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl);
-}
-
-// same, with the RMSNorm of the A operand fused in (A = raw residual stream)
-template <class Epi>
-static cudaError_t run_gemm_sk_norm(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, const CUtensorMap& tmA,
-                                    const CUtensorMap& tmB, int M, int N, int K, const typename Epi::Params& ep,
-                                    const NormA& na, cudaStream_t s, bool pdl) {
-  h->launches++;
-  const int split = splitk_factor(K, ch.split);
-  if (ch.bn == 128) return launch_gemm_splitk<128, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
-  return launch_gemm_splitk<64, Epi, true>(tmA, tmB, M, N, K, split, ep, s, pdl, na);
+  if (ch.bn == 128) return launch_gemm_splitk<128, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl, 0, h->sk_stages128);
+  return launch_gemm_splitk<64, Epi>(tmA, tmB, M, N, K, split, ep, s, pdl, 0, h->sk_stages64);
 }
 
 // Feed-forward output projection + residual. bf16 build: an ordinary 2-byte product. fp16 build: fp32 weight and
@@ -463,8 +435,8 @@ static cudaError_t run_ffo_sk(b200t5_ctx* h, const b200t5_ctx::SkChoice& ch, con
   constexpr bool tf = B200T5_F16 != 0;
   const int split = splitk_factor(h->ffo_k, ch.split, tf ? kBK / 2 : kBK);
   const int akb = tf ? h->ffo_k / 64 : 0;
-  if (ch.bn == 128) return launch_gemm_splitk<128, EpiResidual, false, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, NormA{}, akb);
-  return launch_gemm_splitk<64, EpiResidual, false, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, NormA{}, akb);
+  if (ch.bn == 128) return launch_gemm_splitk<128, EpiResidual, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, akb, h->sk_stages128);
+  return launch_gemm_splitk<64, EpiResidual, tf>(tmA, tmB, M, N, h->ffo_k, split, ep, s, pdl, akb, h->sk_stages64);
 }
 
 static cudaError_t run_rmsnorm(b200t5_ctx* h, const res_t* x, const act_t* w, act_t* y, int M, int d, float eps,
@@ -485,8 +457,6 @@ static cudaError_t init_kernel_attrs() {
   PREP(32, EpiStore) PREP(32, EpiResidual) PREP(64, EpiGeglu) PREP(128, EpiArgmax) PREP(128, EpiStoreF32)
   PREP(64, EpiStore) PREP(128, EpiStore)
 #undef PREP
-  if ((e = prepare_gemm_mcast()) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(attn_decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXtcSmemBytes)) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiStore>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiResidual>()) != cudaSuccess) return e;
   if ((e = prepare_gemm_2cta<EpiGeglu>()) != cudaSuccess) return e;
@@ -497,20 +467,16 @@ static cudaError_t init_kernel_attrs() {
   PREPSK(64, EpiQkvDecode) PREPSK(128, EpiQkvDecode) PREPSK(64, EpiGeglu) PREPSK(128, EpiGeglu)
 #undef PREPSK
   if ((e = prepare_gemm_2cta<EpiResidual, B200T5_F16 != 0>()) != cudaSuccess) return e;
-  if ((e = prepare_gemm_splitk<64, EpiResidual, false, B200T5_F16 != 0>()) != cudaSuccess) return e;
-  if ((e = prepare_gemm_splitk<128, EpiResidual, false, B200T5_F16 != 0>()) != cudaSuccess) return e;
-#define PREPSKN(BN, EPI) \
-  if ((e = prepare_gemm_splitk<BN, EPI, true>()) != cudaSuccess) return e;
-  PREPSKN(64, EpiStore) PREPSKN(128, EpiStore) PREPSKN(64, EpiQkvDecode) PREPSKN(128, EpiQkvDecode)
-  PREPSKN(64, EpiGeglu) PREPSKN(128, EpiGeglu)
-#undef PREPSKN
-  if ((e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmemBytes)) != cudaSuccess)
-    return e;
+  if ((e = prepare_gemm_splitk<64, EpiResidual, B200T5_F16 != 0>()) != cudaSuccess) return e;
+  if ((e = prepare_gemm_splitk<128, EpiResidual, B200T5_F16 != 0>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(self_attn_decode_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 kSelfWarpsPerCta * 4096 * 4)) != cudaSuccess)
     return e;
   if ((e = cudaFuncSetAttribute(encoder_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(EncTcSmem::bytes(kEncTcMaxS)))) != cudaSuccess)
+    return e;
+  if ((e = cudaFuncSetAttribute(attn_cross_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(XsSmem::bytes(kXsMaxStages, 4096)))) != cudaSuccess)
     return e;
   return cudaFuncSetAttribute(encoder_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
@@ -596,28 +562,16 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   h->use_pdl = pdl_env ? atoi(pdl_env) != 0 : true;
   const char* ea_env = getenv("B200T5_ENC_ATTN");
   h->enc_attn_tc = !(ea_env && strcmp(ea_env, "mma") == 0);
-  const char* sx_env = getenv("B200T5_SERIALIZE_XATTN");
-  if (sx_env) h->serialize_xattn = atoi(sx_env) != 0;
   if (const char* pr_env = getenv("B200T5_PRIO")) h->small_prio = atoi(pr_env);
-  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_tc = strcmp(xa_env, "tc") == 0;
   if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
-  if (const char* mc_env = getenv("B200T5_MCAST")) h->mcast = atoi(mc_env) != 0;
-  if (const char* fn_env = getenv("B200T5_FUSENORM")) h->fuse_norm = atoi(fn_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
-  if (const char* pf_env = getenv("B200T5_L2PF")) h->l2_prefetch = atoi(pf_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
-  if (const char* mg_env = getenv("B200T5_MEGA")) {
-    int v[7];
-    const int n = sscanf(mg_env, "%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
-    if (n == 1) h->mega_on = v[0] != 0;
-    if (n == 7) {
-      auto bn_ok = [](int b) { return b == 32 || b == 64 || b == 128; };
-      if (bn_ok(v[0]) && bn_ok(v[1]) && bn_ok(v[3]) && (v[4] == 64 || v[4] == 128) && bn_ok(v[5]) && v[2] >= 1 && v[6] >= 1) {
-        for (int i = 0; i < 7; ++i) h->mega_cfg[i] = v[i];
-        h->mega_on = true;
-      }
-    }
+  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "ldg") != 0;
+  if (const char* xs_env = getenv("B200T5_XS_STAGES")) {
+    const int v = atoi(xs_env);
+    if (v >= 2 && v <= kXsMaxStages) h->xs_stages = v;
   }
+  if (const char* lp_env = getenv("B200T5_XS_LATE_PDL")) h->xs_late_pdl = atoi(lp_env) != 0;
   if (const char* sk_env = getenv("B200T5_SK")) {
     int v[8];
     const int n = sscanf(sk_env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
@@ -630,12 +584,18 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
       }
     }
   }
+  if (const char* st_env = getenv("B200T5_SK_STAGES")) {
+    int a = 0, b = 0;
+    if (sscanf(st_env, "%d,%d", &a, &b) == 2) {
+      h->sk_stages64 = a;
+      h->sk_stages128 = b;
+    }
+  }
   const char* ch_env = getenv("B200T5_CHAINS");
   h->chains_override = ch_env ? atoi(ch_env) : 0;
 #if B200T5_F16
   // the fp16 build implements the default kernel set only (the measured-slower experiments and the fallbacks
   // they replace assume the bf16 contract: 2-byte residual stream, table-driven gelu)
-  h->mega_on = h->mcast = h->fuse_norm = h->xattn_tc = h->l2_prefetch = false;
   h->use_2cta = h->pack_rows = h->enc_attn_tc = true;
   if (!h->sk_on) {
     delete h;
@@ -688,8 +648,6 @@ extern "C" int b200t5_destroy(b200t5_handle h) {
     if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]);
   for (int i = 0; i <= kMaxChains; ++i)
     if (h->chain_ev[i]) cudaEventDestroy(h->chain_ev[i]);
-  for (cudaEvent_t e : h->xattn_ev)
-    if (e) cudaEventDestroy(e);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -928,17 +886,6 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     const int bn_wi = h->sk_on ? h->sk_wi.bn : 64, bn_ffo = h->sk_on ? h->sk_ffo.bn : 32;
     TRY(interleave_geglu(h, wi0, wi1, w.wi, F, d, bn_wi, &wi_rows));
     w.wi_rows = wi_rows;
-    if (h->mega_on) {
-      const int mbn = h->mega_cfg[4];
-      if (mbn == bn_wi) {
-        w.mega_wi = w.wi.p;
-        w.mega_wi_rows = wi_rows;
-      } else {
-        TRY(interleave_geglu(h, wi0, wi1, w.mega_wi_own, F, d, mbn, &w.mega_wi_rows));
-        w.mega_wi = w.mega_wi_own.p;
-      }
-      w.mega_wi_bn = mbn;
-    }
     if (!(p = take(h, key("layer.2.DenseReluDense.wo.weight"), d, F, &rc))) return rc;
     TRY(build_ffo(h, w.wff_o, key("layer.2.DenseReluDense.wo.weight"), p, d, F, &h->ffo_k));
     TMAP(h, &w.tm_qkv, w.wqkv.p, 3 * I, d, bn_qkv);
@@ -947,9 +894,6 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
     TMAP(h, &w.tm_co, w.wco.p, d, I, bn_proj);
     TMAP(h, &w.tm_wi, w.wi.p, wi_rows, d, bn_wi);
     TMAP_FFO(h, &w.tm_ffo, w.wff_o.p, d, h->ffo_k, bn_ffo);
-    TMAP(h, &w.tm16_o, w.wo.p, d, I, 16);
-    TMAP(h, &w.tm16_cq, w.wcq.p, I, d, 16);
-    TMAP(h, &w.tm16_co, w.wco.p, d, I, 16);
   }
   TMAP(h, &h->tm_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 256);
   TMAP(h, &h->tm2_crosskv, h->wcrosskv.p, static_cast<uint64_t>(c.Ld) * 2 * I, d, 128);
@@ -961,114 +905,6 @@ extern "C" int b200t5_finalize(b200t5_handle h) {
   return B200T5_OK;
 }
 
-
-// ================================================================== persistent decode kernel: host side
-// Largest k-split not above `want` that leaves every slice at least one 64-wide k-block.
-static int mega_ksplit(int K, int want) {
-  const int kblocks = (K + kBK - 1) / kBK;
-  for (int s = want < kblocks ? want : kblocks; s > 1; --s) {
-    const int per = (kblocks + s - 1) / s;
-    if ((s - 1) * per < kblocks) return s;
-  }
-  return 1;
-}
-
-static int build_mega(b200t5_ctx* h, Plan& pl) {
-  pl.mega_ok = false;
-  if (!h->mega_on) return B200T5_OK;
-  const Cfg& c = h->c;
-  const int B = pl.B, S = pl.S, T = pl.Tmax, d = c.d, I = c.I, F = c.F;
-  // shared-memory scratch of the attention phases
-  if (static_cast<size_t>(kMegaWarps) * T * 4 > kMegaScratchBytes ||
-      static_cast<size_t>(kMegaGroups) * (S + 4 * 64 + 8) * 4 > kMegaScratchBytes || d > kMegaWarps * 256)
-    return B200T5_OK;  // too long for the resident kernel: the step graph handles it
-  int occ = 0;
-  CU_OK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, decode_mega_kernel, kMegaThreads, kMegaSmemBytes));
-  int coop = 0;
-  CU_OK(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-  if (occ < 1 || !coop) return B200T5_OK;
-  const int bn_qkv = h->mega_cfg[0], bn_proj = h->mega_cfg[1], bn_cq = h->mega_cfg[3], bn_wi = h->mega_cfg[4], bn_ffo = h->mega_cfg[5];
-  const int ks_proj = mega_ksplit(I, h->mega_cfg[2]), ks_ffo = mega_ksplit(F, h->mega_cfg[6]);
-  const int nmaps = 6 * c.Ld + 4;
-  std::vector<CUtensorMap> maps(nmaps);
-  std::vector<MegaLayer> layers(c.Ld);
-  CU_OK(h, pl.mega_maps.alloc(sizeof(CUtensorMap) * nmaps));
-  CU_OK(h, pl.mega_layers.alloc(sizeof(MegaLayer) * c.Ld));
-  const int ks_max = ks_proj > ks_ffo ? ks_proj : ks_ffo;
-  CU_OK(h, pl.mega_ws.alloc(static_cast<size_t>(ks_max) * B * d * 4));
-  CU_OK(h, pl.mega_bar.alloc(256));
-  const CUtensorMap* dmaps = pl.mega_maps.as<CUtensorMap>();
-  for (int l = 0; l < c.Ld; ++l) {
-    DecLayerW& w = h->dec[l];
-    if (w.mega_wi_bn != bn_wi) return fail(h, B200T5_ESTATE, "decoder wi weights were not packed for the persistent kernel (bn_wi=%d)", bn_wi);
-    CUtensorMap* m = &maps[6 * l];
-    TMAP(h, &m[0], w.wqkv.p, 3 * I, d, bn_qkv);
-    TMAP(h, &m[1], w.wo.p, d, I, bn_proj);
-    TMAP(h, &m[2], w.wcq.p, I, d, bn_cq);
-    TMAP(h, &m[3], w.wco.p, d, I, bn_proj);
-    TMAP(h, &m[4], w.mega_wi, w.mega_wi_rows, d, bn_wi);
-    TMAP(h, &m[5], w.wff_o.p, d, F, bn_ffo);
-    MegaLayer& L = layers[l];
-    L.tm_qkv = dmaps + 6 * l;
-    L.tm_o = dmaps + 6 * l + 1;
-    L.tm_cq = dmaps + 6 * l + 2;
-    L.tm_co = dmaps + 6 * l + 3;
-    L.tm_wi = dmaps + 6 * l + 4;
-    L.tm_ffo = dmaps + 6 * l + 5;
-    L.ln0 = w.ln0.as<act_t>();
-    L.ln1 = w.ln1.as<act_t>();
-    L.ln2 = w.ln2.as<act_t>();
-    L.self_kv = pl.self_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * T);
-    L.cross_kv = pl.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S);
-    L.wi_rows = w.mega_wi_rows;
-  }
-  CUtensorMap* a = &maps[6 * c.Ld];
-  TMAP(h, &a[0], pl.dxn.p, B, d, 128);
-  TMAP(h, &a[1], pl.dctx.p, B, I, 128);
-  TMAP(h, &a[2], pl.dh.p, B, F, 128);
-  TMAP(h, &a[3], h->lm_head.p, c.V, d, 128);
-  CU_OK(h, cudaMemcpy(pl.mega_maps.p, maps.data(), sizeof(CUtensorMap) * nmaps, cudaMemcpyHostToDevice));
-  CU_OK(h, cudaMemcpy(pl.mega_layers.p, layers.data(), sizeof(MegaLayer) * c.Ld, cudaMemcpyHostToDevice));
-  MegaParams& P = pl.mega;
-  P.B = B; P.S = S; P.T = T; P.d = d; P.I = I; P.F = F; P.H = c.H; P.V = c.V; P.Ld = c.Ld;
-  P.eps = c.eps;
-  P.dx = pl.dx.as<act_t>(); P.dxn = pl.dxn.as<act_t>(); P.dq = pl.dq.as<act_t>(); P.dctx = pl.dctx.as<act_t>(); P.dh = pl.dh.as<act_t>();
-  P.ws = pl.mega_ws.as<float>();
-  P.tm_dxn = dmaps + 6 * c.Ld; P.tm_dctx = dmaps + 6 * c.Ld + 1; P.tm_dh = dmaps + 6 * c.Ld + 2; P.tm_lm = dmaps + 6 * c.Ld + 3;
-  P.layers = pl.mega_layers.as<MegaLayer>();
-  P.final_ln = h->dec_final_ln.as<act_t>(); P.E = h->shared.as<act_t>();
-  P.extent = pl.extent.as<int>(); P.key_ok = pl.key_ok.as<unsigned char>(); P.dec_bias = pl.dec_bias.as<float>();
-  P.st = pl.state.as<DecodeState>(); P.unfinished = pl.unfinished.as<int>(); P.out_ids = pl.out_ids.as<long long>();
-  P.out_len = pl.out_len.as<int>(); P.pval = pl.pval.as<float>(); P.pidx = pl.pidx.as<int>(); P.n_vtiles = pl.n_vtiles;
-  P.lut = h->gelu_lut;
-  P.bar = pl.mega_bar.as<unsigned int>();
-  P.prof = nullptr;
-  P.prof_step = -1;
-  if (const char* pe = getenv("B200T5_MEGA_PROF")) {  // diagnostic: phase timeline of one step (tools/mega_phases.py)
-    CU_OK(h, pl.mega_prof.alloc(4096 * 8));
-    CU_OK(h, cudaMemset(pl.mega_prof.p, 0, 4096 * 8));
-    P.prof = pl.mega_prof.as<long long>();
-    P.prof_step = atoi(pe);
-  }
-  P.bn_qkv = bn_qkv; P.bn_proj = bn_proj; P.ks_proj = ks_proj; P.bn_cq = bn_cq; P.bn_wi = bn_wi; P.bn_ffo = bn_ffo;
-  P.ks_ffo = ks_ffo; P.bn_lm = 128;
-  pl.mega_ok = true;
-  return B200T5_OK;
-}
-
-static int launch_mega(b200t5_ctx* h, cudaStream_t s, long long eos, long long pad, int min_new, int nsteps) {
-  Plan& p = *h->plan;
-  p.mega.eos = eos;
-  p.mega.pad = pad;
-  p.mega.min_new = min_new;
-  p.mega.nsteps = nsteps;
-  CU_OK(h, cudaMemsetAsync(p.mega_bar.p, 0, 256, s));
-  void* args[1] = {&p.mega};
-  CU_OK(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_mega_kernel), dim3(h->num_sms), dim3(kMegaThreads), args,
-                                       kMegaSmemBytes, s));
-  h->launches++;
-  return B200T5_OK;
-}
 
 // ================================================================== plans
 static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
@@ -1099,7 +935,6 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->dq.alloc(static_cast<size_t>(B) * I * 2));
   CU_OK(h, pl->dctx.alloc(static_cast<size_t>(B) * I * 2));
   CU_OK(h, pl->dh.alloc(static_cast<size_t>(B) * F * sizeof(ffh_t)));
-  CU_OK(h, pl->dss.alloc(static_cast<size_t>(B) * ((d + 31) / 32) * 4));
   CU_OK(h, pl->self_kv.alloc(static_cast<size_t>(c.Ld) * 2 * B * I * Tmax * 2));
   pl->n_vtiles = (c.V + 127) / 128;
   CU_OK(h, pl->pval.alloc(static_cast<size_t>(B) * pl->n_vtiles * 4));
@@ -1121,6 +956,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->out_row.alloc(static_cast<size_t>(B) * 4));
   CU_OK(h, pl->admit.alloc(static_cast<size_t>(3) * B * 4));
   CU_OK(h, cudaMemset(pl->pos.p, 0, pl->pos.bytes));
+  CU_OK(h, pl->xs_stamps.alloc(static_cast<size_t>(c.Ld) * kMaxChains * 2 * 8));
+  CU_OK(h, pl->xs_acc.alloc(static_cast<size_t>(c.Ld) * kMaxChains * 2 * 8));
+  CU_OK(h, cudaMemset(pl->xs_stamps.p, 0, pl->xs_stamps.bytes));
+  CU_OK(h, cudaMemset(pl->xs_acc.p, 0, pl->xs_acc.bytes));
   CU_OK(h, cudaMemset(pl->out_row.p, 0, pl->out_row.bytes));
   CU_OK(h, cudaMallocHost(&pl->h_unf, static_cast<size_t>(B) * 4));
   CU_OK(h, cudaMallocHost(&pl->h_admit, static_cast<size_t>(3) * B * 4));
@@ -1175,7 +1014,6 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
   TMAP_FFO(h, &pl->tm_hff, pl->hff.p, M, F, 128);
   TMAP(h, &pl->tm_qkv_attn, pl->qkv.p, M, 3 * I, 128);
-  TMAP(h, &pl->tm_cross_kv, pl->cross_kv.p, static_cast<uint64_t>(c.Ld) * 2 * B * H * S, 64, 128);
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
     // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
@@ -1189,13 +1027,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
       ch.b0 = static_cast<int>(static_cast<long long>(B) * i / nc);
       ch.nb = static_cast<int>(static_cast<long long>(B) * (i + 1) / nc) - ch.b0;
       TMAP(h, &ch.tm_dxn, pl->dxn.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
-      if (!B200T5_F16)  // A operand of the fused-RMSNorm experiment (bf16 build only)
-        TMAP(h, &ch.tm_dx, pl->dx.as<act_t>() + static_cast<size_t>(ch.b0) * d, ch.nb, d, 128);
       TMAP(h, &ch.tm_dctx, pl->dctx.as<act_t>() + static_cast<size_t>(ch.b0) * I, ch.nb, I, 128);
       TMAP_FFO(h, &ch.tm_dh, pl->dh.as<ffh_t>() + static_cast<size_t>(ch.b0) * F, ch.nb, F, 128);
     }
   }
-  TRY(build_mega(h, *pl));
   h->plan = std::move(pl);
   return B200T5_OK;
 }
@@ -1360,25 +1195,16 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   DecLayerW& w = h->dec[l];
   // [kv][B][H][T][64]: a row offset of b0 is a pointer offset inside each kv plane
   act_t* skv = p.self_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * T) + static_cast<size_t>(v.b0) * I * T;
-  // Fused RMSNorm: the residual GEMM that produced x left per-chunk sums of squares in `ss`; the consumer GEMM
-  // normalises its A tile in shared memory (gemm_splitk.cuh, NormA). Layer 0's x comes from the embedding
-  // gather (no producer GEMM), so its first norm stays a kernel.
-  const bool fuse = h->fuse_norm && h->sk_on;
-  const int ss_ld = (d + 31) / 32;
-  float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
-  if (!(fuse && l > 0)) CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln0.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiQkvDecode::Params ep{v.dq, skv, step, B, H, T, sstride};
-    if (fuse && l > 0)
-      CU_OK(h, run_gemm_sk_norm<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dx, w.tm_qkv, v.nb, 3 * I, d, ep,
-                                              NormA{ss, ss_ld, w.ln0.as<act_t>(), c.eps}, s, pdl));
-    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiQkvDecode>(h, h->sk_qkv, v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_qkv, v.nb, 3 * I, d, G_QKVDEC64, 1), &ep, s, pdl));
   }
   if (h->self_block)  // 4 warps per (row, head): two memory round trips whatever t is
     CU_OK(h, launch_kernel(attn_decode_kernel<true>, dim3(v.nb * H), dim3(kAttnDecThreads), T * sizeof(float), s, pdl, v.dq, skv,
                            skv + static_cast<size_t>(B) * I * T, v.dctx, H, T, nullptr, nullptr, step, p.dec_bias.as<float>(),
-                           L2Prefetch{}, sstride));
+                           XsStamps{nullptr, 0}, sstride));
   else
     CU_OK(h, launch_kernel(self_attn_decode_warp_kernel, dim3((v.nb * H + kSelfWarpsPerCta - 1) / kSelfWarpsPerCta),
                            dim3(kSelfWarpsPerCta * 32), kSelfWarpsPerCta * T * sizeof(float), s, pdl, v.dq, skv,
@@ -1387,71 +1213,50 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
     ep.round_out = l == 0;  // (fp16 build) the stream is still fp16 before the first feed-forward block
-    if (fuse) {
-      ep.ss = ss;
-      ep.ss_ld = ss_ld;
-    }
-    if (h->sk_on && h->mcast && !fuse && gemm_mcast_supports(d, I)) {
-      h->launches++;
-      CU_OK(h, launch_gemm_mcast<true>(v.ch->tm_dctx, w.tm16_o, v.nb, d, I, ep, EpiStore::Params{}, s, pdl));
-    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_o, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_o, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln1.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiStore::Params ep{v.dq, I};
-    if (fuse)
-      CU_OK(h, run_gemm_sk_norm<EpiStore>(h, h->sk_proj, v.ch->tm_dx, w.tm_cq, v.nb, I, d, ep,
-                                          NormA{ss, ss_ld, w.ln1.as<act_t>(), c.eps}, s, pdl));
-    else if (h->sk_on && h->mcast && gemm_mcast_supports(I, d)) {
-      h->launches++;
-      CU_OK(h, launch_gemm_mcast<false>(v.ch->tm_dxn, w.tm16_cq, v.nb, I, d, EpiResidual::Params{}, ep, s, pdl));
-    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiStore>(h, h->sk_proj, v.ch->tm_dxn, w.tm_cq, v.nb, I, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_cq, v.nb, I, d, G_STORE32, 1), &ep, s, pdl));
   }
   return B200T5_OK;
 }
 
-// layer l, cross-attention over the encoder keys (the HBM-streaming kernel)
-static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l, bool pdl) {
+// One cross-attention launch over rows [b0, b0 + nb) of layer l's K/V planes (`ext` / `ok` are row-b0-relative).
+// `slot` < 0: no in-situ stamps.
+static cudaError_t launch_cross_attention(b200t5_ctx* h, cudaStream_t s, bool pdl, const act_t* q, const act_t* kplane,
+                                          const act_t* vplane, act_t* ctx, int nb, const int* ext, const unsigned char* ok,
+                                          int slot) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
-  const int B = p.B, S = p.S, I = c.I, H = c.H;
+  XsStamps st{slot >= 0 && p.xs_stamps.p ? p.xs_stamps.as<unsigned long long>() : nullptr, slot >= 0 ? slot : 0};
+  if (h->xattn_stream) {
+    const int items = nb * c.H;
+    return launch_kernel(attn_cross_stream_kernel, dim3(xs_grid(items, h->num_sms)), dim3(kXsThreads),
+                         XsSmem::bytes(h->xs_stages, p.S), s, pdl, q, kplane, vplane, ctx, items, c.H, p.S, ext, ok, h->xs_stages,
+                         h->xs_late_pdl ? 1 : 0, st);
+  }
+  return launch_kernel(attn_decode_kernel<false>, dim3(nb * c.H), dim3(kAttnDecThreads), p.S * sizeof(float), s, pdl, q, kplane,
+                       vplane, ctx, c.H, p.S, ext, ok, nullptr, nullptr, st, 0);
+}
+
+// layer l, cross-attention over the encoder keys (the HBM-streaming kernel)
+static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l, int chain_index) {
+  const Cfg& c = h->c;
+  Plan& p = *h->plan;
+  const int B = p.B, S = p.S, I = c.I;
   act_t* ckv = p.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
   struct PrioGuard {
     int saved;
     PrioGuard() : saved(launch_priority()) { launch_priority() = 0; }
     ~PrioGuard() { launch_priority() = saved; }
   } guard;
-  // weights of the kernels that follow (this layer's cross-O / wi / FF-out, the next layer's QKV / O / cross-Q)
-  L2Prefetch pf{};
-  if (h->l2_prefetch) {
-    const DecLayerW& w = h->dec[l];
-    auto add = [&](int k, const DevBuf& b) {
-      pf.ptr[k] = b.p;
-      pf.bytes[k] = static_cast<unsigned int>(b.bytes);
-    };
-    add(0, w.wco);
-    add(1, w.wi);
-    add(2, w.wff_o);
-    if (l + 1 < c.Ld) {
-      const DecLayerW& n = h->dec[l + 1];
-      add(3, n.wqkv);
-      add(4, n.wo);
-      add(5, n.wcq);
-    }
-  }
-  if (h->xattn_tc && S <= kXtcMaxS) {
-    const int nitems = v.nb * H;
-    const int k_row0 = (l * 2) * B * H * S, v_row0 = (l * 2 + 1) * B * H * S;
-    CU_OK(h, launch_kernel(attn_decode_tc_kernel, dim3(nitems < h->num_sms ? nitems : h->num_sms), dim3(kXtcThreads), kXtcSmemBytes, s,
-                           pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, p.dq.as<act_t>(), p.dctx.as<act_t>(), v.b0 * H, nitems, H,
-                           S, p.live_extent.as<int>(), p.live_key_ok.as<unsigned char>(), static_cast<long long*>(nullptr)));
-  } else {
-    CU_OK(h, launch_kernel(attn_decode_kernel<false>, dim3(v.nb * H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl,
-                           v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, H, S, p.live_extent.as<int>() + v.b0,
-                           p.live_key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S, nullptr, nullptr, pf, 0));
-  }
+  CU_OK(h, launch_cross_attention(h, s, h->use_pdl, v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, v.nb,
+                                  p.live_extent.as<int>() + v.b0, p.live_key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S,
+                                  h->profile_xattn ? l * p.n_chains + chain_index : -1));
   h->launches++;
   return B200T5_OK;
 }
@@ -1463,38 +1268,20 @@ static int chain_layer_post(b200t5_ctx* h, cudaStream_t s, const ChainView& v, i
   const bool pdl = h->use_pdl;
   const int wi_tiles = (F + 31) / 32;
   DecLayerW& w = h->dec[l];
-  Plan& p = *h->plan;
-  const bool fuse = h->fuse_norm && h->sk_on;
-  const int ss_ld = (d + 31) / 32;
-  float* ss = p.dss.as<float>() + static_cast<size_t>(v.b0) * ss_ld;
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
     ep.round_out = l == 0;
-    if (fuse) {
-      ep.ss = ss;
-      ep.ss_ld = ss_ld;
-    }
-    if (h->sk_on && h->mcast && !fuse && gemm_mcast_supports(d, I)) {
-      h->launches++;
-      CU_OK(h, launch_gemm_mcast<true>(v.ch->tm_dctx, w.tm16_co, v.nb, d, I, ep, EpiStore::Params{}, s, pdl));
-    } else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiResidual>(h, h->sk_proj, v.ch->tm_dctx, w.tm_co, v.nb, d, I, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dctx, w.tm_co, v.nb, d, I, G_RES32, 1), &ep, s, pdl));
   }
-  if (!fuse) CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
+  CU_OK(h, run_rmsnorm(h, v.dx, w.ln2.as<act_t>(), v.dxn, v.nb, d, c.eps, s, pdl));
   {
     EpiGeglu::Params ep{v.dh, F, h->gelu_lut};
-    if (fuse)
-      CU_OK(h, run_gemm_sk_norm<EpiGeglu>(h, h->sk_wi, v.ch->tm_dx, w.tm_wi, v.nb, w.wi_rows, d, ep,
-                                          NormA{ss, ss_ld, w.ln2.as<act_t>(), c.eps}, s, pdl));
-    else if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
+    if (h->sk_on) CU_OK(h, run_gemm_sk<EpiGeglu>(h, h->sk_wi, v.ch->tm_dxn, w.tm_wi, v.nb, w.wi_rows, d, ep, s, pdl));
     else CU_OK(h, run_gemm(h, mk(v.ch->tm_dxn, w.tm_wi, v.nb, wi_tiles * 64, d, G_GEGLU64, 1), &ep, s, pdl));
   }
   {
     EpiResidual::Params ep{v.dx, v.dx, d};
-    if (fuse) {  // consumed by the next layer's QKV GEMM
-      ep.ss = ss;
-      ep.ss_ld = ss_ld;
-    }
     ep.round_acc = B200T5_F16 ? 0 : 1;  // fp16 build: `wo` is an fp32 Linear, its output is not rounded
     ep.round_out = B200T5_F16 ? 0 : 1;
     if (h->sk_on) CU_OK(h, run_ffo_sk(h, h->sk_ffo, v.ch->tm_dh, w.tm_ffo, v.nb, d, ep, s, pdl));
@@ -1533,22 +1320,8 @@ static int chain_head(b200t5_ctx* h, cudaStream_t s, const ChainView& v, float* 
   return B200T5_OK;
 }
 
-static cudaEvent_t xattn_event(b200t5_ctx* h, size_t k) {
-  while (h->xattn_ev.size() <= k) {
-    cudaEvent_t e = nullptr;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    h->xattn_ev.push_back(e);
-  }
-  return h->xattn_ev[k];
-}
-
-// All chains of one step. `fork` (used while capturing the step graph) runs the chains on their
-// own streams and, in addition, threads ONE dependency through every cross-attention kernel in
-// round-robin order (layer-major, chain-minor). Without it the chains run in lock-step: all of
-// them stream KV at the same moment (sharing HBM four ways) and all of them sit in their
-// latency-bound GEMM phases at the same moment (HBM idle). With it at most one chain streams KV at
-// a time at full bandwidth while the other chains' GEMM phases fill the gaps - a software pipeline
-// across chains that needs no kernel changes, only graph edges.
+// All chains of one step. `fork` (used while capturing the step graph) runs the chains on their own streams, so
+// that one chain's HBM-streaming cross-attention overlaps the other chain's latency-bound GEMM phases.
 static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logits_out, int ldl, long long eos,
                            long long pad, int min_new) {
   Plan& p = *h->plan;
@@ -1566,15 +1339,10 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
     for (int i = 1; i < nc; ++i) cs[i] = h->chain_streams[i];
     CU_OK(h, cudaEventRecord(h->chain_ev[0], s));
     for (int i = 1; i < nc; ++i) CU_OK(h, cudaStreamWaitEvent(cs[i], h->chain_ev[0], 0));
-    size_t k = 0;
     for (int l = 0; l < c.Ld; ++l) {
       for (int i = 0; i < nc; ++i) {
         TRY(chain_layer_pre(h, cs[i], v[i], l));
-        if (h->serialize_xattn && k > 0) CU_OK(h, cudaStreamWaitEvent(cs[i], xattn_event(h, k - 1), 0));
-        // after an event wait the kernel has two predecessors: launch it without the PDL attribute
-        TRY(chain_layer_cross(h, cs[i], v[i], l, h->use_pdl && !(h->serialize_xattn && k > 0)));
-        if (h->serialize_xattn) CU_OK(h, cudaEventRecord(xattn_event(h, k), cs[i]));
-        ++k;
+        TRY(chain_layer_cross(h, cs[i], v[i], l, i));
         TRY(chain_layer_post(h, cs[i], v[i], l));
       }
     }
@@ -1589,14 +1357,17 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
     for (int i = 0; i < nc; ++i) {
       for (int l = 0; l < c.Ld; ++l) {
         TRY(chain_layer_pre(h, s, v[i], l));
-        TRY(chain_layer_cross(h, s, v[i], l, h->use_pdl));
+        TRY(chain_layer_cross(h, s, v[i], l, i));
         TRY(chain_layer_post(h, s, v[i], l));
       }
       TRY(chain_head(h, s, v[i], logits_out, ldl, eos, pad, min_new));
     }
   }
   // joins every chain; not PDL-launched so that it sees all of them complete
-  CU_OK(h, launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, s, false, p.state.as<DecodeState>()));
+  CU_OK(h, launch_kernel(advance_step_kernel, dim3(1), dim3(32), 0, s, false, p.state.as<DecodeState>(),
+                         h->profile_xattn ? p.xs_stamps.as<unsigned long long>() : static_cast<unsigned long long*>(nullptr),
+                         h->profile_xattn ? p.xs_acc.as<unsigned long long>() : static_cast<unsigned long long*>(nullptr),
+                         c.Ld * nc));
   h->launches++;
   return B200T5_OK;
 }
@@ -1677,8 +1448,7 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   TRY(ensure_plan(h, B, S, T));
   Plan& p = *h->plan;
   p.stream_mode = false;
-  const bool mega = p.mega_ok;
-  if (!mega) TRY(ensure_graph(h, eos, pad, min_new));
+  TRY(ensure_graph(h, eos, pad, min_new));
   h->launches = 0;
   CU_OK(h, cudaEventRecord(h->ev[0], s));
   TRY(run_encoder(h, ids, mask, s));
@@ -1691,22 +1461,7 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   CU_OK(h, cudaGetLastError());
   CU_OK(h, cudaEventRecord(h->ev[1], s));
   int steps = 0;
-  if (mega) {
-    // the whole greedy loop, EOS early exit included, is one resident kernel
-    TRY(launch_mega(h, s, eos, pad, min_new, T));
-    CU_OK(h, cudaMemcpyAsync(p.h_state, p.state.p, sizeof(DecodeState), cudaMemcpyDeviceToHost, s));
-    steps = -1;  // read back from the device state in get_stats
-    if (p.mega.prof) {
-      std::vector<long long> st(4096);
-      CU_OK(h, cudaStreamSynchronize(s));
-      CU_OK(h, cudaMemcpy(st.data(), p.mega_prof.p, 4096 * 8, cudaMemcpyDeviceToHost));
-      // pairs (before barrier, after barrier): phase k runs from after[k-1] to before[k]
-      fprintf(stderr, "MEGA_PROF step %d (SM clocks of CTA 0):", p.mega.prof_step);
-      for (int i = 0; i < 4096 && st[i]; ++i) fprintf(stderr, " %lld", st[i] - st[0]);
-      fprintf(stderr, "\n");
-    }
-  }
-  for (int t = 0; t < T && !mega; ++t) {
+  for (int t = 0; t < T; ++t) {
     if (t % kStepsPerGraph == 0 && t + kStepsPerGraph <= T && poll % kStepsPerGraph == 0) {
       // eight steps in one launch; the early-exit poll below happens on the same boundaries
       CU_OK(h, cudaGraphLaunch(p.gexec8, s));
@@ -1911,7 +1666,6 @@ extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
   CU_OK(h, cudaEventSynchronize(h->ev[2]));
   CU_OK(h, cudaEventElapsedTime(&out->encoder_ms, h->ev[0], h->ev[1]));
   CU_OK(h, cudaEventElapsedTime(&out->decode_ms, h->ev[1], h->ev[2]));
-  if (h->last_steps < 0) h->last_steps = h->plan->h_state->step;  // persistent kernel: steps were counted on the device
   out->decode_steps = h->last_steps;
   out->kernel_launches = h->launches;
   fill_stats_model(h, h->last_steps);
@@ -1920,69 +1674,117 @@ extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
   return B200T5_OK;
 }
 
-// ================================================================== measurement hook
-// Times the roofline-setting kernel (cross-attention decode, D7) alone, on the cross-KV arena
-// of the last generate call: `reps` sweeps over all decoder layers (each launch streams a
-// different 2*B*I*S*2-byte slab, far larger than L2), CUDA events on the launching stream.
-extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_per_launch, double* bytes_per_launch,
-                                       void* stream) {
+// ================================================================== measurement hooks
+// Times the roofline-setting kernel (cross-attention decode, D7) alone, on the cross-KV arena of the last
+// generate call, in launches of `rows_per_launch` batch rows (0 = the whole batch; the step graph launches one
+// chain's rows at a time): `reps` sweeps over all decoder layers (every launch streams a different slab, the sweep
+// is far larger than L2), CUDA events on the launching stream. A microbenchmark: back-to-back launches with nothing
+// else on the GPU. What the launches cost INSIDE the step graph is b200t5_get_xattn_profile's figure.
+extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_launch, float* avg_ms_per_launch,
+                                       double* bytes_per_launch, void* stream) {
   if (!h || !avg_ms_per_launch || !bytes_per_launch || reps < 1) return fail(h, B200T5_EINVAL, "bad argument");
   if (!h->plan) return fail(h, B200T5_ESTATE, "no plan: call generate first");
   CU_OK(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan& p = *h->plan;
   const Cfg& c = h->c;
+  const int rows = rows_per_launch > 0 && rows_per_launch < p.B ? rows_per_launch : p.B;
   const size_t cross_layer = static_cast<size_t>(2) * p.B * c.I * p.S;
-  long long* xtc_prof = nullptr;  // B200T5_XTC_PROF=1: per-item stamps of the tensor-core kernel (diagnostic)
-  DevBuf prof_buf;
-  if (getenv("B200T5_XTC_PROF") && h->xattn_tc) {
-    CU_OK(h, prof_buf.alloc(32 * 8 * 8));
-    CU_OK(h, cudaMemset(prof_buf.p, 0, 32 * 8 * 8));
-    xtc_prof = prof_buf.as<long long>();
-  }
+  int launches = 0;
+  cudaError_t le = cudaSuccess;
   auto sweep = [&]() {
+    launches = 0;
     for (int l = 0; l < c.Ld; ++l) {
-      act_t* ckv = p.cross_kv.as<act_t>() + l * cross_layer;
-      if (h->xattn_tc && p.S <= kXtcMaxS) {
-        const int nitems = p.B * c.H;
-        attn_decode_tc_kernel<<<nitems < h->num_sms ? nitems : h->num_sms, kXtcThreads, kXtcSmemBytes, s>>>(
-            p.tm_cross_kv, p.tm_cross_kv, (l * 2) * nitems * p.S, (l * 2 + 1) * nitems * p.S, p.dq.as<act_t>(), p.dctx.as<act_t>(), 0,
-            nitems, c.H, p.S, p.extent.as<int>(), p.key_ok.as<unsigned char>(), xtc_prof);
-        continue;
+      for (int b0 = 0; b0 < p.B; b0 += rows) {
+        const int nb = p.B - b0 < rows ? p.B - b0 : rows;
+        act_t* ckv = p.cross_kv.as<act_t>() + l * cross_layer + static_cast<size_t>(b0) * c.I * p.S;
+        cudaError_t e = launch_cross_attention(h, s, false, p.dq.as<act_t>() + static_cast<size_t>(b0) * c.I, ckv,
+                                               ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<act_t>() + static_cast<size_t>(b0) * c.I,
+                                               nb, p.extent.as<int>() + b0, p.key_ok.as<unsigned char>() + static_cast<size_t>(b0) * p.S, -1);
+        if (e != cudaSuccess) le = e;
+        ++launches;
       }
-      attn_decode_kernel<false><<<p.B * c.H, kAttnDecThreads, p.S * sizeof(float), s>>>(
-          p.dq.as<act_t>(), ckv, ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<act_t>(), c.H, p.S,
-          p.extent.as<int>(), p.key_ok.as<unsigned char>(), nullptr, nullptr, L2Prefetch{});
     }
   };
   sweep();  // warm-up
-  cudaEvent_t e0, e1;
+  CU_OK(h, le);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  struct EvGuard {
+    cudaEvent_t &a, &b;
+    ~EvGuard() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } guard{e0, e1};
   CU_OK(h, cudaEventCreate(&e0));
   CU_OK(h, cudaEventCreate(&e1));
   CU_OK(h, cudaEventRecord(e0, s));
   for (int r = 0; r < reps; ++r) sweep();
   CU_OK(h, cudaEventRecord(e1, s));
   CU_OK(h, cudaEventSynchronize(e1));
+  CU_OK(h, le);
   float ms = 0.f;
   CU_OK(h, cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   CU_OK(h, cudaGetLastError());
-  *avg_ms_per_launch = ms / (static_cast<float>(reps) * c.Ld);
-  if (xtc_prof) {
-    long long st[32 * 8];
-    CU_OK(h, cudaMemcpy(st, prof_buf.p, sizeof(st), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "XTC_PROF (SM clocks, CTA 0 softmax thread 0; per item: start, s_full, scores read, softmax, p_free, p staged, epilogue):\n");
-    for (int i = 0; i < 24 && st[i * 8]; ++i)
-      fprintf(stderr, "  item %2d: +%lld | %lld %lld %lld %lld %lld %lld\n", i, i ? st[i * 8] - st[(i - 1) * 8] : 0LL, st[i * 8 + 1] - st[i * 8],
-              st[i * 8 + 2] - st[i * 8 + 1], st[i * 8 + 3] - st[i * 8 + 2], st[i * 8 + 4] - st[i * 8 + 3], st[i * 8 + 5] - st[i * 8 + 4],
-              st[i * 8 + 6] - st[i * 8 + 5]);
-  }
+  *avg_ms_per_launch = ms / (static_cast<float>(reps) * launches);
   std::vector<int> ext(p.B);
   CU_OK(h, cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost));
   double sum_s = 0;
   for (int v : ext) sum_s += v;
-  *bytes_per_launch = 2.0 * 2.0 * c.I * sum_s;  // K and V rows of every attended key, bf16
+  // K and V rows of every attended key, bf16; averaged over the launches of one layer
+  *bytes_per_launch = 2.0 * 2.0 * c.I * sum_s / (static_cast<double>(launches) / c.Ld);
+  return B200T5_OK;
+}
+
+// Runtime options (what the B200T5_* environment variables set at create time, changeable on a live handle so
+// that a sweep does not reload the model). Any change drops the execution plan: the next call re-captures the
+// step graph. Names: "chains" (row-chains per step, 0 = default), "xattn" (1 = bulk-copy stream kernel, 0 = the
+// per-thread-load kernel), "xattn_stages", "xattn_late_pdl", "pdl", "profile_xattn" (1 = every cross-attention launch
+// inside the step graph stamps %globaltimer; read with b200t5_get_xattn_profile; off in any timed region).
+extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
+  if (!h || !name) return fail(h, B200T5_EINVAL, "null argument");
+  const std::string n(name);
+  if (n == "chains") h->chains_override = value < 0 ? 0 : value;
+  else if (n == "xattn") h->xattn_stream = value != 0;
+  else if (n == "xattn_stages") {
+    if (value < 2 || value > kXsMaxStages) return fail(h, B200T5_EINVAL, "xattn_stages must be in [2, %d]", kXsMaxStages);
+    h->xs_stages = value;
+  } else if (n == "xattn_late_pdl") h->xs_late_pdl = value != 0;
+  else if (n == "pdl") h->use_pdl = value != 0;
+  else if (n == "sk_stages64") h->sk_stages64 = value;
+  else if (n == "sk_stages128") h->sk_stages128 = value;
+  else if (n == "profile_xattn") h->profile_xattn = value != 0;
+  else return fail(h, B200T5_EINVAL, "unknown option '%s'", name);
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  h->plan.reset();
+  return B200T5_OK;
+}
+
+// Cross-attention launches of the step graph since profiling was switched on: their mean in-situ duration
+// (first CTA's start to last CTA's end, %globaltimer), the number of launches seen, and the algorithmic bytes of
+// one launch at the moment of the call (K and V rows of the keys the live rows still attend).
+extern "C" int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch) {
+  if (!h || !avg_us_per_launch || !launches || !bytes_per_launch) return fail(h, B200T5_EINVAL, "null argument");
+  if (!h->plan || !h->profile_xattn) return fail(h, B200T5_ESTATE, "profiling is off (b200t5_set_option(h, \"profile_xattn\", 1), then generate)");
+  CU_OK(h, cudaSetDevice(h->device));
+  CU_OK(h, cudaDeviceSynchronize());
+  Plan& p = *h->plan;
+  const int n = h->c.Ld * p.n_chains;
+  std::vector<unsigned long long> acc(static_cast<size_t>(n) * 2);
+  CU_OK(h, cudaMemcpy(acc.data(), p.xs_acc.p, acc.size() * 8, cudaMemcpyDeviceToHost));
+  unsigned long long ns = 0, cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    ns += acc[2 * i];
+    cnt += acc[2 * i + 1];
+  }
+  *avg_us_per_launch = cnt ? static_cast<double>(ns) / static_cast<double>(cnt) / 1e3 : 0.0;
+  *launches = static_cast<int64_t>(cnt);
+  std::vector<int> ext(p.B);
+  CU_OK(h, cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost));
+  double sum_s = 0;
+  for (int v : ext) sum_s += v;
+  *bytes_per_launch = 2.0 * 2.0 * h->c.I * sum_s / p.n_chains;
   return B200T5_OK;
 }
 
@@ -2098,6 +1900,42 @@ extern "C" int b200t5_test_gemm(int device, const void* A, const void* W, void* 
 #endif
 }
 
+// lm_head + fused arg-max + greedy bookkeeping exactly as chain_head launches them (EpiArgmax partials per 128-column
+// tile, finalize_step_kernel's lowest-index reduction). W doubles as the embedding table of the gather.
+extern "C" int b200t5_test_lm_argmax(int device, const void* x, const void* W, int M, int V, int K, int step, int eos,
+                                     int min_new, int64_t* tokens, void* stream) {
+  const int sms = hook_device(device);
+  if (sms < 0) return sms;
+  if (!x || !W || !tokens || M < 1 || V < 2 || K % 8 || step < 0) return fail(nullptr, B200T5_EINVAL, "test_lm_argmax: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, x, M, K, 128) || !make_tmap(&tb, W, V, K, 128)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
+  const int n_tiles = (V + 127) / 128, out_ld = step + 2;
+  DevBuf pval, pidx, st, unf, out, len, xn, ext;
+  if (pval.alloc(static_cast<size_t>(M) * n_tiles * 4) != cudaSuccess || pidx.alloc(static_cast<size_t>(M) * n_tiles * 4) != cudaSuccess ||
+      st.alloc(sizeof(DecodeState)) != cudaSuccess || unf.alloc(static_cast<size_t>(M) * 4) != cudaSuccess ||
+      out.alloc(static_cast<size_t>(M) * out_ld * 8) != cudaSuccess || len.alloc(static_cast<size_t>(M) * 4) != cudaSuccess ||
+      xn.alloc(static_cast<size_t>(M) * K * sizeof(res_t)) != cudaSuccess || ext.alloc(static_cast<size_t>(M) * 4) != cudaSuccess)
+    return fail(nullptr, B200T5_ENOMEM, "test_lm_argmax: allocation failed");
+  b200t5_ctx dummy;
+  dummy.num_sms = sms;
+  decode_init_kernel<<<M, 128, 0, s>>>(st.as<DecodeState>(), unf.as<int>(), out.as<long long>(), len.as<int>(), out_ld, M, 0, 0,
+                                       static_cast<const act_t*>(W), xn.as<res_t>(), K);
+  set_state_kernel<<<1, 1, 0, s>>>(st.as<DecodeState>(), step);
+  EpiArgmax::Params ep{pval.as<float>(), pidx.as<int>(), n_tiles, &st.as<DecodeState>()->step, eos, min_new, 0};
+  cudaError_t e = run_gemm(&dummy, mk(ta, tb, M, V, K, G_ARGMAX128, 1), &ep, s, false);
+  if (e == cudaSuccess)
+    e = launch_kernel(finalize_step_kernel, dim3(M), dim3(128), 0, s, false, pval.as<float>(), pidx.as<int>(), n_tiles, st.as<DecodeState>(),
+                      unf.as<int>(), out.as<long long>(), len.as<int>(), out_ld, static_cast<long long>(-1), static_cast<long long>(0),
+                      static_cast<const act_t*>(W), xn.as<res_t>(), K, ext.as<int>(), static_cast<int*>(nullptr),
+                      static_cast<const int*>(nullptr), 1 << 30);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(tokens, 8, out.as<long long>() + step + 1, static_cast<size_t>(out_ld) * 8, 8, M, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_lm_argmax: %s", cudaGetErrorString(e));
+  return B200T5_OK;
+}
+
 extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn,
                                        int split, int mode, int pow_mode, void* aux, int Tmax, int step, void* stream) {
 #if B200T5_F16
@@ -2107,19 +1945,8 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
   if (sms < 0) return sms;
   if (K % 8) return fail(nullptr, B200T5_EINVAL, "K must be a multiple of 8");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (bn == 16) {  // A-multicast kernel (gemm_mcast.cuh): modes 0 (store) and 1 (+= residual), split ignored
-    if (!gemm_mcast_supports(N, K) || (mode != 0 && mode != 1))
-      return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk(bn=16): needs K <= 768, N %% 64 == 0, mode 0 or 1");
-    CUtensorMap ta, tb;
-    if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, 16)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
-    act_t* Cb = static_cast<act_t*>(C);
-    cudaError_t e = mode == 0 ? launch_gemm_mcast<false>(ta, tb, M, N, K, EpiResidual::Params{}, EpiStore::Params{Cb, N}, s, false)
-                              : launch_gemm_mcast<true>(ta, tb, M, N, K, EpiResidual::Params{Cb, Cb, N}, EpiStore::Params{}, s, false);
-    if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_gemm_splitk(bn=16, mode=%d): %s", mode, cudaGetErrorString(e));
-    return B200T5_OK;
-  }
   if ((bn != 64 && bn != 128) || (split != 1 && split != 2 && split != 4 && split != 8))
-    return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bn in {16,64,128}, split in {1,2,4,8}");
+    return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: bn in {64,128}, split in {1,2,4,8}");
   CUtensorMap ta, tb;
   if (!make_tmap(&ta, A, M, K, 128) || !make_tmap(&tb, W, N, K, bn)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
   b200t5_ctx dummy;
@@ -2133,19 +1960,7 @@ extern "C" int b200t5_test_gemm_splitk(int device, const void* A, const void* W,
     e = run_gemm_sk<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
   } else if (mode == 1) {
     EpiResidual::Params ep{Cb, Cb, N};
-    if (aux) {  // also emit the per-chunk sums of squares: float [M][ceil(N/32)]
-      ep.ss = static_cast<float*>(aux);
-      ep.ss_ld = (N + 31) / 32;
-    }
     e = run_gemm_sk<EpiResidual>(&dummy, ch, ta, tb, M, N, K, ep, s, false);
-  } else if (mode == 5) {
-    // fused RMSNorm on A: aux = float ss[M][ceil(K/32)] followed by bf16 w[K]; eps 1e-6
-    if (!aux) return fail(nullptr, B200T5_EINVAL, "test_gemm_splitk: mode 5 needs aux");
-    const int ss_ld = (K + 31) / 32;
-    const float* ssp = static_cast<const float*>(aux);
-    const act_t* wln = reinterpret_cast<const act_t*>(ssp + static_cast<size_t>(M) * ss_ld);
-    EpiStore::Params ep{Cb, N};
-    e = run_gemm_sk_norm<EpiStore>(&dummy, ch, ta, tb, M, N, K, ep, NormA{ssp, ss_ld, wln, 1e-6f}, s, false);
   } else if (mode == 2) {
     GeluLut lut;
     int lrc = ensure_gelu_lut(nullptr, pow_mode, &lut);
@@ -2194,8 +2009,8 @@ extern "C" int b200t5_test_ffo(int device, const void* A, const void* W, void* R
     e = launch_gemm_2cta<EpiResidual, true>(ta, tb, M, N, 2 * Fp, ep, sms, s, Fp / 32);
   } else {
     const int sp = splitk_factor(2 * Fp, split, kBK / 2);
-    e = bn == 128 ? launch_gemm_splitk<128, EpiResidual, false, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, NormA{}, Fp / 32)
-                  : launch_gemm_splitk<64, EpiResidual, false, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, NormA{}, Fp / 32);
+    e = bn == 128 ? launch_gemm_splitk<128, EpiResidual, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, Fp / 32)
+                  : launch_gemm_splitk<64, EpiResidual, true>(ta, tb, M, N, 2 * Fp, sp, ep, s, false, Fp / 32);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "test_ffo: %s", cudaGetErrorString(e));
@@ -2233,18 +2048,17 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
         static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx),
         B * H, H, Tk, &st.as<DecodeState>()->step, dist_bias);
     cudaStreamSynchronize(s);
-  } else if (self == 2) {  // cross-attention on the tensor cores (attention_decode_tc.cuh)
-    if (Tk > kXtcMaxS) return fail(nullptr, B200T5_EINVAL, "attn_decode(tc): Tk <= %d", kXtcMaxS);
-    CUtensorMap tk, tv;
-    if (!make_tmap(&tk, K, static_cast<uint64_t>(B) * H * Tk, 64, 128) || !make_tmap(&tv, V, static_cast<uint64_t>(B) * H * Tk, 64, 128))
-      return fail(nullptr, B200T5_ECUDA, "%s", g_err);
-    const int nitems = B * H;
-    attn_decode_tc_kernel<<<nitems < sms ? nitems : sms, kXtcThreads, kXtcSmemBytes, s>>>(
-        tk, tv, 0, 0, static_cast<const act_t*>(q), static_cast<act_t*>(ctx), 0, nitems, H, Tk, extent, key_ok);
+  } else if (self == 2) {  // the bulk-copy stream kernel (attention_cross_stream.cuh); `step` = ring stages (0: 5)
+    const int stages = step > 0 ? step : 5;
+    if (stages < 2 || stages > kXsMaxStages || Tk > 4096) return fail(nullptr, B200T5_EINVAL, "attn_decode(stream): 2 <= stages <= %d, Tk <= 4096", kXsMaxStages);
+    const int items = B * H;
+    attn_cross_stream_kernel<<<xs_grid(items, sms), kXsThreads, XsSmem::bytes(stages, Tk), s>>>(
+        static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), items, H, Tk,
+        extent, key_ok, stages, 1, XsStamps{nullptr, 0});
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
         static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), H,
-        Tk, extent, key_ok, nullptr, nullptr, L2Prefetch{});
+        Tk, extent, key_ok, nullptr, nullptr, XsStamps{nullptr, 0});
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "attn_decode: %s", cudaGetErrorString(e));

@@ -356,10 +356,24 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
   for (int i = threadIdx.x; i < d / 8; i += blockDim.x) store_res8_from_act(dst + i * 8, src[i]);
 }
 
-__global__ void advance_step_kernel(DecodeState* st) {
+// End of a step (joins every chain). With in-situ profiling on, fold the cross-attention launch stamps of this
+// step ({min start, max end} per launch, attention_decode.cuh: XsStamps) into {sum of durations in ns, launches}.
+__global__ void advance_step_kernel(DecodeState* st, unsigned long long* __restrict__ stamps,
+                                    unsigned long long* __restrict__ acc, int n_slots) {
   pdl_launch_dependents();
   pdl_wait();
-  st->step += 1;
+  if (threadIdx.x == 0) st->step += 1;
+  if (stamps != nullptr) {
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+      const unsigned long long t0 = stamps[2 * i], t1 = stamps[2 * i + 1];
+      if (t1 > t0 && t0 != 0 && t0 != ~0ull) {  // (slots start zeroed: the first step after a plan is built is skipped)
+        acc[2 * i] += t1 - t0;
+        acc[2 * i + 1] += 1;
+      }
+      stamps[2 * i] = ~0ull;
+      stamps[2 * i + 1] = 0;
+    }
+  }
 }
 
 // teacher forcing (test hook): overwrite the next decoder input with a given token

@@ -12,16 +12,20 @@
 // depend on the previous kernel and are requested BEFORE griddepcontrol.wait), warp 1 = TMEM
 // owner + tcgen05.mma issuer, warps 2..5 = epilogue. After its MMAs complete each CTA holds a
 // 128 x BN fp32 partial tile in TMEM. Reduce-scatter by ROWS: rank r of the cluster owns tile
-// rows [r*128/S, (r+1)*128/S); every epilogue thread (= one tile row) sends its row to the
-// owner's `red` buffer slot [src rank][row] with st.shared::cluster, a cluster barrier
-// (release/acquire) publishes the writes, and the owner sums the S partials in rank order
-// (deterministic) and feeds 32-column chunks to the same epilogue functors the persistent GEMM
-// uses (gemm.cuh), so the T5 rounding contract is shared.
-// (Measured alternative: st.async with a receiver-side mbarrier instead of the release fence +
-// cluster barrier - the fence/barrier pair is ~30 % of this kernel's stall samples - was slower,
-// 194.8 vs 188.3 ms per batch: thousands of 16-byte complete_tx updates serialise on the barrier; staging
-// the rows locally and moving them with one cp.async.bulk (shared::cta -> shared::cluster) per destination
-// rank was slower too, 195.3 ms: the extra staging pass and the exit barrier outweigh the saved fence.)
+// rows [r*128/S, (r+1)*128/S); every epilogue thread (= one tile row) whose row belongs to ANOTHER
+// rank sends it to that rank's `red` buffer with st.shared::cluster, a cluster barrier
+// (release/acquire) publishes the writes, and the owner's thread of each row sums the S partials in
+// rank order (deterministic; its own partial comes straight from TMEM) and feeds 32-column chunks to
+// the same epilogue functors the persistent GEMM uses (gemm.cuh), so the T5 rounding contract is shared.
+//
+// Footprint: the `red` buffer holds only the (S-1)/S of the tile that arrives from peers and the number of
+// pipeline stages is a launch parameter, so that a CTA (~115-140 KB) fits on an SM next to the two resident CTAs
+// of the other row-chain's cross-attention stream (attention_cross_stream.cuh).
+// (Measured alternatives, round 1: st.async with a receiver-side mbarrier instead of the release fence +
+// cluster barrier, 194.8 vs 188.3 ms per batch; staging the rows locally and moving them with one
+// cp.async.bulk per destination rank, 195.3 ms; normalising the A tile in shared memory instead of a separate
+// RMSNorm kernel, 201.1 vs 189.1 ms; an A-multicast kernel without reduction, 201.4 vs 191.0 ms -
+// profiles/decode_trace_r1.md.)
 #pragma once
 #include "gemm.cuh"
 
@@ -29,6 +33,7 @@ namespace b200 {
 
 constexpr int kSkThreads = 192;
 constexpr int kSkMaxSplit = 8;
+constexpr int kSkMaxStages = 4;
 
 template <int BN>
 struct SkCfg {
@@ -36,10 +41,14 @@ struct SkCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 64 ? 4 : 3;
+  static constexpr int kDefaultStages = BN == 64 ? 4 : 3;
   static constexpr int kRedLd = BN + 4;  // floats; +4 keeps the per-row v4 stores of a warp conflict-free
-  static constexpr int kRedBytes = kBM * kRedLd * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRedBytes + kEpiSmemBytes;
+  // rows received from the S - 1 peers: (S - 1) * 128 / S
+  static constexpr int red_bytes(int split) { return (split - 1) * (kBM / split) * kRedLd * 4; }
+  static constexpr int smem_bytes(int stages, int split) {
+    return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + red_bytes(split) + kEpiSmemBytes;
+  }
+  static constexpr int kMaxSmemBytes = smem_bytes(kSkMaxStages, kSkMaxSplit);
 };
 
 // ---------------------------------------------------------------- cluster PTX
@@ -65,46 +74,44 @@ DEVINL void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uin
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Optional fused T5LayerNorm on the A operand (kNormA): A is the RAW residual stream x and the tile the tensor
-// core consumes is xn = bf16(w * bf16(x * rstd)) (modeling_t5.py:55-68), produced in place in shared memory by
-// the four epilogue warps - idle during the main loop - between the TMA completion and the MMA (one tile row
-// per thread, 16-byte units in the 128-B swizzle). rstd comes from per-(row, 32-column chunk) sums of squares
-// that the residual epilogue of the PREVIOUS GEMM left in `ss` (EpiResidual::Params::ss), added in a fixed
-// order. This removes a separate RMSNorm launch before the QKV, cross-Q and wi products of every decoder
-// layer - but measured on B200 it LOSES (201.1 vs 189.1 ms per batch): the partial-sum fetch and the
-// TMA -> transform -> MMA serialisation add more to each GEMM's critical path than the PDL-overlapped norm
-// kernel costs. Kept as an opt-in (B200T5_FUSENORM=1) with its parity test.
-struct NormA {
-  const float* ss;            // [M][ss_ld] partial sums of squares of x
-  int ss_ld;                  // = d / 32
-  const act_t* w;     // [K] layer-norm weight
-  float eps;
-};
+DEVINL void add32(uint32_t (&acc)[32], const uint32_t (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(x[j]));
+}
+DEVINL void add32_smem(uint32_t (&acc)[32], const float* src) {
+  const float4* r4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 a = r4[v];
+    acc[4 * v] = __float_as_uint(__uint_as_float(acc[4 * v]) + a.x);
+    acc[4 * v + 1] = __float_as_uint(__uint_as_float(acc[4 * v + 1]) + a.y);
+    acc[4 * v + 2] = __float_as_uint(__uint_as_float(acc[4 * v + 2]) + a.z);
+    acc[4 * v + 3] = __float_as_uint(__uint_as_float(acc[4 * v + 3]) + a.w);
+  }
+}
 
 // grid = (S, tiles_n, tiles_m), cluster = (S, 1, 1); S in {1,2,4,8} divides 128.
 // kTf32 / a_kblocks: as in gemm_2cta.cuh (fp32 operands consumed as tf32, W' = [W_hi | W_lo], A walked twice).
-template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
+template <int BN, class Epi, bool kTf32 = false>
 __global__ void __launch_bounds__(kSkThreads, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                   int K, typename Epi::Params ep, const NormA na, int a_kblocks) {
+                   int K, typename Epi::Params ep, int a_kblocks, int stages) {
   using Cfg = SkCfg<BN>;
   constexpr int kbk = kTf32 ? kBK / 2 : kBK;  // elements per k-block (128 bytes)
-  static_assert(!(kNormA && kTf32), "the fused RMSNorm transforms 2-byte A tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * Cfg::kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::kStages;
-  uint64_t* tfull = bars + 2 * Cfg::kStages;
-  uint64_t* ready = tfull + 1;  // [stages] kNormA: the A tile of the stage has been normalised in place
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + Cfg::kStages);
-  float* red = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
-  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(red) + Cfg::kRedBytes;
+  uint64_t* empty = bars + kSkMaxStages;
+  uint64_t* tfull = bars + 2 * kSkMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  float* red = reinterpret_cast<float*>(smem + stages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = static_cast<int>(cluster_nctarank());
   const int rank = static_cast<int>(cluster_ctarank());
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(red) + Cfg::red_bytes(S);
   const int n_tile = blockIdx.y, m_tile = blockIdx.z;
   const int kblocks = (K + kbk - 1) / kbk;
   if (a_kblocks <= 0) a_kblocks = kblocks;
@@ -122,10 +129,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < Cfg::kStages; ++i) {
+      for (int i = 0; i < stages; ++i) {
         mbar_init(&full[i], 1);
         mbar_init(&empty[i], 1);
-        mbar_init(&ready[i], 128);
       }
       mbar_init(tfull, 1);
       mbar_fence_init();
@@ -141,7 +147,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int first = nkb < Cfg::kStages ? nkb : Cfg::kStages;
+      const int first = nkb < stages ? nkb : stages;
       // weights first: they never depend on the previous kernel
       for (int i = 0; i < first; ++i) {
         uint8_t* sA = smem + i * Cfg::kStageBytes;
@@ -150,15 +156,15 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       pdl_wait();
       for (int i = 0; i < first; ++i) tma_load_2d(smem + i * Cfg::kStageBytes, &tmA, &full[i], ((kb0 + i) % a_kblocks) * kbk, m0);
-      int stage = first == Cfg::kStages ? 0 : first;
-      uint32_t phase = first == Cfg::kStages ? 1u : 0u;
+      int stage = first == stages ? 0 : first;
+      uint32_t phase = first == stages ? 1u : 0u;
       for (int i = first; i < nkb; ++i) {
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
         tma_load_2d(sA, &tmA, &full[stage], ((kb0 + i) % a_kblocks) * kbk, m0);
         tma_load_2d(sA + Cfg::kABytes, &tmB, &full[stage], (kb0 + i) * kbk, n0t);
-        if (++stage == Cfg::kStages) {
+        if (++stage == stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -175,7 +181,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(kNormA ? &ready[stage] : &full[stage], phase);
+        mbar_wait(&full[stage], phase);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t a_desc = make_desc_sw128_kmajor(a_addr);
@@ -190,7 +196,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
-        if (++stage == Cfg::kStages) {
+        if (++stage == stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -201,6 +207,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     cluster_wait_acquire();    // #1
     cluster_arrive_release();  // #2
     cluster_wait_acquire();
+    // the owners' epilogue threads still read their own partials from TMEM after barrier #2
+    asm volatile("bar.sync 3, %0;" ::"r"(5 * 32) : "memory");
     tc_fence_after_sync();
     tmem_dealloc<BN>(tmem_base);
   } else {
@@ -209,68 +217,26 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                      // tile row held by this thread
     const int rows_per = kBM / S;
+    const int owner = row / rows_per;                   // rank that reduces this row
+    const int rl = row - owner * rows_per;              // its index among the owner's rows
+    const bool mine = owner == rank;
+    const int m = m0 + row;
     if constexpr (Epi::kPaired) Epi::prologue(ep, epi_smem, et);  // gelu table; overlaps the main loop
     constexpr int kChunks = Epi::kPaired ? BN / 64 : BN / 32;
-    const int items = rows_per * kChunks;
     pdl_wait();
-    if constexpr (kNormA) {
-      // this thread's tile row: 1/rms from the previous epilogue's partial sums, then normalise stage by stage
-      const int m = m0 + row;
-      float ssum = 0.f;
-      if (m < M) {
-        const float* sp = na.ss + static_cast<size_t>(m) * na.ss_ld;
-        for (int c = 0; c < na.ss_ld; ++c) ssum += sp[c];  // fixed order: deterministic
-      }
-      const float inv = rsqrtf(ssum / static_cast<float>(K) + na.eps);  // the normalised width is this GEMM's K
-      int st = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full[st], ph);
-        const uint32_t rbase = smem_u32(smem + st * Cfg::kStageBytes) + row * 128;
-        const int k0 = (kb0 + i) * kBK;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t addr = rbase + ((u ^ (row & 7)) << 4);  // 128-B swizzle: 16-B unit u of row r sits at u ^ (r & 7)
-          uint4 v;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-          const int k = k0 + u * 8;
-          const uint4 wv = k + 8 <= K ? *reinterpret_cast<const uint4*>(na.w + k) : make_uint4(0, 0, 0, 0);
-          const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
-          const uint32_t wsv[4] = {wv.x, wv.y, wv.z, wv.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = act_round(act_lo(xs[j]) * inv);
-            const float b = act_round(act_hi(xs[j]) * inv);
-            o[j] = pack_act2(act_lo(wsv[j]) * a, act_hi(wsv[j]) * b);
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
-        mbar_arrive(&ready[st]);
-        if (++st == Cfg::kStages) {
-          st = 0;
-          ph ^= 1u;
-        }
-      }
-    }
-    // the first work item's accumulator-independent operands (residual row) are fetched now
+    // the first chunk's accumulator-independent operands (residual row) are fetched now
     typename Epi::ChunkPre pre0;
-    {
-      const int rl = et / kChunks, c = et - rl * kChunks;
-      const int m = m0 + rank * rows_per + rl;
-      if constexpr (!Epi::kPaired) {
-        if (et < items && m < M && n0t + c * 32 < N) Epi::chunk_pre(ep, m, n0t + c * 32, N, pre0);
-      }
+    if constexpr (!Epi::kPaired) {
+      if (mine && m < M && n0t < N) Epi::chunk_pre(ep, m, n0t, N, pre0);
     }
     mbar_wait(tfull, 0);
     tc_fence_after_sync();
     cluster_wait_acquire();  // #1: every CTA of the cluster is running, its `red` buffer may be written
-    {
-      const int dst_rank = row / rows_per;
-      const int slot = rank * rows_per + (row - dst_rank * rows_per);
-      const uint32_t dst = mapa_shared(smem_u32(red + static_cast<size_t>(slot) * Cfg::kRedLd), static_cast<uint32_t>(dst_rank));
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (!mine) {
+      // slot = [source index among the owner's S - 1 peers, in rank order][row of the owner]
+      const int src_idx = rank < owner ? rank : rank - 1;
+      const uint32_t dst = mapa_shared(smem_u32(red + static_cast<size_t>(src_idx * rows_per + rl) * Cfg::kRedLd), static_cast<uint32_t>(owner));
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t acc[32];
@@ -284,67 +250,67 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_before_sync();
     cluster_arrive_release();  // #2: partials published
     cluster_wait_acquire();
+    if (mine && m < M) {
+      // partial sums added in rank order, starting from zero (the order the round-1 kernel used: results are
+      // bit-identical to it whatever the split)
 #pragma unroll 1
-    for (int it = et; it < items; it += 128) {
-      const int rl = it / kChunks, c = it - rl * kChunks;
-      const int m = m0 + rank * rows_per + rl;
-      if (m >= M) continue;
-      if constexpr (Epi::kPaired) {
-        constexpr int HALF = BN / 2;
-        const int f0 = n_tile * HALF + c * 32;
-        if (f0 >= ep.F) continue;
-        uint32_t g[32], u[32];
+      for (int c = 0; c < kChunks; ++c) {
+        if constexpr (Epi::kPaired) {
+          constexpr int HALF = BN / 2;
+          const int f0 = n_tile * HALF + c * 32;
+          if (f0 >= ep.F) continue;
+          uint32_t g[32], u[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = u[j] = 0u;
-        for (int src = 0; src < S; ++src) {
-          const float4* r4 = reinterpret_cast<const float4*>(red + static_cast<size_t>(src * rows_per + rl) * Cfg::kRedLd + c * 32);
-          const float4* u4 = reinterpret_cast<const float4*>(red + static_cast<size_t>(src * rows_per + rl) * Cfg::kRedLd + HALF + c * 32);
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 a = r4[v], b = u4[v];
-            g[4 * v] = __float_as_uint(__uint_as_float(g[4 * v]) + a.x);
-            g[4 * v + 1] = __float_as_uint(__uint_as_float(g[4 * v + 1]) + a.y);
-            g[4 * v + 2] = __float_as_uint(__uint_as_float(g[4 * v + 2]) + a.z);
-            g[4 * v + 3] = __float_as_uint(__uint_as_float(g[4 * v + 3]) + a.w);
-            u[4 * v] = __float_as_uint(__uint_as_float(u[4 * v]) + b.x);
-            u[4 * v + 1] = __float_as_uint(__uint_as_float(u[4 * v + 1]) + b.y);
-            u[4 * v + 2] = __float_as_uint(__uint_as_float(u[4 * v + 2]) + b.z);
-            u[4 * v + 3] = __float_as_uint(__uint_as_float(u[4 * v + 3]) + b.w);
+          for (int j = 0; j < 32; ++j) g[j] = u[j] = 0u;
+          for (int src = 0; src < S; ++src) {
+            if (src == rank) {
+              uint32_t tg[32], tu[32];
+              tmem_ld_32x32(taddr + c * 32, tg);
+              tmem_ld_32x32(taddr + HALF + c * 32, tu);
+              tmem_ld_wait();
+              add32(g, tg);
+              add32(u, tu);
+            } else {
+              const float* base = red + static_cast<size_t>((src < rank ? src : src - 1) * rows_per + rl) * Cfg::kRedLd;
+              add32_smem(g, base + c * 32);
+              add32_smem(u, base + HALF + c * 32);
+            }
           }
-        }
-        Epi::chunk2(ep, g, u, m, f0, epi_smem);
-      } else {
-        const int n0 = n0t + c * 32;
-        if (n0 >= N) continue;
-        typename Epi::ChunkPre pre;
-        if (it == et) pre = pre0;
-        else Epi::chunk_pre(ep, m, n0, N, pre);
-        uint32_t acc[32];
+          Epi::chunk2(ep, g, u, m, f0, epi_smem);
+        } else {
+          const int n0 = n0t + c * 32;
+          if (n0 >= N) continue;
+          typename Epi::ChunkPre pre;
+          if (c == 0) pre = pre0;
+          else Epi::chunk_pre(ep, m, n0, N, pre);
+          uint32_t acc[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0u;
-        for (int src = 0; src < S; ++src) {
-          const float4* r4 = reinterpret_cast<const float4*>(red + static_cast<size_t>(src * rows_per + rl) * Cfg::kRedLd + c * 32);
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 a = r4[v];
-            acc[4 * v] = __float_as_uint(__uint_as_float(acc[4 * v]) + a.x);
-            acc[4 * v + 1] = __float_as_uint(__uint_as_float(acc[4 * v + 1]) + a.y);
-            acc[4 * v + 2] = __float_as_uint(__uint_as_float(acc[4 * v + 2]) + a.z);
-            acc[4 * v + 3] = __float_as_uint(__uint_as_float(acc[4 * v + 3]) + a.w);
+          for (int j = 0; j < 32; ++j) acc[j] = 0u;
+          for (int src = 0; src < S; ++src) {
+            if (src == rank) {
+              uint32_t t[32];
+              tmem_ld_32x32(taddr + c * 32, t);
+              tmem_ld_wait();
+              add32(acc, t);
+            } else {
+              add32_smem(acc, red + static_cast<size_t>((src < rank ? src : src - 1) * rows_per + rl) * Cfg::kRedLd + c * 32);
+            }
           }
+          Epi::chunk(ep, acc, m, n0, N, epi_smem, pre);
         }
-        Epi::chunk(ep, acc, m, n0, N, epi_smem, pre);
       }
     }
+    tc_fence_before_sync();
+    asm volatile("bar.sync 3, %0;" ::"r"(5 * 32) : "memory");  // TMEM may be released (warp 1)
   }
 }
 
-template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
+template <int BN, class Epi, bool kTf32 = false>
 cudaError_t prepare_gemm_splitk() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SkCfg<BN>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SkCfg<BN>::kMaxSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return cudaFuncSetAttribute(gemm_splitk_kernel<BN, Epi, kTf32>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 // Largest split in {8,4,2,1} not above `want` that leaves every rank at least one k-block.
@@ -357,15 +323,16 @@ inline int splitk_factor(int K, int want, int kbk = kBK) {
   return 1;
 }
 
-template <int BN, class Epi, bool kNormA = false, bool kTf32 = false>
+// stages: 0 = the tile's default (4 for BN = 64, 3 for BN = 128), otherwise 2..4
+template <int BN, class Epi, bool kTf32 = false>
 cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int split,
-                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl, const NormA& norm = NormA{},
-                               int a_kblocks = 0) {
+                               const typename Epi::Params& ep, cudaStream_t stream, bool pdl, int a_kblocks = 0, int stages = 0) {
   using Cfg = SkCfg<BN>;
+  if (stages < 2 || stages > kSkMaxStages) stages = Cfg::kDefaultStages;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(split, (N + BN - 1) / BN, (M + kBM - 1) / kBM);
   cfg.blockDim = dim3(kSkThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages, split);
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int na = 0;
@@ -386,7 +353,7 @@ cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, i
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi, kNormA, kTf32>, tmA, tmB, M, N, K, ep, norm, a_kblocks);
+  return cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<BN, Epi, kTf32>, tmA, tmB, M, N, K, ep, a_kblocks, stages);
 }
 
 }  // namespace b200

@@ -27,6 +27,7 @@ import torch
 from . import _lib
 from .synth import read_safetensors
 
+_POOL_MAX_S = 512  # the slot pool admits prompts through the packed tcgen05 encoder (csrc: kEncTcMaxS)
 _HF_DEFAULT_MAX_LENGTH = 20  # GenerationConfig default the notebook's single-prompt cell relies on (NB:577)
 
 _IGNORED_WEIGHTS = ("decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight",)
@@ -227,9 +228,12 @@ class B200T5ForConditionalGeneration:
             raise ValueError("input_ids is required")
         if do_sample or (num_beams is not None and num_beams != 1):
             raise NotImplementedError("only greedy decoding (do_sample=False, num_beams=1) is implemented")
-        for k in ("temperature", "top_k", "top_p", "repetition_penalty", "no_repeat_ngram_size", "num_return_sequences",
-                  "logits_processor", "stopping_criteria", "forced_bos_token_id", "decoder_input_ids"):
-            if unused.get(k) not in (None, 1, 1.0):
+        for k in ("temperature", "top_k", "top_p", "repetition_penalty", "no_repeat_ngram_size", "num_return_sequences"):
+            v = unused.get(k)
+            if v is not None and not (isinstance(v, (int, float)) and v == 1):
+                raise NotImplementedError(f"generate({k}=...) is not supported by the B200 path")
+        for k in ("logits_processor", "stopping_criteria", "forced_bos_token_id", "decoder_input_ids", "encoder_outputs"):
+            if unused.get(k) is not None:  # (may be tensors: no truth-value tests)
                 raise NotImplementedError(f"generate({k}=...) is not supported by the B200 path")
         gp = self._gen_params(max_new_tokens, max_length, min_new_tokens, min_length, eos_token_id, pad_token_id,
                               decoder_start_token_id, poll_interval)
@@ -237,17 +241,48 @@ class B200T5ForConditionalGeneration:
         if ids.dim() != 2:
             raise ValueError(f"input_ids must be [batch, seq], got {tuple(ids.shape)}")
         B, S = ids.shape
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.config.vocab_size):
-            raise IndexError("input_ids contain token ids outside [0, vocab_size)")
+        if ids.numel():
+            lo, hi = torch.aminmax(ids)  # one kernel, one synchronisation
+            if bool(((lo < 0) | (hi >= self.config.vocab_size)).item()):
+                raise IndexError("input_ids contain token ids outside [0, vocab_size)")
         mask = None
         if attention_mask is not None:
             mask = torch.as_tensor(attention_mask).to(device=self._device, dtype=torch.long).contiguous()
             if mask.shape != ids.shape:
                 raise ValueError("attention_mask shape must match input_ids")
-        if B > self.pool_size and os.environ.get("B200T5_STREAM", "1") != "0":
-            # more rows than one pool of decode slots: continuous batching, same tokens row for row
-            out_np, _ = self.generate_stream(ids.cpu().numpy(), None if mask is None else mask.cpu().numpy(), _gen_params=gp)
-            return torch.from_numpy(out_np).to(self._device)
+        else:
+            mask = self._infer_attention_mask(ids, gp)
+        if B > self.pool_size:
+            if S <= _POOL_MAX_S and os.environ.get("B200T5_STREAM", "1") != "0":
+                # more rows than one pool of decode slots: continuous batching, same tokens row for row. The pool
+                # admits prompts from host memory as slots free up (its entry point takes host buffers).
+                out_np, _ = self.generate_stream(ids.cpu().numpy(), None if mask is None else mask.cpu().numpy(), _gen_params=gp)
+                return torch.from_numpy(out_np).to(self._device)
+            # prompts the slot pool cannot take (it needs the packed tcgen05 encoder, S <= 512): static batches
+            outs = [self._generate_static(ids[lo:lo + self.pool_size], None if mask is None else mask[lo:lo + self.pool_size], gp)
+                    for lo in range(0, B, self.pool_size)]
+            width = max(o.shape[1] for o in outs)
+            pad = gp.pad_token_id if gp.pad_token_id >= 0 else self.generation_config.pad_token_id
+            return torch.cat([torch.nn.functional.pad(o, (0, width - o.shape[1]), value=pad) for o in outs], dim=0)
+        return self._generate_static(ids, mask, gp)
+
+    def _infer_attention_mask(self, ids: torch.Tensor, gp) -> Optional[torch.Tensor]:
+        """GenerationMixin._prepare_attention_mask_for_generation (transformers generation/utils.py): without an
+        attention_mask the pad positions are masked when the pad token occurs in the inputs and is not the EOS
+        token; otherwise every position is attended (None = all ones for the library)."""
+        pad = gp.pad_token_id if gp.pad_token_id >= 0 else self.generation_config.pad_token_id
+        eos = gp.eos_token_id if gp.eos_token_id >= 0 else self.generation_config.eos_token_id
+        if pad is None or pad == eos:
+            return None
+        is_pad = ids == pad
+        if not bool(is_pad.any().item()):
+            return None
+        return (~is_pad).to(torch.long).contiguous()
+
+    def _generate_static(self, ids: torch.Tensor, mask: Optional[torch.Tensor], gp) -> torch.Tensor:
+        B, S = ids.shape
+        ids = ids.contiguous()
+        mask = None if mask is None else mask.contiguous()
         T = gp.max_new_tokens
         with torch.cuda.device(self._index):
             out = torch.empty((B, T + 1), dtype=torch.long, device=self._device)
@@ -259,6 +294,13 @@ class B200T5ForConditionalGeneration:
             steps = int(lens.max().item())  # synchronises; HF returns exactly the steps it ran
         return out[:, : steps + 1]
 
+    def _infer_mask_np(self, ids: np.ndarray, gp) -> Optional[np.ndarray]:
+        pad = gp.pad_token_id if gp.pad_token_id >= 0 else self.generation_config.pad_token_id
+        eos = gp.eos_token_id if gp.eos_token_id >= 0 else self.generation_config.eos_token_id
+        if pad is None or pad == eos or not (ids == pad).any():
+            return None
+        return np.ascontiguousarray(ids != pad, dtype=np.int64)
+
     def generate_host(self, input_ids: np.ndarray, attention_mask: Optional[np.ndarray] = None, **kw):
         """numpy in / numpy out through b200t5_generate_host (the foreign-host entry point):
         H2D copy, generation, D2H copy and synchronisation all happen inside the library."""
@@ -267,7 +309,7 @@ class B200T5ForConditionalGeneration:
                               kw.get("decoder_start_token_id"), kw.get("poll_interval", 8))
         ids = np.ascontiguousarray(input_ids, dtype=np.int64)
         B, S = ids.shape
-        mask = None if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
+        mask = self._infer_mask_np(ids, gp) if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
         out = np.empty((B, gp.max_new_tokens + 1), dtype=np.int64)
         lens = np.empty((B,), dtype=np.int32)
         _chk(self, self._lib.b200t5_generate_host(
@@ -291,7 +333,7 @@ class B200T5ForConditionalGeneration:
         N, S = ids.shape
         if ids.size and (int(ids.min()) < 0 or int(ids.max()) >= self.config.vocab_size):
             raise IndexError("input_ids contain token ids outside [0, vocab_size)")
-        mask = None if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
+        mask = self._infer_mask_np(ids, gp) if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
         if mask is not None and mask.shape != ids.shape:
             raise ValueError("attention_mask shape must match input_ids")
         out = np.empty((N, gp.max_new_tokens + 1), dtype=np.int64)
@@ -308,14 +350,25 @@ class B200T5ForConditionalGeneration:
         _chk(self, self._lib.b200t5_get_stats(self._h, C.byref(s)), self._h)
         return {k: getattr(s, k) for k, _ in _lib.Stats._fields_}
 
-    def bench_cross_attention(self, reps: int = 5) -> Dict[str, float]:
-        """Average launch time of the cross-attention decode kernel on the last call's KV arena."""
+    def bench_cross_attention(self, reps: int = 5, rows_per_launch: int = 0) -> Dict[str, float]:
+        """Average launch time of the cross-attention decode kernel ALONE on the last call's KV arena, in launches of
+        `rows_per_launch` rows (0 = the whole batch). A microbenchmark; `xattn_profile` is the in-situ figure."""
         ms, nbytes = C.c_float(), C.c_double()
         with torch.cuda.device(self._index):
             stream = torch.cuda.current_stream(self._device)
-            _chk(self, self._lib.b200t5_bench_cross_attn(self._h, reps, C.byref(ms), C.byref(nbytes),
+            _chk(self, self._lib.b200t5_bench_cross_attn(self._h, reps, int(rows_per_launch), C.byref(ms), C.byref(nbytes),
                                                          C.c_void_p(stream.cuda_stream)), self._h)
         return {"ms_per_launch": ms.value, "bytes_per_launch": nbytes.value}
+
+    def set_option(self, name: str, value: int) -> None:
+        """Runtime knob of the library (include/b200t5.h: b200t5_set_option); drops the execution plan."""
+        _chk(self, self._lib.b200t5_set_option(self._h, name.encode(), int(value)), self._h)
+
+    def xattn_profile(self) -> Dict[str, float]:
+        """In-situ duration of the cross-attention launches of the step graph since set_option("profile_xattn", 1)."""
+        us, n, nbytes = C.c_double(), C.c_int64(), C.c_double()
+        _chk(self, self._lib.b200t5_get_xattn_profile(self._h, C.byref(us), C.byref(n), C.byref(nbytes)), self._h)
+        return {"us_per_launch": us.value, "launches": int(n.value), "bytes_per_launch": nbytes.value}
 
     # ------------------------------------------------------------------ parity hooks (tests)
     @torch.no_grad()

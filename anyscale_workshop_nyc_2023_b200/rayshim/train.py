@@ -195,6 +195,9 @@ class BatchPredictor:
         self._predictor_kwargs = predictor_kwargs
         self._override_preprocessor = None
         self._worker: Optional[_ScoringWorker] = None  # kept warm between predict() calls
+        self._worker_key = None
+        self._pool = None                              # likewise the one-process-per-GPU pool
+        self._pool_key = None
 
     @classmethod
     def from_checkpoint(cls, checkpoint: Any, predictor_cls: Type[Predictor], **kwargs: Any) -> "BatchPredictor":
@@ -205,6 +208,19 @@ class BatchPredictor:
 
     def set_preprocessor(self, preprocessor) -> None:
         self._override_preprocessor = preprocessor
+
+    def shutdown(self) -> None:
+        """Stop the scoring processes (they otherwise live as long as this BatchPredictor, like Ray's actor pool
+        lives for the duration of the job)."""
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.shutdown()
+        except Exception:  # noqa: BLE001
+            pass
 
     def predict(self, data: Dataset, *, feature_columns: Optional[List[str]] = None,
                 keep_columns: Optional[List[str]] = None, batch_size: int = 4096, min_scoring_workers: int = 1,
@@ -217,42 +233,46 @@ class BatchPredictor:
         sig = inspect.signature(self._predictor_cls.from_checkpoint)
         if num_gpus > 0 and "use_gpu" in sig.parameters and "use_gpu" not in kwargs:
             kwargs["use_gpu"] = True
-        prep = self.get_preprocessor()
-        override_prep = False
-        stream_prep = None
-        if prep is not None and num_gpus > 0 and separate_gpu_stage:
-            # CPU stage of its own, as AIR does before a GPU stage. With one scoring worker it is STREAMED: a
-            # producer thread tokenises block i+1 while the GPU generates block i (the library call releases the
-            # GIL), instead of materialising the whole tokenised dataset first. Tokenisation is row-wise, so the
-            # results are the same whichever way the rows are blocked.
-            override_prep = True
-            if pipeline_cpu_stage and (max_scoring_workers == 1 or _visible_gpus() <= 1):
-                stream_prep = prep
-            else:
-                data = prep.transform(data)
         batches = list(data.iter_batches(batch_size=batch_size, batch_format="pandas"))
+        # how many scoring workers: decided BEFORE the CPU stage is placed (it runs inside them)
         n_workers = 1
         if num_gpus > 0:
-            import torch
-
-            visible = torch.cuda.device_count() if torch.cuda.is_available() else 0
+            visible = _visible_gpus()
             cap = max_scoring_workers or visible
             n_workers = max(min(cap, visible // max(num_gpus, 1), len(batches)), 1)
-            n_workers = max(n_workers, min(min_scoring_workers, max(visible, 1)))
+            n_workers = max(n_workers, min(min_scoring_workers, max(visible // max(num_gpus, 1), 1)))
+        prep = self.get_preprocessor()
+        # With a GPU stage the preprocessor is a CPU stage of its own, as in AIR - but STREAMED inside each scoring
+        # worker: a producer thread tokenises block i+1 while the GPU generates block i (the library call releases
+        # the GIL). Tokenisation is row-wise, so the results do not depend on how the rows are blocked.
+        # pipeline_cpu_stage=False: materialise the whole tokenised dataset first (what AIR 2.3 does).
+        override_prep = prep is not None and num_gpus > 0 and separate_gpu_stage
+        worker_prep = None
+        if override_prep:
+            if pipeline_cpu_stage:
+                worker_prep = prep
+            else:
+                batches = list(prep.transform(data).iter_batches(batch_size=batch_size, batch_format="pandas"))
+        key = (id(self._checkpoint), override_prep, repr(sorted(kwargs.items(), key=lambda kv: kv[0])))
         if n_workers <= 1:
-            if self._worker is None or self._worker_key != (id(self._checkpoint), override_prep, repr(sorted(kwargs))):
+            if self._worker is None or self._worker_key != key:
                 self._worker = _ScoringWorker(self._checkpoint, self._predictor_cls, kwargs, override_prep)
-                self._worker_key = (id(self._checkpoint), override_prep, repr(sorted(kwargs)))
-            if stream_prep is not None:
+                self._worker_key = key
+            if worker_prep is not None:
                 outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs)
-                        for b in _prefetch(batches, lambda raw: _to_pandas(_to_block(stream_prep.transform_batch(raw))))]
+                        for b in _prefetch(batches, lambda raw: _to_pandas(_to_block(worker_prep.transform_batch(raw))))]
             else:
                 outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs) for b in batches]
         else:
             from .pool import GpuWorkerPool
 
-            with GpuWorkerPool(n_workers, self._checkpoint, self._predictor_cls, kwargs, override_prep) as pool:
-                outs = pool.map_ordered(batches, feature_columns, keep_columns, predict_kwargs)
+            pool_key = key + (n_workers, num_gpus)
+            if self._pool is None or self._pool.closed or self._pool_key != pool_key:
+                self.shutdown()
+                self._pool = GpuWorkerPool(n_workers, self._checkpoint, self._predictor_cls, kwargs, override_prep,
+                                           gpus_per_worker=num_gpus)
+                self._pool_key = pool_key
+            outs = self._pool.map_ordered(batches, feature_columns, keep_columns, predict_kwargs, prep=worker_prep)
         return Dataset([_to_block(o) for o in outs])
 
 

@@ -9,10 +9,15 @@ seeded random FLAN-T5-base weights: no checkpoints or datasets exist offline).
   e2e        the same metric through the reference-facing plug-in call
              HuggingFaceModelPredictor._predict_numpy(host numpy batch) -> DataFrame of strings:
              pinned H2D copy + generate + D2H copy + detokenisation inside the timed region
-  roofline   cross-attention decode kernel (85 % of decode bytes): algorithmic bytes / launch
-             duration vs the measured HBM copy bandwidth; plus the whole decode loop's figure
-  cpu_baseline  the reference's CPU path (HF eager fp32 generate through the same predictor)
-             on a bounded sample of the same workload, host cores stated
+  roofline   cross-attention decode kernel (85 % of decode bytes): algorithmic bytes / launch duration
+             INSIDE the step graph (per-chain launches, %globaltimer stamps taken in an extra untimed
+             pass) vs the measured HBM copy bandwidth; the isolated-launch figure, the whole decode
+             loop's, the encoder's and the whole batch's fractions beside it
+  parity     a sample of the LAST TIMED batch's rows against transformers' eager model in the same
+             dtype on this GPU (outside the timed region)
+  incumbent_hf_gpu  transformers eager bf16 generate on this GPU, same workload, same run
+  cpu_baseline  the reference's CPU path (HF eager fp32 generate through the predictor plug-in),
+             one 64-prompt batch of the same workload, thread count chosen by a 3-point sweep
 
 python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
 python bench.py --impl reference ...                     (reference arm: the CPU path only)
@@ -49,9 +54,11 @@ def parse_args():
     ap.add_argument("--lengths", default="full", choices=["full", "alpaca", "uniform"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="numerics contract: bf16 (headline) or the notebook's literal torch_dtype=float16 (fp32 wo, fp32 residual stream)")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="prompts in the CPU-baseline sample")
-    ap.add_argument("--cpu-timeout", type=int, default=240, help="seconds allowed for the in-run CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="prompts per CPU step (one batch of this size)")
+    ap.add_argument("--cpu-timeout", type=int, default=420, help="seconds allowed for the in-run CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hf-gpu-batches", type=int, default=2, help="timed 256-prompt batches of the HF-eager-on-GPU incumbent (0 = skip)")
+    ap.add_argument("--parity-rows", type=int, default=16, help="rows of the last timed batch checked against HF on this GPU (0 = skip)")
     return ap.parse_args()
 
 
@@ -134,31 +141,56 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU path (reference arm / baseline)
-def run_cpu_path(a, steps: int, warmup: int, sample: int):
-    """The reference's own CPU implementation of the path: the predictor plug-in driving
-    transformers' T5ForConditionalGeneration.generate (eager, fp32) on the host cores, on a
-    bounded sample (`sample` prompts per step) of the same workload. Returns tokens/s."""
-    import numpy as np
+def _cpu_predictor(a):
+    """HF eager fp32 model behind the predictor plug-in: the reference's OWN predictor.py when its checkout is
+    present (kind "reference"), this package's mirror of it otherwise (kind "port"; the arithmetic is the genuine
+    dependency either way)."""
     import torch
-
-    from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_token_batch
-    from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir
-    from oracle.hf_anchor import load_hf_model
-    from anyscale_workshop_nyc_2023_b200.predictor import HuggingFaceModelPredictor
     from transformers import T5Tokenizer
 
-    # eager generate is ~4k tiny ATen ops per decode step: beyond a few dozen threads the
-    # per-op fork/join cost dominates, so the intra-op pool is capped (the count used is reported)
-    cores = min(effective_cores(), int(os.environ.get("B200T5_CPU_THREADS", "32")))
-    torch.set_num_threads(cores)
-    log(f"cpu path: {cores} torch threads (host reports {os.cpu_count()} cpus), {sample} prompts/step")
-    spec = SPECS[a.model]
+    from anyscale_workshop_nyc_2023_b200 import refsource
+    from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir
+    from oracle.hf_anchor import load_hf_model
+
     ckpt = checkpoint_dir(a.model, seed=0)
     model = load_hf_model(ckpt, dtype=torch.float32, device="cpu")
     tok = T5Tokenizer.from_pretrained(str(ckpt))
-    pred = HuggingFaceModelPredictor(model, tokenizer=tok)
+    ref = refsource.load_reference_predictor_module()
+    if ref is not None:
+        return ref.HuggingFaceModelPredictor(model, tokenizer=tok), "reference"
+    from anyscale_workshop_nyc_2023_b200.predictor import HuggingFaceModelPredictor
+
+    return HuggingFaceModelPredictor(model, tokenizer=tok), "port"
+
+
+def run_cpu_path(a, steps: int, warmup: int, sample: int):
+    """The reference's CPU implementation of the path on the host cores: `steps` predictor calls, each ONE batch of
+    `sample` prompts of the same workload. The intra-op thread count is chosen by a 3-point sweep on a short probe
+    (eager generate is ~4k small ATen ops per decode step: more threads is not monotonically faster). Returns tokens/s."""
+    import torch
+
+    from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_token_batch
+
+    spec = SPECS[a.model]
+    cores = effective_cores()
+    pred, kind = _cpu_predictor(a)
     ids0, mask0 = synthetic_token_batch(1, 16, spec.vocab_size, seed=1, lengths="full")
     pred._predict_numpy({"input_ids": ids0, "attention_mask": mask0}, max_new_tokens=2)  # lazy-init costs, untimed
+    sweep = {}
+    forced = os.environ.get("B200T5_CPU_THREADS")
+    cands = [int(forced)] if forced else sorted({max(cores // 4, 1), max(cores // 2, 1), cores})
+    pids, pmask = synthetic_token_batch(sample, a.seq, spec.vocab_size, seed=999, lengths=a.lengths)
+    probe_new = 8
+    for n in cands:
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        pred._predict_numpy({"input_ids": pids, "attention_mask": pmask, "labels": pids.copy()},
+                            max_new_tokens=probe_new, min_new_tokens=probe_new)
+        sweep[n] = time.perf_counter() - t0
+        log(f"cpu path: thread sweep {n} threads -> {sweep[n]:.2f} s for {sample} prompts x {probe_new} tokens")
+    threads = min(sweep, key=sweep.get)
+    torch.set_num_threads(threads)
+    log(f"cpu path [{kind}]: {threads} torch threads of {cores} usable (host reports {os.cpu_count()} cpus), {sample} prompts/step")
     times = []
     for s in range(warmup + steps):
         ids, mask = synthetic_token_batch(sample, a.seq, spec.vocab_size, seed=1000 + s, lengths=a.lengths)
@@ -172,10 +204,13 @@ def run_cpu_path(a, steps: int, warmup: int, sample: int):
             times.append(dt)
     total = sum(times)
     toks = steps * sample * a.new
-    return {"value": toks / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample} prompts/step x {steps} steps of the same {a.seq}->{a.new} workload, HF transformers "
-                      f"eager fp32 generate via the predictor plug-in, torch threads={cores}",
-            "prompts_per_s": steps * sample / total, "ms_per_step": 1e3 * total / steps}
+    return {"value": toks / total, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{steps} step(s) x one batch of {sample} prompts of the same {a.seq}->{a.new} workload, HF transformers eager "
+                      f"fp32 generate via {'the reference predictor.py' if kind == 'reference' else 'the predictor plug-in mirror'}, "
+                      f"torch threads={threads} (3-point sweep {dict((k, round(v, 2)) for k, v in sweep.items())} s per probe; "
+                      f"{cores} usable cores)",
+            "prompts_per_s": steps * sample / total, "ms_per_step": 1e3 * total / steps,
+            "thread_sweep_s": {str(k): v for k, v in sweep.items()}}
 
 
 def main_reference(a):
@@ -184,18 +219,86 @@ def main_reference(a):
         return 0
     steps = max(a.steps, 1)
     warm = min(a.warmup, 1)  # CPU steps are seconds long; at most one warm-up pass
-    base = run_cpu_path(a, steps, warm, a.cpu_sample)
+    # bounded: one 64-prompt batch per step for short runs, smaller batches when the driver asks for many steps
+    sample = a.cpu_sample if steps <= 3 else max(8, min(a.cpu_sample, 16))
+    base = run_cpu_path(a, steps, warm, sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sampled_prompts_per_step": a.cpu_sample},
-        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": workload_name(a), "sampled_prompts_per_step": sample},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "thread_sweep_s")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "prompts_per_s": base["prompts_per_s"],
     }
     print(json.dumps(line))
     return 0
+
+
+# --------------------------------------------------------------------------- HF on the same GPU: parity + incumbent
+def hf_gpu_legs(a, ckpt, spec, last_batch, last_out, dtype):
+    """transformers' eager model in the same dtype on this GPU (torch 2.11 + cuBLAS: 'the existing Blackwell path').
+    (1) parity of a sample of the last TIMED batch, (2) its own throughput on the same workload."""
+    import numpy as np
+    import torch
+
+    from anyscale_workshop_nyc_2023_b200.synth import synthetic_token_batch
+    from oracle.hf_anchor import hf_generate, hf_teacher_forced_logits, load_hf_model
+
+    out = {}
+    hf = load_hf_model(ckpt, dtype=dtype, device="cuda")
+    T = a.new
+    if a.parity_rows > 0:
+        ids, mask = last_batch
+        B = ids.shape[0]
+        sub = np.linspace(0, B - 1, min(a.parity_rows, B)).round().astype(int)
+        ref = hf_generate(hf, ids[sub], mask[sub], T, min_new_tokens=T)
+        ours = last_out[sub]
+        lg = hf_teacher_forced_logits(hf, ids[sub], mask[sub], ref[:, :-1])
+        lg[:, :, spec.eos_token_id] = -np.inf
+        top2 = np.partition(lg, -2, axis=-1)[:, :, -2:]
+        margins = top2[:, :, 1] - top2[:, :, 0]
+        tau = 0.13 if dtype == torch.bfloat16 else 0.03  # tests/test_model_gpu.py: TAU / TAU_FP16
+        gated = full = 0
+        for r in range(len(sub)):
+            low = np.where(~(margins[r] > tau))[0]
+            upto = 1 + (int(low[0]) if len(low) else T)
+            gated += int((ours[r, :upto] == ref[r, :upto]).all())
+            full += int((ours[r] == ref[r]).all())
+        out["parity"] = {
+            "anchor": f"transformers {__import__('transformers').__version__} eager {str(dtype).split('.')[-1]} generate on this GPU",
+            "what": f"{len(sub)} rows of the last timed batch (forced length {T})", "rows": int(len(sub)),
+            "rows_equal_up_to_first_near_tie": gated / len(sub), "tau": tau,
+            "rows_fully_equal": full / len(sub), "token_agreement": float((ours == ref).mean()),
+            "first_tokens_equal": float((ours[:, 1] == ref[:, 1]).mean()),
+        }
+        log(f"parity vs HF on this GPU: {out['parity']}")
+    if a.hf_gpu_batches > 0:
+        B = a.batch
+        times = []
+        for s in range(a.hf_gpu_batches + 1):  # first pass = warm-up
+            ids, mask = synthetic_token_batch(B, a.seq, spec.vocab_size, seed=5000 + s, lengths=a.lengths)
+            di, dm = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.no_grad():
+                o = hf.generate(input_ids=di, attention_mask=dm, max_new_tokens=T, min_new_tokens=T, do_sample=False, num_beams=1)
+            e1.record()
+            torch.cuda.synchronize()
+            assert o.shape == (B, T + 1)
+            if s > 0:
+                times.append(e0.elapsed_time(e1))
+            log(f"HF eager on this GPU, batch {s}: {e0.elapsed_time(e1):.0f} ms")
+        ms = sum(times) / len(times)
+        out["incumbent_hf_gpu"] = {"value": B * T / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+                                   "prompts_per_s": B / (ms / 1e3),
+                                   "what": f"transformers eager {str(dtype).split('.')[-1]} T5ForConditionalGeneration.generate, torch "
+                                           f"{torch.__version__}, same GPU, {a.hf_gpu_batches} timed batch(es) of {B} prompts after one "
+                                           "warm-up, inputs resident, CUDA events"}
+    del hf
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -204,6 +307,8 @@ def main_b200(a):
     import torch
     import torch.distributed as dist
 
+    from anyscale_workshop_nyc_2023_b200 import roofline
+    from anyscale_workshop_nyc_2023_b200.parallel import max_over_ranks
     from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_token_batch
     from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir, make_batch_predictor
 
@@ -225,7 +330,8 @@ def main_b200(a):
     ckpt = checkpoint_dir(a.model, seed=0)
 
     log(f"rank {rank}/{world}: checkpoint at {ckpt}; loading the model")
-    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=torch.float16 if a.dtype == "fp16" else torch.bfloat16)
+    tdtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=tdtype)
     from anyscale_workshop_nyc_2023_b200.rayshim.train import _ScoringWorker
 
     worker = _ScoringWorker(bp._checkpoint, bp._predictor_cls, {**bp._predictor_kwargs, "use_gpu": True}, False)
@@ -262,6 +368,7 @@ def main_b200(a):
     launches = 0
     enc_ms = dec_ms = 0.0
     dec_bytes = enc_flops = 0.0
+    out = None
     e0.record()
     for s in range(W, W + K):
         out = model.generate(input_ids=dev_batches[s][0], attention_mask=dev_batches[s][1], **gen_kw)
@@ -276,6 +383,7 @@ def main_b200(a):
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    last_out = out.cpu().numpy()  # the last TIMED batch's tokens: checked against HF below, outside the timed region
 
     if rank == 0:
         log(f"device-resident: {elapsed_ms / K:.1f} ms/step")
@@ -291,13 +399,21 @@ def main_b200(a):
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
 
-    # ---------------- roofline of the dominant kernel (cross-attention decode), measured live
-    ca = model.bench_cross_attention(reps=5)
+    # ---------------- roofline of the dominant kernel (cross-attention decode): inside the step graph, then alone
+    model.set_option("profile_xattn", 1)  # re-captures the step graph with %globaltimer stamps; untimed passes only
+    for s in (0, 1):
+        model.generate(input_ids=dev_batches[s][0], attention_mask=dev_batches[s][1], **gen_kw)
+    prof = model.xattn_profile()
+    model.set_option("profile_xattn", 0)
+    model.generate(input_ids=dev_batches[0][0], attention_mask=dev_batches[0][1], **gen_kw)  # plan for the calls below
+    full_bytes = roofline.cross_attention_bytes_per_launch(spec, host[0][1].sum(axis=1).tolist())
+    n_chains = max(1, int(round(full_bytes / max(prof["bytes_per_launch"], 1.0))))
+    rows_per_launch = (B + n_chains - 1) // n_chains
+    ca_chain = model.bench_cross_attention(reps=5, rows_per_launch=rows_per_launch)
+    ca_full = model.bench_cross_attention(reps=5, rows_per_launch=0)
 
-    t_max = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(t_max[0]), float(t_max[1])
+    elapsed_ms = max_over_ranks(elapsed_ms, dev)
+    e2e_ms = max_over_ranks(e2e_ms, dev)
 
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
@@ -305,13 +421,13 @@ def main_b200(a):
         hbm_peak, tf_peak, peak_src = float(pk["hbm_gbs"]), float(pk.get("bf16_tflops_sustained", 1458.8)), "measured (MEASURED_PEAKS.json)"
     else:
         hbm_peak, tf_peak, peak_src = 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
-    # DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture: only valid for the
-    # configuration that was captured (FLAN-T5-base, B=256, S=512, full-length prompts)
+    # DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (per batch row, scaled
+    # to the rows one in-situ launch covers): only valid for the captured configuration (base, S=512, full-length)
     traffic = None
     tf = ROOT / "profiles" / "cross_attn_traffic.json"
-    if tf.exists() and a.model == "flan-t5-base" and (B, S, a.lengths) == (256, 512, "full"):
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-    from anyscale_workshop_nyc_2023_b200 import roofline  # SURVEY 8(d)'s byte model (tests/test_roofline_cpu.py)
+    if tf.exists() and a.model == "flan-t5-base" and (S, a.lengths) == (512, "full"):
+        tj = json.loads(tf.read_text())
+        traffic = tj["dram_bytes_per_launch"] * rows_per_launch / float(tj.get("rows_per_launch", 256))
 
     kv_gb = roofline.cross_attention_bytes_per_launch(spec, [S] * B) * spec.num_decoder_layers / 1e9
     w_gb = 2.0 * roofline.step_weight_elements(spec) / 1e9
@@ -319,7 +435,13 @@ def main_b200(a):
     if rank == 0:
         tokens = world * K * B * T
         value = tokens / (elapsed_ms / 1e3)
-        ach = ca["bytes_per_launch"] / (ca["ms_per_launch"] / 1e3) / 1e9
+        gbs = lambda nbytes, ms: nbytes / (ms / 1e3) / 1e9  # noqa: E731
+        ach_situ = gbs(prof["bytes_per_launch"], prof["us_per_launch"] / 1e3) if prof["launches"] else None
+        ach_chain = gbs(ca_chain["bytes_per_launch"], ca_chain["ms_per_launch"])
+        ach_full = gbs(ca_full["bytes_per_launch"], ca_full["ms_per_launch"])
+        dec_frac = dec_bytes / (dec_ms / 1e3) / 1e9 / hbm_peak
+        enc_frac = enc_flops / (enc_ms / 1e3) / 1e12 / tf_peak
+        roof_ms = (dec_bytes / K) / (hbm_peak * 1e9) * 1e3 + (enc_flops / K) / (tf_peak * 1e12) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,22 +450,35 @@ def main_b200(a):
                        "parallelism": f"dataset sharded over {world} replica(s), no collective",
                        "l2": f"inputs exceed L2 (cross-KV arena {kv_gb:.1f} GB and {w_gb:.2f} GB of decoder weights "
                              "are streamed every step vs 126 MB L2)",
-                       "forced_length": "min_new_tokens == max_new_tokens"},
+                       "forced_length": "min_new_tokens == max_new_tokens", "row_chains": n_chains},
             "prompts_per_s": world * K * B / (elapsed_ms / 1e3),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * S * 8,
                     "d2h_bytes_per_step": B * (T + 1) * 8, "ms_per_step": e2e_ms / K,
                     "api": "HuggingFaceModelPredictor._predict_numpy (numpy batch -> DataFrame[generated_output])"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "attn_decode_kernel<false> (cross-attention decode)",
-                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algo_bytes_per_launch": ca["bytes_per_launch"], "ms_per_launch": ca["ms_per_launch"]},
+            # frac = the dominant kernel AS THE TIMED PATH LAUNCHES IT: one row-chain's rows per launch, inside the step
+            # graph, overlapped with the other chain's GEMMs (first CTA start -> last CTA end, %globaltimer, averaged
+            # over every launch of two extra untimed passes). frac_isolated_*: the same kernel alone, back to back.
+            "roofline": {"bound": "hbm", "kernel": "cross-attention decode (attn_cross_stream_kernel; B200T5_XATTN=ldg: attn_decode_kernel<false>)",
+                         "achieved": ach_situ, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (ach_situ / hbm_peak) if ach_situ else None, "traffic": traffic, "peak_source": peak_src,
+                         "in_situ": {"rows_per_launch": rows_per_launch, "launches_timed": prof["launches"],
+                                     "algo_bytes_per_launch": prof["bytes_per_launch"], "us_per_launch": prof["us_per_launch"]},
+                         "frac_isolated_chain_rows": ach_chain / hbm_peak, "frac_isolated_full_batch": ach_full / hbm_peak,
+                         "isolated": {"chain_rows": {"rows": rows_per_launch, **ca_chain}, "full_batch": {"rows": B, **ca_full}},
+                         "decode_loop_frac_of_hbm_peak": dec_frac, "encoder_frac_of_bf16_sustained": enc_frac,
+                         "whole_batch_frac": roof_ms / (elapsed_ms / K), "whole_batch_roofline_ms": roof_ms},
             "decode_loop": {"algo_gbytes_per_step_batch": dec_bytes / K / 1e9, "ms": dec_ms / K,
-                            "achieved_gbs": dec_bytes / (dec_ms / 1e3) / 1e9, "frac_of_hbm_peak": dec_bytes / (dec_ms / 1e3) / 1e9 / hbm_peak},
+                            "achieved_gbs": dec_bytes / (dec_ms / 1e3) / 1e9, "frac_of_hbm_peak": dec_frac},
             "encoder": {"tflop_per_batch": enc_flops / K / 1e12, "ms": enc_ms / K,
-                        "achieved_tflops": enc_flops / (enc_ms / 1e3) / 1e12, "frac_of_bf16_sustained": enc_flops / (enc_ms / 1e3) / 1e12 / tf_peak},
+                        "achieved_tflops": enc_flops / (enc_ms / 1e3) / 1e12, "frac_of_bf16_sustained": enc_frac},
         }
+        if world == 1 and (a.parity_rows > 0 or a.hf_gpu_batches > 0):
+            try:
+                line.update(hf_gpu_legs(a, ckpt, spec, host[W + K - 1], last_out, tdtype))
+            except Exception as e:  # noqa: BLE001 - the headline number must still be printed
+                line["parity"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not a.no_cpu_baseline:
             log("timing the CPU baseline (bounded sample, own process)")
             cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
@@ -352,8 +487,8 @@ def main_b200(a):
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
             env["CUDA_VISIBLE_DEVICES"] = ""
             try:
-                out = subprocess.run(cmd, capture_output=True, text=True, timeout=a.cpu_timeout, env=env)
-                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                sub = subprocess.run(cmd, capture_output=True, text=True, timeout=a.cpu_timeout, env=env)
+                ref = json.loads(sub.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = ref["cpu_baseline"]
             except (subprocess.TimeoutExpired, IndexError, ValueError, KeyError) as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": effective_cores(), "kind": "port",

@@ -133,12 +133,30 @@ int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids, const int6
                            int32_t* out_len);
 int b200t5_get_stats(b200t5_handle h, b200t5_stats* out);
 
-/* ---- measurement hook (bench.py) ---------------------------------------------------- */
-/* Times the cross-attention decode kernel alone over the cross-KV arena of the last generate
- * call (reps sweeps over all decoder layers, CUDA events on `stream`); returns the average
- * launch duration and the algorithmic bytes one launch must read (K+V rows of attended keys). */
-int b200t5_bench_cross_attn(b200t5_handle h, int reps, float* avg_ms_per_launch, double* bytes_per_launch,
-                            void* stream);
+/* ---- measurement hooks (bench.py) --------------------------------------------------- */
+/* Times the cross-attention decode kernel alone over the cross-KV arena of the last generate call, in launches of
+ * `rows_per_launch` batch rows (0 = the whole batch; the step graph launches one row-chain at a time): reps sweeps
+ * over all decoder layers, CUDA events on `stream`; returns the average launch duration and the algorithmic bytes
+ * one launch must read (K+V rows of attended keys). A microbenchmark (back-to-back launches, nothing else on the
+ * GPU); b200t5_get_xattn_profile gives the figure inside the step graph. */
+int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_launch, float* avg_ms_per_launch,
+                            double* bytes_per_launch, void* stream);
+/* Runtime options: what the B200T5_* environment variables set at create time, on a live handle (a sweep need not
+ * reload the model). A change drops the execution plan; the next call re-captures the step graph. Names: "chains"
+ * (row-chains per decode step, 0 = default), "xattn" (1 = bulk-copy stream kernel, 0 = per-thread-load kernel),
+ * "xattn_stages" (8 KB ring stages per CTA), "xattn_late_pdl", "pdl", "sk_stages64", "sk_stages128" (pipeline stages of
+ * the split-K decode GEMM tiles, 0 = default), "profile_xattn" (1 = every cross-attention launch inside the step graph
+ * records %globaltimer stamps; never on in a timed region). */
+int b200t5_set_option(b200t5_handle h, const char* name, int value);
+/* With "profile_xattn" on: mean in-situ duration (first CTA start to last CTA end) of the cross-attention launches the
+ * step graph made since the option was set, how many there were, and the algorithmic bytes of one such launch. */
+int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch);
+/* lm_head + fused greedy arg-max exactly as the decode step runs them (csrc/gemm.cuh EpiArgmax -> finalize_step_kernel):
+ * x [M,K] and W [V,K] in the build's 2-byte type (device), `step` the decode position, EOS masked while
+ * step < min_new. tokens: int64 [M] (device) = argmax_n act(x . W[n]) with torch.argmax's first-index tie rule
+ * (transformers generation/utils.py:2762,2793; logits_process.py:225-233). Test hook. */
+int b200t5_test_lm_argmax(int device, const void* x, const void* W, int M, int V, int K, int step, int eos, int min_new,
+                          int64_t* tokens, void* stream);
 
 /* ---- parity hooks (used by tests/ only) --------------------------------------------- */
 /* Encoder last hidden state after the final RMSNorm, bf16 [B,S,d_model] (device). */
@@ -158,12 +176,9 @@ int b200t5_relative_bucket(int relative_position, int bidirectional, int num_buc
 int b200t5_test_gemm(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int mode,
                      int pow_mode, void* stream);
 /* Same contract through the cluster split-K kernel the decode step uses (csrc/gemm_splitk.cuh):
- * bn in {64,128} (bn = 16 selects the A-multicast kernel of csrc/gemm_mcast.cuh instead: K <= 768, N % 64 == 0,
- * modes 0 and 1, `split` ignored); split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
- * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C; a non-NULL `aux` also receives the sums of
- * squares of every 32-column output chunk, float [M][ceil(N/32)]), 2 GeGLU, 4 decoder QKV: C is the q
- * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written, 5 plain store
- * with the T5 RMSNorm of A fused in: `aux` = float ss[M][ceil(K/32)] followed by the bf16 norm weight [K]. */
+ * bn in {64,128}; split in {1,2,4,8} CTAs per cluster along K (reduced automatically when K has
+ * fewer 64-wide k-blocks); mode 0 plain, 1 += residual (in C), 2 GeGLU, 4 decoder QKV: C is the q
+ * buffer [M, N/3] and `aux` the self-KV cache [2][M][H][Tmax][64] whose row `step` is written. */
 int b200t5_test_gemm_splitk(int device, const void* A, const void* W, void* C, int M, int N, int K, int bn, int split,
                             int mode, int pow_mode, void* aux, int Tmax, int step, void* stream);
 /* fp16 build (libb200t5_f16.so) only: the fp32-weight feed-forward output projection (transformers keeps T5's `wo`
@@ -174,8 +189,8 @@ int b200t5_test_ffo(int device, const void* A, const void* W, void* R, int M, in
                     void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);
 /* self == 1: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk];
- * self == 2: as 0 through the tensor-core kernel (csrc/attention_decode_tc.cuh, Tk <= 512; K and V must be finite
- * beyond the extent as well). */
+ * self == 2: as 0 through the bulk-copy stream kernel (csrc/attention_cross_stream.cuh), `step` = ring stages (0: 5);
+ * results are bit-identical to self == 0. */
 int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx, int B,
                             int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
                             const float* dist_bias, void* stream);

@@ -227,62 +227,6 @@ def test_gemm_splitk_qkv_append(lib, B, H, K, bn, split, Tmax, step):
     assert (cache[:, :, :, other] == 0).all()  # no other cache row is touched
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (128, 768, 768), (64, 384, 512), (8, 512, 384), (300, 1024, 704), (256, 64, 64)])
-@pytest.mark.parametrize("mode", [0, 1])
-def test_gemm_multicast(lib, M, N, K, mode):
-    """A-multicast cluster kernel (csrc/gemm_mcast.cuh, bn = 16): four CTAs share one copy of the A tile, no
-    reduction; plain store and += residual."""
-    g = torch.Generator(device="cuda").manual_seed(M * 5 + N + K + mode)
-    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-    W = (torch.randn(N, K, device="cuda", generator=g) * 0.3).bfloat16()
-    R = torch.randn(M, N, device="cuda", generator=g).bfloat16()
-    Cio = R.clone() if mode == 1 else torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A), P(W), P(Cio), M, N, K, 16, 1, mode, 0, None, 0, 0, None))
-    torch.cuda.synchronize()
-    y = (A.float() @ W.float().T).bfloat16()
-    ref = (R.float() + y.float()).bfloat16() if mode == 1 else y
-    assert torch.isfinite(Cio.float()).all()
-    tol = 2.0 ** -7 * (y.float().abs() + ref.float().abs()) + 1e-3
-    assert ((Cio.float() - ref.float()).abs() <= tol).all()
-    assert (Cio == ref).float().mean().item() > 0.99
-
-
-@pytest.mark.parametrize("M,N,K,bn,split", [(256, 768, 768, 64, 4), (256, 4096, 768, 128, 2), (100, 1152, 512, 64, 2), (8, 384, 1024, 64, 4)])
-def test_gemm_splitk_fused_rmsnorm(lib, M, N, K, bn, split):
-    """Producer: the residual epilogue emits per-32-column sums of squares of x; consumer: the GEMM normalises its
-    A tile in shared memory. Together they must equal T5LayerNorm (modeling_t5.py:55-68) followed by the Linear."""
-    g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    # producer: x = R + bf16(A0 W0^T), ss = chunk sums of squares
-    K0 = 256
-    A0 = (torch.randn(M, K0, device="cuda", generator=g) * 0.5).bfloat16()
-    W0 = (torch.randn(K, K0, device="cuda", generator=g) * 0.2).bfloat16()
-    R = (torch.randn(M, K, device="cuda", generator=g) * 2).bfloat16()
-    x = R.clone()
-    ss_ld = (K + 31) // 32
-    wln = (1 + 0.1 * torch.randn(K, device="cuda", generator=g)).bfloat16()
-    aux = torch.zeros(M * ss_ld * 4 + K * 2 + 64, device="cuda", dtype=torch.uint8)
-    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(A0), P(W0), P(x), M, K, K0, 64, 4, 1, 0, P(aux), 0, 0, None))
-    torch.cuda.synchronize()
-    ss = aux[: M * ss_ld * 4].view(torch.float32).view(M, ss_ld)
-    ref_ss = x.float().pow(2).view(M, ss_ld, 32).sum(-1) if K % 32 == 0 else None
-    if ref_ss is not None:
-        assert torch.allclose(ss, ref_ss, rtol=1e-5, atol=1e-6)
-    # consumer
-    aux[M * ss_ld * 4: M * ss_ld * 4 + K * 2] = wln.view(torch.uint8)
-    W = (torch.randn(N, K, device="cuda", generator=g) * 0.3).bfloat16()
-    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.check(lib.b200t5_test_gemm_splitk(DEV, P(x), P(W), P(out), M, N, K, bn, split, 5, 0, P(aux), 0, 0, None))
-    torch.cuda.synchronize()
-    var = x.float().pow(2).mean(-1, keepdim=True)
-    xn = wln * (x * torch.rsqrt(var + 1e-6)).to(torch.bfloat16)
-    ref32 = xn.float() @ W.float().T
-    assert torch.isfinite(out.float()).all()
-    ok = ulp_close(out, ref32.bfloat16(), 1.0) | ((out.float() - ref32).abs() <= 2e-3)
-    # 1/rms differs from torch's by at most an fp32 ulp (summation order), which can flip a bf16 rounding of xn
-    assert ok.float().mean().item() > 0.999, (out.float() - ref32).abs().max().item()
-    assert (out == ref32.bfloat16()).float().mean().item() > 0.98
-
-
 def test_gemm_logits_f32(lib):
     M, N, K = 256, 1000, 512
     g = torch.Generator(device="cuda").manual_seed(9)
@@ -321,7 +265,7 @@ def torch_attn_decode(q, K, V, bias_add):
     return torch.matmul(p.float(), V.float()).bfloat16().squeeze(2)
 
 
-@pytest.mark.parametrize("impl", [0, 2])  # 0: CUDA-core streaming kernel, 2: tensor-core kernel (attention_decode_tc.cuh)
+@pytest.mark.parametrize("impl", [0, 2])  # 0: per-thread-load kernel (attention_decode.cuh), 2: bulk-copy stream kernel (attention_cross_stream.cuh)
 @pytest.mark.parametrize("B,H,S", [(4, 6, 512), (3, 2, 77), (16, 12, 256), (40, 12, 512), (5, 3, 130)])
 def test_cross_attn_decode(lib, B, H, S, impl):
     g = torch.Generator(device="cuda").manual_seed(B * S)
@@ -346,6 +290,110 @@ def test_cross_attn_decode(lib, B, H, S, impl):
     # fp32 accumulation-order noise only: within 2 bf16 ulps of |value| or 2e-3 absolute
     assert (err <= 2 * 2.0 ** -7 * ref.float().abs() + 2e-3).all(), err.max().item()
     assert (ctx == ref).float().mean().item() > 0.97
+
+
+@pytest.mark.parametrize("stages", [2, 5, 12])
+@pytest.mark.parametrize("B,H,S", [(256, 12, 512), (7, 3, 77), (64, 16, 200), (300, 12, 64), (5, 3, 513), (2, 1, 1)])
+def test_cross_attn_stream_kernel_is_bit_identical(lib, B, H, S, stages):
+    """The bulk-copy stream kernel keeps the per-thread-load kernel's key -> (warp, lane, slot) assignment and the
+    order of every fp32 accumulation, so the two return the same bits: ragged extents, mask holes, retired rows
+    (extent 0), persistent CTAs with several items each (B*H > 2 * SMs), every ring depth."""
+    g = torch.Generator(device="cuda").manual_seed(B * S + stages)
+    q = (torch.randn(B, H, 64, device="cuda", generator=g) * 0.3).bfloat16()
+    K = torch.randn(B, H, S, 64, device="cuda", generator=g).bfloat16()
+    V = torch.randn(B, H, S, 64, device="cuda", generator=g).bfloat16()
+    lens = torch.randint(1, S + 1, (B,), generator=torch.Generator().manual_seed(2))
+    lens[0] = S
+    ok = (torch.arange(S)[None, :] < lens[:, None])
+    if S > 4:
+        ok[B // 2, 1:3] = False
+    extent = lens.clone().int()
+    if B > 3:
+        extent[3] = 0  # a retired row: nothing is read, the output is zero
+    extent, key_ok = extent.cuda(), ok.to(torch.uint8).cuda().contiguous()
+    out = []
+    for impl, arg in ((0, 0), (2, stages)):
+        ctx = torch.full((B, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.b200t5_test_attn_decode(DEV, impl, P(q), P(K), P(V), P(ctx), B, H, S, P(extent), P(key_ok), arg, None, None))
+        torch.cuda.synchronize()
+        out.append(ctx)
+    assert torch.isfinite(out[1].float()).all()
+    assert torch.equal(out[0].view(torch.int16), out[1].view(torch.int16))
+    if B > 3:
+        assert (out[1][3] == 0).all()
+
+
+def _argmax_case(lib, x, W, step, eos, min_new):
+    M, K = x.shape
+    V = W.shape[0]
+    toks = torch.full((M,), -7, device="cuda", dtype=torch.long)
+    _lib.check(lib.b200t5_test_lm_argmax(DEV, P(x), P(W), M, V, K, step, eos, min_new, P(toks), None))
+    torch.cuda.synchronize()
+    logits = (x.float() @ W.float().T).bfloat16().float()  # the lm_head output is rounded to bf16 before the arg-max
+    if step < min_new:
+        logits[:, eos] = -float("inf")
+    return toks, logits
+
+
+def test_fused_argmax_lowest_index_tie_rule(lib):
+    """torch.argmax returns the FIRST index among equal maxima (transformers generation/utils.py:2762,2793). The fused
+    path reduces in three places: inside a 32-column chunk, across the chunks of a 128-column tile (EpiArgmax),
+    across tiles and warps (finalize_step_kernel). Exact ties are constructed in all of them, including across the
+    last, partial tile of V = 32128 = 251 * 128 and against the masked EOS column."""
+    K, V, M = 64, 32128, 160
+    g = torch.Generator(device="cuda").manual_seed(0)
+    W = (torch.randn(V, K, device="cuda", generator=g) * 0.05).bfloat16()
+    x = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    x[:, 0] = 1.0  # logit(n) = W[n, 0] exactly (one product, exact in fp32, bf16 in -> bf16 out)
+    W[:, 0] = (torch.randn(V, device="cuda", generator=g) * 0.5).bfloat16().clamp(-3, 3)
+    W[:, 1:] = 0
+    top = 8.0
+    ties = {
+        0: [5, 17],                    # same 32-column chunk
+        1: [40, 100],                  # same tile, different chunks
+        2: [300, 20000],               # different tiles
+        3: [127, 128],                 # adjacent columns across a tile boundary
+        4: [32000, 32127],             # inside the last tile
+        5: [31999, 32127, 7],          # three-way, lowest index far from the others
+        6: [1, 2],                     # EOS (= 1) is one of the maxima: blocked while step < min_new, wins afterwards
+        7: [0, 32127],                 # first and last column
+    }
+    Wt = W.clone()
+    rows = sorted(ties)
+    # every row needs its own tie pattern: give row r the vector e_{r+1} instead and put the pattern in column r+1
+    x.zero_()
+    for r in range(M):
+        x[r, 0] = 1.0
+    for r in rows:
+        x[r, 0] = 0.0
+        x[r, r + 1] = 1.0
+        Wt[:, r + 1] = W[:, 0]
+        for n in ties[r]:
+            Wt[n, r + 1] = top
+    for step, min_new in ((0, 4), (4, 4), (9, 0)):
+        toks, logits = _argmax_case(lib, x, Wt, step, 1, min_new)
+        ref = logits.argmax(dim=-1)  # torch: first index among equal maxima
+        assert torch.equal(toks, ref), (step, min_new, toks[:10].tolist(), ref[:10].tolist())
+        for r in rows:
+            want = min(n for n in ties[r] if not (step < min_new and n == 1))
+            assert int(toks[r]) == want, (r, step, int(toks[r]), want)
+    # rows >= 8 share one logit vector: all equal, whatever tile row / CTA they sit in
+    toks, _ = _argmax_case(lib, x, Wt, 0, 1, 0)
+    assert len(set(toks[8:].tolist())) == 1
+
+
+@pytest.mark.parametrize("V,K,M", [(32128, 768, 256), (1000, 512, 37), (384, 128, 130)])
+def test_fused_argmax_random_with_quantised_ties(lib, V, K, M):
+    """Random activations against a head quantised so coarsely that many columns share the row maximum exactly."""
+    g = torch.Generator(device="cuda").manual_seed(V + K)
+    x = (torch.randn(M, K, device="cuda", generator=g)).bfloat16()
+    W = torch.randint(-1, 2, (V, K), device="cuda", generator=g).bfloat16()  # {-1, 0, 1}: integer logits, heavy ties
+    x = torch.randint(-2, 3, (M, K), device="cuda", generator=g).bfloat16()
+    for step, min_new in ((0, 0), (2, 5)):
+        toks, logits = _argmax_case(lib, x, W, step, 1, min_new)
+        n_ties = (logits == logits.max(dim=-1, keepdim=True).values).sum(-1)
+        assert (n_ties > 1).float().mean().item() > 0.2, "the case should contain exact ties"
+        assert torch.equal(toks, logits.argmax(dim=-1))
 
 
 @pytest.mark.parametrize("B,H,T,step", [(4, 6, 128, 0), (4, 6, 128, 5), (8, 12, 128, 127), (3, 2, 40, 33)])
