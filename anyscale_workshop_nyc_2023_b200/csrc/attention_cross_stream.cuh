@@ -27,12 +27,13 @@ constexpr int kXsConsumerWarps = 4;
 constexpr int kXsThreads = (kXsConsumerWarps + 1) * 32;  // + the producer warp
 constexpr int kXsChunkKeys = 64;                         // 8 KB of K or V rows per ring stage
 constexpr int kXsChunkBytes = kXsChunkKeys * 128;
+constexpr int kXsStageBytes = kXsChunkBytes + 128;       // + the chunk's 64 key_ok bytes (K phase), 128-byte aligned
 constexpr int kXsMaxStages = 12;
 
 struct XsSmem {
-  // [stages][8 KB] ring | scores [Tk] | red [4][64] | stat [8] | full[stages] empty[stages]
+  // [stages][8 KB + 128 B] ring | scores [Tk] | red [4][64] | stat [8] | full[stages] empty[stages]
   static __host__ __device__ size_t bytes(int stages, int Tk) {
-    return static_cast<size_t>(stages) * kXsChunkBytes + static_cast<size_t>((Tk + 3) & ~3) * 4 + 4 * 64 * 4 + 8 * 4 +
+    return static_cast<size_t>(stages) * kXsStageBytes + static_cast<size_t>((Tk + 3) & ~3) * 4 + 4 * 64 * 4 + 8 * 4 +
            2 * kXsMaxStages * 8 + 128 /* alignment slack */;
   }
 };
@@ -45,7 +46,8 @@ DEVINL void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, 
 }
 DEVINL void xs_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kXsConsumerWarps * 32) : "memory"); }  // the consumer warps only
 
-__global__ void __launch_bounds__(kXsThreads, 2)
+// <= 88 registers: two of these CTAs (28 K registers) and one split-K GEMM CTA (192 x 160) share an SM's 64 K
+__global__ void __maxnreg__(88)
 attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
                          const act_t* __restrict__ Kc,   // [B][H][Tk][64]
                          const act_t* __restrict__ Vc,   // [B][H][Tk][64]
@@ -57,7 +59,7 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
                          int stages, int late_pdl, XsStamps stamps) {
   extern __shared__ uint8_t xs_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 127) & ~uintptr_t(127));
-  float* s_scores = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * kXsChunkBytes);
+  float* s_scores = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * kXsStageBytes);
   float* s_red = s_scores + ((Tk + 3) & ~3);  // [4][64]
   float* s_stat = s_red + 4 * 64;             // [8]
   uint64_t* full = reinterpret_cast<uint64_t*>(s_stat + 8);
@@ -82,6 +84,11 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
   unsigned long long t_start = 0;
   if (stamps.slots != nullptr && threadIdx.x == 0) t_start = global_timer_ns();
   const int first = blockIdx.x, stride = gridDim.x;
+  // The key_ok bytes of a K chunk travel with it (a second, 64-byte bulk copy on the same barrier) when the rows
+  // are 16-byte aligned; otherwise the consumers read them from global memory. They must not be fetched with
+  // ordinary loads on the consumers' critical path: with four consumer warps per CTA there is nothing to hide an
+  // L2 round trip per chunk behind (first version of this kernel: 11 us per item instead of 6, 3.3 TB/s).
+  const bool mask_bulk = (Tk & 15) == 0;
   const int last_item = first + ((n_items - 1 - first) / stride) * stride;
 
   if (warp == kXsConsumerWarps) {
@@ -90,19 +97,25 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
       const uint64_t policy = l2_policy_evict_first();
       int stage = 0;
       uint32_t phase = 0;
+      int n_next = first < n_items ? extent[first / H] : 0;
       for (int it = first; it < n_items; it += stride) {
         const int b = it / H;
-        const int n = extent[b];
+        const int n = n_next;
+        // (the next item's extent is fetched a whole item ahead: the ring holds < 2 us of stream, an L2 round trip
+        // under load is of that order)
+        if (it + stride < n_items) n_next = extent[(it + stride) / H];
         const size_t slab = static_cast<size_t>(it) * Tk * 64;
 #pragma unroll 1
         for (int kv = 0; kv < 2; ++kv) {
           const act_t* src = (kv ? Vc : Kc) + slab;
           for (int k0 = 0; k0 < n; k0 += kXsChunkKeys) {
             const int keys = n - k0 < kXsChunkKeys ? n - k0 : kXsChunkKeys;
+            const uint32_t mbytes = (kv == 0 && mask_bulk) ? static_cast<uint32_t>((keys + 15) & ~15) : 0u;
+            uint8_t* dst = ring + static_cast<size_t>(stage) * kXsStageBytes;
             mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(keys) * 128u);
-            bulk_load_1d_hint(ring + static_cast<size_t>(stage) * kXsChunkBytes, src + static_cast<size_t>(k0) * 64,
-                              static_cast<uint32_t>(keys) * 128u, &full[stage], policy);
+            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(keys) * 128u + mbytes);
+            bulk_load_1d_hint(dst, src + static_cast<size_t>(k0) * 64, static_cast<uint32_t>(keys) * 128u, &full[stage], policy);
+            if (mbytes) bulk_load_1d(dst + kXsChunkBytes, key_ok + static_cast<size_t>(b) * Tk + k0, mbytes, &full[stage]);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -141,8 +154,8 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
     // ---------------- phase 1: scores (keys 4*warp + ks + 16u of every 128-key block, u = 0..7, as in attn_decode_kernel)
     for (int k0 = 0; k0 < nkeys; k0 += kXsChunkKeys) {
       // this lane group's four keys of the chunk: chunk-local key 4*warp + ks + 16*uu
-      unsigned char okv[4];
-      if (dg == 0) {
+      unsigned char okv[4] = {0, 0, 0, 0};
+      if (!mask_bulk && dg == 0) {
 #pragma unroll
         for (int uu = 0; uu < 4; ++uu) {
           const int j = k0 + warp * 4 + ks + 16 * uu;
@@ -150,7 +163,12 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
         }
       }
       mbar_wait(&full[stage], phase);
-      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsChunkBytes + dg * 16;
+      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsStageBytes + dg * 16;
+      if (mask_bulk && dg == 0) {
+        const uint8_t* okb = ring + static_cast<size_t>(stage) * kXsStageBytes + kXsChunkBytes;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) okv[uu] = okb[warp * 4 + ks + 16 * uu];
+      }
       uint4 kv[4];
 #pragma unroll
       for (int uu = 0; uu < 4; ++uu) {
@@ -204,7 +222,7 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     for (int k0 = 0; k0 < nkeys; k0 += kXsChunkKeys) {
       mbar_wait(&full[stage], phase);
-      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsChunkBytes + dg * 16;
+      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsStageBytes + dg * 16;
       uint4 vv[4];
       float p[4];
 #pragma unroll

@@ -290,7 +290,9 @@ struct b200t5_ctx {
   std::vector<EncLayerW> enc;
   std::vector<DecLayerW> dec;
   std::unique_ptr<Plan> plan;
-  cudaStream_t cap_stream = nullptr, exec_stream = nullptr;
+  cudaStream_t cap_stream = nullptr, exec_stream = nullptr, enc_stream = nullptr;  // enc_stream: slot-pool admission encoder passes (lowest priority)
+  cudaEvent_t enc_done_ev = nullptr, admitted_ev = nullptr;
+  bool admit_overlap = true;  // B200T5_ADMIT_OVERLAP=0: admission encoder passes on the decode stream (round-1 behaviour)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
   int pow_mode = 0;
@@ -602,8 +604,14 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
     return fail(nullptr, B200T5_EINVAL, "B200T5_SK=0 is not available in the fp16 build");
   }
 #endif
+  if (const char* ao_env = getenv("B200T5_ADMIT_OVERLAP")) h->admit_overlap = atoi(ao_env) != 0;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // (lowest, highest)
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->exec_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->exec_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->enc_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->enc_done_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->admitted_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return fail(nullptr, B200T5_ECUDA, "cudaStreamCreate failed");
   }
@@ -644,6 +652,9 @@ extern "C" int b200t5_destroy(b200t5_handle h) {
   h->plan.reset();
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->exec_stream) cudaStreamDestroy(h->exec_stream);
+  if (h->enc_stream) cudaStreamDestroy(h->enc_stream);
+  if (h->enc_done_ev) cudaEventDestroy(h->enc_done_ev);
+  if (h->admitted_ev) cudaEventDestroy(h->admitted_ev);
   for (int i = 0; i < kMaxChains; ++i)
     if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]);
   for (int i = 0; i <= kMaxChains; ++i)
@@ -1583,67 +1594,107 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     CU_OK(h, cudaGetLastError());
   }
   CU_OK(h, cudaEventRecord(h->ev[1], s));
-  std::vector<long long> slot_row(B, -1);
+  // Slot states: FREE -> (staged for an admission whose encoder pass is in flight) PENDING -> ACTIVE -> FREE.
+  // The encoder pass of an admission runs on its own low-priority stream UNDER the decode steps of the slots that
+  // are already active (its kernels touch only the encoder workspace and the arena rows of the pending slots, which
+  // no decode kernel reads: their live extent is 0 until admit_slots_kernel starts them); the admitted slots join
+  // at the next poll boundary. B200T5_ADMIT_OVERLAP=0 keeps everything on one stream (round-1 behaviour).
+  enum : char { FREE = 0, PENDING = 1, ACTIVE = 2 };
+  std::vector<char> state(B, FREE);
   long long next = 0, done = 0;
-  int active = 0, steps = 0;
+  int active = 0, steps = 0, n_free = B;
+  bool pending = false, enc_used = false;
+  int pend_k = 0;
   double enc_flops = 0;
   int* row_on = p.h_admit;
   int* a_slot = p.h_admit + B;
   int* a_row = p.h_admit + 2 * B;
   const size_t row_bytes = static_cast<size_t>(S) * 8;
+  auto admit_now = [&](int k) -> int {
+    admit_slots_kernel<<<k, 128, 0, s>>>(p.admit.as<int>() + B, p.admit.as<int>() + 2 * B, p.unfinished.as<int>(), p.pos.as<int>(),
+                                         p.out_row.as<int>(), p.extent.as<int>(), p.live_extent.as<int>(),
+                                         p.key_ok.as<unsigned char>(), p.live_key_ok.as<unsigned char>(), S, start,
+                                         h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
+    h->launches++;
+    CU_OK(h, cudaGetLastError());
+    CU_OK(h, cudaEventRecord(h->admitted_ev, s));  // the staging buffers may be reused after this point
+    for (int b = 0; b < B; ++b)
+      if (state[b] == PENDING) state[b] = ACTIVE;
+    active += k;
+    return B200T5_OK;
+  };
   while (done < N) {
-    const int nfree = B - active;
+    // ---- (a) an admission whose encoder pass ran under the previous round of decode steps: start its slots
+    if (pending) {
+      CU_OK(h, cudaStreamWaitEvent(s, h->enc_done_ev, 0));
+      TRY(admit_now(pend_k));
+      pending = false;
+    }
+    // ---- (b) `poll` decode steps for every slot (eight = one graph launch); queued BEFORE the next admission's
+    //          encoder pass so that the two overlap
+    const bool stepping = active > 0;
+    if (stepping) {
+      if (poll % kStepsPerGraph == 0) {
+        for (int r = 0; r < poll / kStepsPerGraph; ++r) CU_OK(h, cudaGraphLaunch(p.gexec8, s));
+      } else {
+        for (int r = 0; r < poll; ++r) CU_OK(h, cudaGraphLaunch(p.gexec, s));
+      }
+      h->launches += static_cast<int64_t>(p.graph_nodes) * poll;
+      steps += poll;
+      CU_OK(h, cudaMemcpyAsync(p.h_unf, p.unfinished.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    // ---- (c) admission: the next k prompts go to the free slots
     const long long left = N - next;
-    if (left > 0 && nfree > 0 && (active == 0 || nfree >= (left < admit_min ? left : admit_min))) {
-      // ---- admission: the next k prompts go to the free slots
-      const int k = static_cast<int>(left < nfree ? left : nfree);
+    if (left > 0 && n_free > 0 && (active == 0 || n_free >= (left < admit_min ? left : admit_min))) {
+      const bool overlap = h->admit_overlap && stepping;
+      cudaStream_t es = overlap ? h->enc_stream : s;
+      if (enc_used) CU_OK(h, cudaEventSynchronize(h->enc_done_ev));  // the pinned staging rows of the previous pass are free
+      const int k = static_cast<int>(left < n_free ? left : n_free);
       int j = 0;
       for (int b = 0; b < B; ++b) {
         row_on[b] = 0;
-        if (slot_row[b] < 0 && j < k) {
+        if (state[b] == FREE && j < k) {
           const long long r = next + j;
           row_on[b] = 1;
           a_slot[j] = b;
           a_row[j] = static_cast<int>(r);
-          slot_row[b] = r;
+          state[b] = PENDING;
           memcpy(p.h_ids + static_cast<size_t>(b) * S, input_ids + static_cast<size_t>(r) * S, row_bytes);
           if (attention_mask) memcpy(p.h_mask + static_cast<size_t>(b) * S, attention_mask + static_cast<size_t>(r) * S, row_bytes);
           ++j;
         }
       }
+      n_free -= k;
+      if (overlap) CU_OK(h, cudaStreamWaitEvent(es, h->admitted_ev, 0));  // the previous admit kernel has read `admit` / extent / key_ok
       const size_t nb = static_cast<size_t>(B) * row_bytes;
-      CU_OK(h, cudaMemcpyAsync(p.ids_dev.p, p.h_ids, nb, cudaMemcpyHostToDevice, s));
-      if (attention_mask) CU_OK(h, cudaMemcpyAsync(p.mask_dev.p, p.h_mask, nb, cudaMemcpyHostToDevice, s));
-      CU_OK(h, cudaMemcpyAsync(p.admit.p, p.h_admit, static_cast<size_t>(3) * B * 4, cudaMemcpyHostToDevice, s));
+      CU_OK(h, cudaMemcpyAsync(p.ids_dev.p, p.h_ids, nb, cudaMemcpyHostToDevice, es));
+      if (attention_mask) CU_OK(h, cudaMemcpyAsync(p.mask_dev.p, p.h_mask, nb, cudaMemcpyHostToDevice, es));
+      CU_OK(h, cudaMemcpyAsync(p.admit.p, p.h_admit, static_cast<size_t>(3) * B * 4, cudaMemcpyHostToDevice, es));
       // rows that are not admitted keep stale ids / masks in the staging buffers: row_on switches them off
-      TRY(run_encoder(h, p.ids_dev.as<long long>(), attention_mask ? p.mask_dev.as<long long>() : nullptr, s, p.admit.as<int>()));
-      TRY(run_cross_kv(h, s));
-      admit_slots_kernel<<<k, 128, 0, s>>>(p.admit.as<int>() + B, p.admit.as<int>() + 2 * B, p.unfinished.as<int>(), p.pos.as<int>(),
-                                           p.out_row.as<int>(), p.extent.as<int>(), p.live_extent.as<int>(),
-                                           p.key_ok.as<unsigned char>(), p.live_key_ok.as<unsigned char>(), S, start,
-                                           h->shared.as<act_t>(), p.dx.as<res_t>(), c.d);
-      h->launches++;
-      CU_OK(h, cudaGetLastError());
+      TRY(run_encoder(h, p.ids_dev.as<long long>(), attention_mask ? p.mask_dev.as<long long>() : nullptr, es, p.admit.as<int>()));
+      TRY(run_cross_kv(h, es));
       fill_stats_model(h, 0);
       enc_flops += h->last_enc_flops;
       next += k;
-      active += k;
+      if (overlap) {
+        CU_OK(h, cudaEventRecord(h->enc_done_ev, es));
+        enc_used = true;
+        pending = true;
+        pend_k = k;
+      } else {
+        TRY(admit_now(k));
+      }
     }
-    // ---- `poll` decode steps for every slot (eight = one graph launch), then see which slots have finished
-    if (poll % kStepsPerGraph == 0) {
-      for (int r = 0; r < poll / kStepsPerGraph; ++r) CU_OK(h, cudaGraphLaunch(p.gexec8, s));
-    } else {
-      for (int r = 0; r < poll; ++r) CU_OK(h, cudaGraphLaunch(p.gexec, s));
-    }
-    h->launches += static_cast<int64_t>(p.graph_nodes) * poll;
-    steps += poll;
-    CU_OK(h, cudaMemcpyAsync(p.h_unf, p.unfinished.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
-    CU_OK(h, cudaStreamSynchronize(s));
-    for (int b = 0; b < B; ++b) {
-      if (slot_row[b] >= 0 && !p.h_unf[b]) {
-        slot_row[b] = -1;
-        --active;
-        ++done;
+    // ---- (d) which slots have finished
+    if (stepping) {
+      CU_OK(h, cudaStreamSynchronize(s));
+      for (int b = 0; b < B; ++b) {
+        if (state[b] == ACTIVE && !p.h_unf[b]) {
+          state[b] = FREE;
+          ++n_free;
+          --active;
+          ++done;
+        }
       }
     }
   }
@@ -1751,6 +1802,7 @@ extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
     h->xs_stages = value;
   } else if (n == "xattn_late_pdl") h->xs_late_pdl = value != 0;
   else if (n == "pdl") h->use_pdl = value != 0;
+  else if (n == "admit_overlap") h->admit_overlap = value != 0;
   else if (n == "sk_stages64") h->sk_stages64 = value;
   else if (n == "sk_stages128") h->sk_stages128 = value;
   else if (n == "profile_xattn") h->profile_xattn = value != 0;

@@ -12,15 +12,16 @@
 // depend on the previous kernel and are requested BEFORE griddepcontrol.wait), warp 1 = TMEM
 // owner + tcgen05.mma issuer, warps 2..5 = epilogue. After its MMAs complete each CTA holds a
 // 128 x BN fp32 partial tile in TMEM. Reduce-scatter by ROWS: rank r of the cluster owns tile
-// rows [r*128/S, (r+1)*128/S); every epilogue thread (= one tile row) whose row belongs to ANOTHER
-// rank sends it to that rank's `red` buffer with st.shared::cluster, a cluster barrier
-// (release/acquire) publishes the writes, and the owner's thread of each row sums the S partials in
-// rank order (deterministic; its own partial comes straight from TMEM) and feeds 32-column chunks to
-// the same epilogue functors the persistent GEMM uses (gemm.cuh), so the T5 rounding contract is shared.
+// rows [r*128/S, (r+1)*128/S); every epilogue thread (= one tile row) sends its row to the
+// owner's `red` buffer slot [src rank][row] with st.shared::cluster, a cluster barrier
+// (release/acquire) publishes the writes, and the owner sums the S partials in rank order
+// (deterministic) and feeds 32-column chunks to the same epilogue functors the persistent GEMM
+// uses (gemm.cuh), so the T5 rounding contract is shared.
 //
-// Footprint: the `red` buffer holds only the (S-1)/S of the tile that arrives from peers and the number of
-// pipeline stages is a launch parameter, so that a CTA (~115-140 KB) fits on an SM next to the two resident CTAs
-// of the other row-chain's cross-attention stream (attention_cross_stream.cuh).
+// Footprint: the number of pipeline stages is a launch parameter, so that a CTA (115-140 KB) can be sized to fit on
+// an SM next to the resident CTAs of the other row-chain's cross-attention stream (attention_cross_stream.cuh).
+// (Round 2: keeping each rank's OWN rows in TMEM instead of sending them to itself saves 1/S of `red` but leaves the
+// reduction to the 128/S threads whose TMEM lanes hold those rows - measured +8 ms per batch; reverted.)
 // (Measured alternatives, round 1: st.async with a receiver-side mbarrier instead of the release fence +
 // cluster barrier, 194.8 vs 188.3 ms per batch; staging the rows locally and moving them with one
 // cp.async.bulk per destination rank, 195.3 ms; normalising the A tile in shared memory instead of a separate
@@ -43,12 +44,11 @@ struct SkCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kDefaultStages = BN == 64 ? 4 : 3;
   static constexpr int kRedLd = BN + 4;  // floats; +4 keeps the per-row v4 stores of a warp conflict-free
-  // rows received from the S - 1 peers: (S - 1) * 128 / S
-  static constexpr int red_bytes(int split) { return (split - 1) * (kBM / split) * kRedLd * 4; }
-  static constexpr int smem_bytes(int stages, int split) {
-    return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + red_bytes(split) + kEpiSmemBytes;
+  static constexpr int kRedBytes = kBM * kRedLd * 4;  // [src rank][row of the owner] = 128 slots whatever the split
+  static constexpr int smem_bytes(int stages) {
+    return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRedBytes + kEpiSmemBytes;
   }
-  static constexpr int kMaxSmemBytes = smem_bytes(kSkMaxStages, kSkMaxSplit);
+  static constexpr int kMaxSmemBytes = smem_bytes(kSkMaxStages);
 };
 
 // ---------------------------------------------------------------- cluster PTX
@@ -74,10 +74,6 @@ DEVINL void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uin
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-DEVINL void add32(uint32_t (&acc)[32], const uint32_t (&x)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(x[j]));
-}
 DEVINL void add32_smem(uint32_t (&acc)[32], const float* src) {
   const float4* r4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
@@ -111,7 +107,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int S = static_cast<int>(cluster_nctarank());
   const int rank = static_cast<int>(cluster_ctarank());
-  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(red) + Cfg::red_bytes(S);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(red) + Cfg::kRedBytes;
   const int n_tile = blockIdx.y, m_tile = blockIdx.z;
   const int kblocks = (K + kbk - 1) / kbk;
   if (a_kblocks <= 0) a_kblocks = kblocks;
@@ -207,8 +203,6 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     cluster_wait_acquire();    // #1
     cluster_arrive_release();  // #2
     cluster_wait_acquire();
-    // the owners' epilogue threads still read their own partials from TMEM after barrier #2
-    asm volatile("bar.sync 3, %0;" ::"r"(5 * 32) : "memory");
     tc_fence_after_sync();
     tmem_dealloc<BN>(tmem_base);
   } else {
@@ -217,26 +211,28 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                      // tile row held by this thread
     const int rows_per = kBM / S;
-    const int owner = row / rows_per;                   // rank that reduces this row
-    const int rl = row - owner * rows_per;              // its index among the owner's rows
-    const bool mine = owner == rank;
-    const int m = m0 + row;
     if constexpr (Epi::kPaired) Epi::prologue(ep, epi_smem, et);  // gelu table; overlaps the main loop
     constexpr int kChunks = Epi::kPaired ? BN / 64 : BN / 32;
+    const int items = rows_per * kChunks;
     pdl_wait();
-    // the first chunk's accumulator-independent operands (residual row) are fetched now
+    // the first work item's accumulator-independent operands (residual row) are fetched now
     typename Epi::ChunkPre pre0;
-    if constexpr (!Epi::kPaired) {
-      if (mine && m < M && n0t < N) Epi::chunk_pre(ep, m, n0t, N, pre0);
+    {
+      const int rl = et / kChunks, c = et - rl * kChunks;
+      const int m = m0 + rank * rows_per + rl;
+      if constexpr (!Epi::kPaired) {
+        if (et < items && m < M && n0t + c * 32 < N) Epi::chunk_pre(ep, m, n0t + c * 32, N, pre0);
+      }
     }
     mbar_wait(tfull, 0);
     tc_fence_after_sync();
     cluster_wait_acquire();  // #1: every CTA of the cluster is running, its `red` buffer may be written
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    if (!mine) {
-      // slot = [source index among the owner's S - 1 peers, in rank order][row of the owner]
-      const int src_idx = rank < owner ? rank : rank - 1;
-      const uint32_t dst = mapa_shared(smem_u32(red + static_cast<size_t>(src_idx * rows_per + rl) * Cfg::kRedLd), static_cast<uint32_t>(owner));
+    {
+      // (every lane of the warp executes the TMEM loads: tcgen05.ld is warp-collective)
+      const int dst_rank = row / rows_per;
+      const int slot = rank * rows_per + (row - dst_rank * rows_per);
+      const uint32_t dst = mapa_shared(smem_u32(red + static_cast<size_t>(slot) * Cfg::kRedLd), static_cast<uint32_t>(dst_rank));
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t acc[32];
@@ -250,58 +246,37 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_before_sync();
     cluster_arrive_release();  // #2: partials published
     cluster_wait_acquire();
-    if (mine && m < M) {
-      // partial sums added in rank order, starting from zero (the order the round-1 kernel used: results are
-      // bit-identical to it whatever the split)
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        if constexpr (Epi::kPaired) {
-          constexpr int HALF = BN / 2;
-          const int f0 = n_tile * HALF + c * 32;
-          if (f0 >= ep.F) continue;
-          uint32_t g[32], u[32];
+    for (int it = et; it < items; it += 128) {
+      const int rl = it / kChunks, c = it - rl * kChunks;
+      const int m = m0 + rank * rows_per + rl;
+      if (m >= M) continue;
+      if constexpr (Epi::kPaired) {
+        constexpr int HALF = BN / 2;
+        const int f0 = n_tile * HALF + c * 32;
+        if (f0 >= ep.F) continue;
+        uint32_t g[32], u[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = u[j] = 0u;
-          for (int src = 0; src < S; ++src) {
-            if (src == rank) {
-              uint32_t tg[32], tu[32];
-              tmem_ld_32x32(taddr + c * 32, tg);
-              tmem_ld_32x32(taddr + HALF + c * 32, tu);
-              tmem_ld_wait();
-              add32(g, tg);
-              add32(u, tu);
-            } else {
-              const float* base = red + static_cast<size_t>((src < rank ? src : src - 1) * rows_per + rl) * Cfg::kRedLd;
-              add32_smem(g, base + c * 32);
-              add32_smem(u, base + HALF + c * 32);
-            }
-          }
-          Epi::chunk2(ep, g, u, m, f0, epi_smem);
-        } else {
-          const int n0 = n0t + c * 32;
-          if (n0 >= N) continue;
-          typename Epi::ChunkPre pre;
-          if (c == 0) pre = pre0;
-          else Epi::chunk_pre(ep, m, n0, N, pre);
-          uint32_t acc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0u;
-          for (int src = 0; src < S; ++src) {
-            if (src == rank) {
-              uint32_t t[32];
-              tmem_ld_32x32(taddr + c * 32, t);
-              tmem_ld_wait();
-              add32(acc, t);
-            } else {
-              add32_smem(acc, red + static_cast<size_t>((src < rank ? src : src - 1) * rows_per + rl) * Cfg::kRedLd + c * 32);
-            }
-          }
-          Epi::chunk(ep, acc, m, n0, N, epi_smem, pre);
+        for (int j = 0; j < 32; ++j) g[j] = u[j] = 0u;
+        for (int src = 0; src < S; ++src) {
+          const float* base = red + static_cast<size_t>(src * rows_per + rl) * Cfg::kRedLd;
+          add32_smem(g, base + c * 32);
+          add32_smem(u, base + HALF + c * 32);
         }
+        Epi::chunk2(ep, g, u, m, f0, epi_smem);
+      } else {
+        const int n0 = n0t + c * 32;
+        if (n0 >= N) continue;
+        typename Epi::ChunkPre pre;
+        if (it == et) pre = pre0;
+        else Epi::chunk_pre(ep, m, n0, N, pre);
+        uint32_t acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0u;
+        for (int src = 0; src < S; ++src) add32_smem(acc, red + static_cast<size_t>(src * rows_per + rl) * Cfg::kRedLd + c * 32);
+        Epi::chunk(ep, acc, m, n0, N, epi_smem, pre);
       }
     }
-    tc_fence_before_sync();
-    asm volatile("bar.sync 3, %0;" ::"r"(5 * 32) : "memory");  // TMEM may be released (warp 1)
   }
 }
 
@@ -332,7 +307,7 @@ cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, i
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(split, (N + BN - 1) / BN, (M + kBM - 1) / kBM);
   cfg.blockDim = dim3(kSkThreads);
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages, split);
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages);
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int na = 0;

@@ -22,6 +22,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_cuda = False
     if has_cuda:
+        # A protocol bug in a hand-written kernel (mbarrier / cluster barrier / warp-collective tcgen05 op) hangs
+        # instead of failing: every GPU test gets a watchdog that ends the process (the "thread" method works while
+        # the main thread is blocked inside a CUDA call), so one hang cannot eat the whole GPU lease.
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(240, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -476,6 +476,7 @@ def _headline_parity(model, ckpt, spec, dtype, B, S, T, lengths, rows, tau, tag)
 UNGATED_FLOOR = {"bf16": 0.85, "fp16": 0.95}
 
 
+@pytest.mark.timeout(600, method="thread")
 @pytest.mark.parametrize("dtype_name,lengths", [("bf16", "full"), ("bf16", "alpaca"), ("fp16", "full")])
 def test_headline_config_flan_t5_base_b256_s512_t128(models, models_fp16, dtype_name, lengths):
     pytest.importorskip("transformers")
@@ -500,6 +501,7 @@ def test_headline_config_flan_t5_base_b256_s512_t128(models, models_fp16, dtype_
         assert m["tf_argmax_agreement"] >= fl["tf_argmax_agreement"], (mode, m, fl)
 
 
+@pytest.mark.timeout(900, method="thread")
 def test_headline_config_flan_t5_large_b64(models):
     """BASELINE configs[3]'s model at a batch HF can anchor in seconds: 24 layers, d_model 1024, 16 heads."""
     pytest.importorskip("transformers")
