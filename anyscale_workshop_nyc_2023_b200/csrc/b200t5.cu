@@ -312,7 +312,7 @@ struct b200t5_ctx {
   // Cross-attention of the decode step: the bulk-copy stream kernel (attention_cross_stream.cuh; bandwidth independent
   // of the warps resident per SM, so it survives sharing the SMs with the other chain's GEMM CTAs) or, B200T5_XATTN=ldg,
   // the per-thread-load kernel of round 1 (attention_decode.cuh). Bit-identical results.
-  bool xattn_stream = true;
+  bool xattn_stream = false;  // (round 2, first measurements: 0.63 of the HBM peak alone against 0.96 for the per-thread-load kernel)
   int xs_stages = 5;        // 8 KB ring stages per CTA (two CTAs per SM): B200T5_XS_STAGES
   bool xs_late_pdl = true;  // release the dependent GEMM when a CTA starts its last item instead of at once: B200T5_XS_LATE_PDL
   bool profile_xattn = false;  // b200t5_set_option("profile_xattn"): stamp every cross-attention launch inside the step graph
@@ -568,7 +568,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
-  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "ldg") != 0;
+  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "stream") == 0;
   if (const char* xs_env = getenv("B200T5_XS_STAGES")) {
     const int v = atoi(xs_env);
     if (v >= 2 && v <= kXsMaxStages) h->xs_stages = v;
@@ -1113,7 +1113,7 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
       else CU_OK(h, run_gemm(h, mk(p.tm_xn, w.tm_qkv, M, 3 * I, d, G_STORE256, 0), &ep, s));
     }
     if (h->enc_attn_tc && S <= kEncTcMaxS) {
-      encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
+      encoder_attn_tc_kernel<<<dim3(B * H), kEncTcThreads, EncTcSmem::bytes(S), s>>>(
           p.tm_qkv_attn, p.ctx.as<act_t>(), p.enc_bias.as<float>(), p.key_ok.as<unsigned char>(), p.extent.as<int>(), cu, S, H,
           enc_prof && l == 0 ? enc_prof->as<long long>() : nullptr, p.enc_bias_packed.as<uint32_t>());
     } else {
@@ -2130,7 +2130,7 @@ extern "C" int b200t5_test_encoder_attn(int device, const void* qkv, void* ctx, 
     if (S > kEncTcMaxS) return fail(nullptr, B200T5_EINVAL, "tcgen05 encoder attention supports S <= %d", kEncTcMaxS);
     CUtensorMap tm;
     if (!make_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, static_cast<uint64_t>(3) * H * 64, 128)) return fail(nullptr, B200T5_ECUDA, "%s", g_err);
-    encoder_attn_tc_kernel<<<dim3((S + kEncTcQ - 1) / kEncTcQ, B * H), kEncTcThreads, EncTcSmem::bytes(S), static_cast<cudaStream_t>(stream)>>>(
+    encoder_attn_tc_kernel<<<dim3(B * H), kEncTcThreads, EncTcSmem::bytes(S), static_cast<cudaStream_t>(stream)>>>(
         tm, static_cast<act_t*>(ctx), rel_bias, key_ok, extent, nullptr, S, H);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(nullptr, B200T5_ECUDA, "encoder_attn_tc: %s", cudaGetErrorString(e2));

@@ -17,7 +17,7 @@ ASSETS = Path(__file__).resolve().parent / "assets"
 def checkpoint_dir(spec_name: str, seed: int = 0, root: Optional[str] = None) -> Path:
     """Create (once) and return a synthetic checkpoint directory for `spec_name`."""
     root = Path(root or os.environ.get("B200T5_CKPT_ROOT", tempfile.gettempdir()))
-    d = root / f"b200t5_ckpt_{spec_name}_seed{seed}"
+    d = root / f"b200t5_ckpt_{spec_name}_seed{seed}_q{SPECS[spec_name].q_init_gain:g}"
     marker = d / ".complete"
     if not marker.exists():
         tmp = Path(tempfile.mkdtemp(prefix=d.name + ".", dir=root))

@@ -386,9 +386,11 @@ def test_fused_argmax_lowest_index_tie_rule(lib):
 def test_fused_argmax_random_with_quantised_ties(lib, V, K, M):
     """Random activations against a head quantised so coarsely that many columns share the row maximum exactly."""
     g = torch.Generator(device="cuda").manual_seed(V + K)
-    x = (torch.randn(M, K, device="cuda", generator=g)).bfloat16()
-    W = torch.randint(-1, 2, (V, K), device="cuda", generator=g).bfloat16()  # {-1, 0, 1}: integer logits, heavy ties
-    x = torch.randint(-2, 3, (M, K), device="cuda", generator=g).bfloat16()
+    W = torch.randint(-1, 2, (V, K), device="cuda", generator=g).bfloat16()  # {-1, 0, 1}
+    # six non-zero activations per row: integer logits in [-6, 6], so the row maximum is shared by many columns
+    x = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    cols = torch.rand(M, K, device="cuda", generator=g).argsort(dim=1)[:, :6]
+    x.scatter_(1, cols, (torch.randint(0, 2, (M, 6), device="cuda", generator=g) * 2 - 1).bfloat16())
     for step, min_new in ((0, 0), (2, 5)):
         toks, logits = _argmax_case(lib, x, W, step, 1, min_new)
         n_ties = (logits == logits.max(dim=-1, keepdim=True).values).sum(-1)

@@ -220,7 +220,7 @@ def test_missing_attention_mask_is_inferred_from_pad_tokens_like_hf(models):
 
 
 def test_cross_attention_kernels_give_identical_tokens(models):
-    """The step graph with the bulk-copy stream kernel (default) and with the per-thread-load kernel of round 1 produce
+    """The step graph with the per-thread-load cross-attention kernel (default) and with the bulk-copy stream kernel produce
     the same tokens; so do 1, 2 and 3 row-chains (rows are independent in every kernel)."""
     model, _ = models("mini", 2)
     spec = SPECS["mini"]
@@ -232,7 +232,7 @@ def test_cross_attention_kernels_give_identical_tokens(models):
             model.set_option(name, value)
             assert torch.equal(model.generate(**kw).cpu(), base), (name, value)
     finally:
-        for name, value in (("xattn", 1), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1)):
+        for name, value in (("xattn", 0), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1)):
             model.set_option(name, value)
 
 
