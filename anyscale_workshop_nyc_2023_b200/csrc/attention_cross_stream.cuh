@@ -1,23 +1,34 @@
-// Cross-attention of the decode step (D7) as a bulk-copy stream: the HBM roofline kernel, second design.
+// Cross-attention of the decode step (D7) as a TMA stream feeding the (legacy) tensor cores: the HBM roofline
+// kernel, second design.
 //
-// attention_decode.cuh reads K/V with per-thread 16-byte loads, so its bandwidth is proportional to the warps
-// resident per SM (it needs ~28 of them for 42 GB/s per SM). That is fine when it has the GPU to itself, but the
-// decode step overlaps it with the latency-bound split-K GEMMs of the other row-chain, whose CTAs (29 K registers,
-// ~130 KB of shared memory each) evict more than half of the attention CTAs from the SMs they land on: measured in
-// round 1, a 64-row launch took 25 us instead of 16 under that contention and the step gained nothing from the
-// overlap (profiles/decode_trace_r1.md).
+// attention_decode.cuh reads K/V with per-thread 16-byte loads and does the arithmetic on the CUDA cores: ~54 warp
+// instructions per 512 bytes, i.e. ~60 % of an SM's issue slots at the HBM rate, and its bandwidth is proportional to
+// the warps resident per SM (it needs ~28 of them for 42 GB/s per SM). That is fine when it has the GPU to itself
+// (0.96 of the HBM peak), but the decode step overlaps it with the latency-bound split-K GEMMs of the other
+// row-chain, whose CTAs (30 K registers, ~140 KB of shared memory each) cannot co-reside with a full complement of
+// attention CTAs and take their place: in situ a 128-row launch runs at 0.73 (round 2, %globaltimer stamps).
 //
-// Here the bytes in flight do not depend on how many warps are resident: one producer lane per CTA streams the
-// K and V slabs of the CTA's (row, head) items through a ring of 8 KB shared-memory stages with cp.async.bulk
-// (complete_tx on an mbarrier, L2 evict-first), and four consumer warps do the arithmetic out of shared memory.
-// Two CTAs per SM x `stages` x 8 KB are in flight whatever else is resident, the CTAs are persistent (grid sized
-// so that every CTA gets the same number of items), and their footprint (2 x ~45 KB, 2 x 160 threads x <= 64
-// registers) leaves room for a split-K GEMM CTA of the other chain on the same SM.
+// Here neither the bytes in flight nor the arithmetic depend on how many warps are resident:
+//   * one producer lane per CTA streams the K and V slabs of the CTA's (row, head) items through a ring of 8 KB
+//     shared-memory stages with TMA (cp.async.bulk.tensor.2d, 64 keys x 64 d per box, 128-byte swizzle, L2
+//     evict-first; the chunk's 64 key_ok bytes ride along as a second bulk copy on the same mbarrier);
+//   * four consumer warps compute out of shared memory with mma.sync.m16n8k16 (bf16 / fp16 inputs, fp32
+//     accumulation): scores = K_chunk[64 x 64] . q as four 16-key tiles (one per warp), out = V_chunk^T[64 d x 64] . p
+//     as four 16-d tiles (one per warp, accumulated over the whole item in registers), the vectors q and p occupying
+//     column 0 of the B operand. ~25 warp instructions per 8 KB chunk and warp instead of ~220.
+//     The tensor pipe runs at 1/8 utilisation by construction - irrelevant for a kernel that is bound by HBM; what
+//     matters is that the issue slots are free. (First version of this kernel, same ring with the CUDA-core
+//     arithmetic of attention_decode.cuh on 2 x 4 consumer warps per SM: 0.63 of the HBM peak, issue-bound -
+//     39 % of the issue slots with 2.3 warps per scheduler; profiles/decode_r2.md. The tcgen05 formulation of round 1
+//     (0.73, profiles/xattn_tc_r1.md) paid ~80 clocks per tiny UMMA.)
+// Two CTAs per SM x `stages` x 8 KB are in flight whatever else is resident, the CTAs are persistent (grid sized so
+// that every CTA gets the same number of items), and their footprint (2 x ~45 KB, 2 x 160 threads) leaves room for
+// a split-K GEMM CTA of the other chain on the same SM.
 //
-// The arithmetic, the rounding points AND the order of every fp32 accumulation are those of
-// attn_decode_kernel<false>: within each 128-key block warp w / lane group ks / unroll slot u owns key
-// 4w + ks + 16u exactly as there, so the two kernels return bit-identical results (tests/test_kernels_gpu.py) and
-// the model-level parity evidence carries over unchanged.
+// Rounding contract as in attention_decode.cuh: s = act(q.k) with fp32 accumulation; masked
+// keys replaced by finfo.min; p = act(exp(s - max) / sum) from an exact two-pass fp32 softmax over the rounded scores;
+// out = act(sum_j p_j v_j) with fp32 accumulation. Only the ORDER of the fp32 accumulations differs (the tensor core's
+// instead of a sequential one), which no contract fixes: HF's own bmm does not either.
 #pragma once
 #include "attention_decode.cuh"
 
@@ -27,30 +38,54 @@ constexpr int kXsConsumerWarps = 4;
 constexpr int kXsThreads = (kXsConsumerWarps + 1) * 32;  // + the producer warp
 constexpr int kXsChunkKeys = 64;                         // 8 KB of K or V rows per ring stage
 constexpr int kXsChunkBytes = kXsChunkKeys * 128;
-constexpr int kXsStageBytes = kXsChunkBytes + 128;       // + the chunk's 64 key_ok bytes (K phase), 128-byte aligned
 constexpr int kXsMaxStages = 12;
 
 struct XsSmem {
-  // [stages][8 KB + 128 B] ring | scores [Tk] | red [4][64] | stat [8] | full[stages] empty[stages]
+  // [stages][8 KB] ring (1024-byte aligned: swizzle atoms) | masks [stages][64] | scores f32 [Tk64] | p act [Tk64] |
+  // stat [8] | q act [64] | full[stages] empty[stages]
+  static __host__ __device__ int tk64(int Tk) { return (Tk + 63) & ~63; }
   static __host__ __device__ size_t bytes(int stages, int Tk) {
-    return static_cast<size_t>(stages) * kXsStageBytes + static_cast<size_t>((Tk + 3) & ~3) * 4 + 4 * 64 * 4 + 8 * 4 +
-           2 * kXsMaxStages * 8 + 128 /* alignment slack */;
+    return static_cast<size_t>(stages) * (kXsChunkBytes + 64) + static_cast<size_t>(tk64(Tk)) * 6 + 8 * 4 + 64 * 2 +
+           2 * kXsMaxStages * 8 + 1024 /* alignment slack */;
   }
 };
 
-DEVINL void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
 DEVINL void xs_bar_sync() { asm volatile("bar.sync 1, %0;" ::"r"(kXsConsumerWarps * 32) : "memory"); }  // the consumer warps only
 
-// <= 88 registers: two of these CTAs (28 K registers) and one split-K GEMM CTA (192 x 160) share an SM's 64 K
-__global__ void __maxnreg__(88)
-attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
-                         const act_t* __restrict__ Kc,   // [B][H][Tk][64]
-                         const act_t* __restrict__ Vc,   // [B][H][Tk][64]
+// 2-D tiled TMA load with an L2 cache hint
+DEVINL void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D (16x8 fp32) += A (16x16, row) * B (16x8, col), 2-byte inputs of the build's activation type
+DEVINL void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if B200T5_F16
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+#else
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+#endif
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// tmK / tmV: [rows, 64] views (box 64 x 64 rows, 128-byte swizzle) of the K and V planes; item `it` (= (row, head),
+// chain-relative) owns rows k_row0 + it * Tk .. + Tk of tmK and v_row0 + it * Tk .. of tmV.
+// <= 64 registers: two of these CTAs (20 K registers) and one split-K GEMM CTA (192 x 160) share an SM's 64 K
+__global__ void __maxnreg__(64)
+attn_cross_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                         int k_row0, int v_row0,
+                         const act_t* __restrict__ q,    // [B, H*64]
                          act_t* __restrict__ ctx,        // [B, H*64]
                          int n_items,                    // B * H
                          int H, int Tk,
@@ -58,15 +93,20 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
                          const unsigned char* __restrict__ key_ok,  // [B][Tk] 1 = attended
                          int stages, int late_pdl, XsStamps stamps) {
   extern __shared__ uint8_t xs_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 127) & ~uintptr_t(127));
-  float* s_scores = reinterpret_cast<float*>(ring + static_cast<size_t>(stages) * kXsStageBytes);
-  float* s_red = s_scores + ((Tk + 3) & ~3);  // [4][64]
-  float* s_stat = s_red + 4 * 64;             // [8]
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stat + 8);
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_mask = ring + static_cast<size_t>(stages) * kXsChunkBytes;          // [stages][64]
+  float* s_scores = reinterpret_cast<float*>(s_mask + static_cast<size_t>(stages) * 64);
+  const int tk64 = XsSmem::tk64(Tk);
+  act_t* s_p = reinterpret_cast<act_t*>(s_scores + tk64);                        // [tk64]
+  float* s_stat = reinterpret_cast<float*>(s_p + tk64);                          // [8]
+  act_t* s_q = reinterpret_cast<act_t*>(s_stat + 8);                             // [64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_q + 64);
   uint64_t* empty = full + kXsMaxStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], kXsConsumerWarps);
@@ -75,7 +115,7 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
   }
   __syncthreads();
   // late_pdl = 0: the dependent kernel (this chain's cross-attention output projection) may start its prologue at
-  // once, as everywhere else in the step. late_pdl = 1: its CTAs would only sit on their SMs (~130 KB of shared
+  // once, as everywhere else in the step. late_pdl = 1: its CTAs would only sit on their SMs (~140 KB of shared
   // memory each) while this kernel streams, in the way of the OTHER chain's GEMMs: release them when this CTA
   // starts its LAST item, so that the prologue overlaps the tail of the stream only.
   if (!late_pdl) pdl_launch_dependents();
@@ -84,12 +124,10 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
   unsigned long long t_start = 0;
   if (stamps.slots != nullptr && threadIdx.x == 0) t_start = global_timer_ns();
   const int first = blockIdx.x, stride = gridDim.x;
-  // The key_ok bytes of a K chunk travel with it (a second, 64-byte bulk copy on the same barrier) when the rows
-  // are 16-byte aligned; otherwise the consumers read them from global memory. They must not be fetched with
-  // ordinary loads on the consumers' critical path: with four consumer warps per CTA there is nothing to hide an
-  // L2 round trip per chunk behind (first version of this kernel: 11 us per item instead of 6, 3.3 TB/s).
-  const bool mask_bulk = (Tk & 15) == 0;
   const int last_item = first + ((n_items - 1 - first) / stride) * stride;
+  // The key_ok bytes of a K chunk travel with it (a second, 64-byte bulk copy on the same barrier) when the rows
+  // are 16-byte aligned; otherwise the consumers read them from global memory.
+  const bool mask_bulk = (Tk & 15) == 0;
 
   if (warp == kXsConsumerWarps) {
     // ------------------------------------------------------------ producer: K chunks then V chunks of every item
@@ -104,18 +142,19 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
         // (the next item's extent is fetched a whole item ahead: the ring holds < 2 us of stream, an L2 round trip
         // under load is of that order)
         if (it + stride < n_items) n_next = extent[(it + stride) / H];
-        const size_t slab = static_cast<size_t>(it) * Tk * 64;
 #pragma unroll 1
         for (int kv = 0; kv < 2; ++kv) {
-          const act_t* src = (kv ? Vc : Kc) + slab;
+          const CUtensorMap* tm = kv ? &tmV : &tmK;
+          const int row0 = (kv ? v_row0 : k_row0) + it * Tk;
           for (int k0 = 0; k0 < n; k0 += kXsChunkKeys) {
             const int keys = n - k0 < kXsChunkKeys ? n - k0 : kXsChunkKeys;
             const uint32_t mbytes = (kv == 0 && mask_bulk) ? static_cast<uint32_t>((keys + 15) & ~15) : 0u;
-            uint8_t* dst = ring + static_cast<size_t>(stage) * kXsStageBytes;
             mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(keys) * 128u + mbytes);
-            bulk_load_1d_hint(dst, src + static_cast<size_t>(k0) * 64, static_cast<uint32_t>(keys) * 128u, &full[stage], policy);
-            if (mbytes) bulk_load_1d(dst + kXsChunkBytes, key_ok + static_cast<size_t>(b) * Tk + k0, mbytes, &full[stage]);
+            // a box is always 64 rows: rows beyond this item's keys belong to the next item / slab (finite values,
+            // multiplied by p = 0) or lie beyond the tensor (zero fill)
+            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(kXsChunkBytes) + mbytes);
+            tma_load_2d_hint(ring + static_cast<size_t>(stage) * kXsChunkBytes, tm, &full[stage], 0, row0 + k0, policy);
+            if (mbytes) bulk_load_1d(s_mask + stage * 64, key_ok + static_cast<size_t>(b) * Tk + k0, mbytes, &full[stage]);
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -124,65 +163,72 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
         }
       }
     }
-    return;  // (the bulk copies complete on barriers the consumer warps wait on: the CTA outlives them)
+    return;  // (the copies complete on barriers the consumer warps wait on: the CTA outlives them)
   }
 
-  // -------------------------------------------------------------- consumers (4 warps = attn_decode_kernel's CTA)
-  const int ks = lane >> 3, dg = lane & 7;
+  // -------------------------------------------------------------- consumers
+  const int gid = lane >> 2, tig = lane & 3;  // mma fragment coordinates: group (row) and thread in group
+  const int tid = threadIdx.x;                // 0..127
   int stage = 0;
   uint32_t phase = 0;
-  // software pipeline over items: the next item's query and extent are fetched while this one streams
-  float qf[8];
-  int n = 0;
-  auto load_q = [&](int it, float (&dst)[8], int& nn) {
-    const uint4 qv = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(it) * 64 + dg * 8);
-    dst[0] = act_lo(qv.x); dst[1] = act_hi(qv.x); dst[2] = act_lo(qv.y); dst[3] = act_hi(qv.y);
-    dst[4] = act_lo(qv.z); dst[5] = act_hi(qv.z); dst[6] = act_lo(qv.w); dst[7] = act_hi(qv.w);
-    nn = extent[it / H];
+  // ldmatrix row / 16-byte-unit provided by this lane (128-byte swizzle: physical unit = unit ^ (row & 7))
+  //   Q K^T (A = K rows, not transposed): matrices (keys 0-7, d 0-7), (keys 8-15, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 8-15)
+  const int a_row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // key row of this warp's 16-key tile
+  const int a_unit = lane >> 4;                                      // + 2 * kstep
+  //   P V (A = V^T, transposed load): matrices (keys 0-7, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 0-7), (keys 8-15, d 8-15)
+  const int v_row = (lane & 7) + ((lane >> 4) & 1) * 8;              // + 16 * kstep (keys)
+  const int v_unit = warp * 2 + ((lane >> 3) & 1);                   // this warp's 16-d tile
+  // software pipeline over items: the next item's query is fetched while this one streams
+  uint32_t q_next = 0;
+  int nn = 0;
+  auto fetch_q = [&](int it) -> uint32_t {  // 64 act_t = 32 words: one per lane of warp 0
+    return warp == 0 ? reinterpret_cast<const uint32_t*>(q + static_cast<size_t>(it) * 64)[lane] : 0u;
   };
-  if (first < n_items) load_q(first, qf, n);
+  if (first < n_items) {
+    q_next = fetch_q(first);
+    nn = extent[first / H];
+  }
   for (int it = first; it < n_items; it += stride) {
     const int b = it / H;
-    const int nkeys = n;
-    float qn[8];
-    int nn = 0;
+    const int nkeys = nn;
+    if (warp == 0) reinterpret_cast<uint32_t*>(s_q)[lane] = q_next;
     const int nxt = it + stride;
-    if (nxt < n_items) load_q(nxt, qn, nn);
+    if (nxt < n_items) {
+      q_next = fetch_q(nxt);
+      nn = extent[nxt / H];
+    }
     if (late_pdl && it == last_item) pdl_launch_dependents();
+    xs_bar_sync();  // s_q visible (and the previous item's s_p / s_scores no longer read)
+    // B operand of Q K^T: q in column 0, i.e. in the lanes of group 0
+    uint32_t qb[8];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qb[2 * ks] = gid == 0 ? reinterpret_cast<const uint32_t*>(s_q)[ks * 8 + tig] : 0u;
+      qb[2 * ks + 1] = gid == 0 ? reinterpret_cast<const uint32_t*>(s_q)[ks * 8 + 4 + tig] : 0u;
+    }
     const unsigned char* ok_row = key_ok + static_cast<size_t>(b) * Tk;
 
-    // ---------------- phase 1: scores (keys 4*warp + ks + 16u of every 128-key block, u = 0..7, as in attn_decode_kernel)
+    // ---------------- phase 1: scores of this warp's 16 keys of every 64-key chunk
     for (int k0 = 0; k0 < nkeys; k0 += kXsChunkKeys) {
-      // this lane group's four keys of the chunk: chunk-local key 4*warp + ks + 16*uu
-      unsigned char okv[4] = {0, 0, 0, 0};
-      if (!mask_bulk && dg == 0) {
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int j = k0 + warp * 4 + ks + 16 * uu;
-          okv[uu] = j < nkeys ? ok_row[j] : 0;
-        }
-      }
       mbar_wait(&full[stage], phase);
-      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsStageBytes + dg * 16;
-      if (mask_bulk && dg == 0) {
-        const uint8_t* okb = ring + static_cast<size_t>(stage) * kXsStageBytes + kXsChunkBytes;
+      const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * kXsChunkBytes) + a_row * 128;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int uu = 0; uu < 4; ++uu) okv[uu] = okb[warp * 4 + ks + 16 * uu];
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(a, base + (((2 * ks + a_unit) ^ (a_row & 7)) << 4));
+        mma_16816(acc, a, qb[2 * ks], qb[2 * ks + 1]);
       }
-      uint4 kv[4];
+      if (tig == 0) {  // column 0: rows gid (acc[0]) and gid + 8 (acc[2]) of the tile
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int jl = warp * 4 + ks + 16 * uu;
-        kv[uu] = k0 + jl < nkeys ? *reinterpret_cast<const uint4*>(base + jl * 128) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int j = k0 + warp * 4 + ks + 16 * uu;
-        float s = dot8(kv[uu], qf);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (dg == 0 && j < nkeys) s_scores[j] = okv[uu] ? act_round(s) : kActMin;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int jl = warp * 16 + gid + 8 * hh;
+          const int j = k0 + jl;
+          if (j < nkeys) {
+            const bool ok = mask_bulk ? s_mask[stage * 64 + jl] != 0 : ok_row[j] != 0;
+            s_scores[j] = ok ? act_round(acc[2 * hh]) : kActMin;
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -193,8 +239,7 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
     }
     xs_bar_sync();
 
-    // ---------------- softmax statistics over the rounded scores (fp32, exact two-pass; same order as attn_decode_kernel)
-    const int tid = threadIdx.x;  // 0..127
+    // ---------------- softmax statistics over the rounded scores (fp32, exact two-pass)
     float mx = -INFINITY;
     for (int j = tid; j < nkeys; j += kXsConsumerWarps * 32) mx = fmaxf(mx, s_scores[j]);
 #pragma unroll
@@ -213,35 +258,26 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
     if (lane == 0) s_stat[4 + warp] = sum;
     xs_bar_sync();
     sum = (s_stat[4] + s_stat[5]) + (s_stat[6] + s_stat[7]);
-    for (int j = tid; j < nkeys; j += kXsConsumerWarps * 32) s_scores[j] = act_round(s_scores[j] / sum);
+    // p in the activation type; zero beyond the row's keys up to the end of the last chunk (the V rows there
+    // belong to somebody else)
+    const int nk64 = (nkeys + kXsChunkKeys - 1) & ~(kXsChunkKeys - 1);
+    for (int j = tid; j < nk64; j += kXsConsumerWarps * 32) s_p[j] = float2act(j < nkeys ? s_scores[j] / sum : 0.f);
     xs_bar_sync();
 
-    // ---------------- phase 2: out = P . V
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // ---------------- phase 2: out[d] = sum_j p_j V[j][d] for this warp's 16 values of d
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < nkeys; k0 += kXsChunkKeys) {
       mbar_wait(&full[stage], phase);
-      const uint8_t* base = ring + static_cast<size_t>(stage) * kXsStageBytes + dg * 16;
-      uint4 vv[4];
-      float p[4];
+      const uint32_t base = smem_u32(ring + static_cast<size_t>(stage) * kXsChunkBytes);
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_p + k0);  // pairs of p
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int jl = warp * 4 + ks + 16 * uu;
-        const bool ok = k0 + jl < nkeys;
-        vv[uu] = ok ? *reinterpret_cast<const uint4*>(base + jl * 128) : make_uint4(0, 0, 0, 0);
-        p[uu] = ok ? s_scores[k0 + jl] : 0.f;
-      }
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        acc[0] = fmaf(p[uu], act_lo(vv[uu].x), acc[0]);
-        acc[1] = fmaf(p[uu], act_hi(vv[uu].x), acc[1]);
-        acc[2] = fmaf(p[uu], act_lo(vv[uu].y), acc[2]);
-        acc[3] = fmaf(p[uu], act_hi(vv[uu].y), acc[3]);
-        acc[4] = fmaf(p[uu], act_lo(vv[uu].z), acc[4]);
-        acc[5] = fmaf(p[uu], act_hi(vv[uu].z), acc[5]);
-        acc[6] = fmaf(p[uu], act_lo(vv[uu].w), acc[6]);
-        acc[7] = fmaf(p[uu], act_hi(vv[uu].w), acc[7]);
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        const int row = ks * 16 + v_row;
+        ldmatrix_x4_trans(a, base + row * 128 + ((v_unit ^ (row & 7)) << 4));
+        const uint32_t b0 = gid == 0 ? pw[ks * 8 + tig] : 0u;
+        const uint32_t b1 = gid == 0 ? pw[ks * 8 + 4 + tig] : 0u;
+        mma_16816(o, a, b0, b1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -250,28 +286,11 @@ attn_cross_stream_kernel(const act_t* __restrict__ q,    // [B, H*64]
         phase ^= 1u;
       }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    if (tig == 0) {
+      act_t* dst = ctx + static_cast<size_t>(it) * 64 + warp * 16 + gid;
+      dst[0] = float2act(o[0]);
+      dst[8] = float2act(o[2]);
     }
-    if (ks == 0) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_red[warp * 64 + dg * 8 + e] = acc[e];
-    }
-    xs_bar_sync();
-    if (tid < 32) {
-      const int d0 = tid * 2;
-      const float o0 = (s_red[d0] + s_red[64 + d0]) + (s_red[128 + d0] + s_red[192 + d0]);
-      const float o1 = (s_red[d0 + 1] + s_red[64 + d0 + 1]) + (s_red[128 + d0 + 1] + s_red[192 + d0 + 1]);
-      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(it) * 64 + d0) = pack_act2(o0, o1);
-    }
-    // (a warp may run ahead into the next item's phase 1 and overwrite s_scores while warp 0 still reads s_red:
-    // different arrays; every warp's phase-2 reads of s_scores completed before the barrier above, and s_red is
-    // next written four barriers later)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) qf[e] = qn[e];
-    n = nn;
   }
   if (late_pdl && first >= n_items) pdl_launch_dependents();
   if (stamps.slots != nullptr && threadIdx.x == 0) {

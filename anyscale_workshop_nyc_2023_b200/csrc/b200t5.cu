@@ -235,6 +235,7 @@ struct Plan {
   int n_vtiles = 0;
   // tensor maps for activations (A operands)
   CUtensorMap tm_xn, tm_ctx, tm_hff, tm_qkv_attn;
+  CUtensorMap tm_cross_kv;  // [Ld*2*B*H*S, 64] view of the cross-KV arena, box 64 x 64 keys (attention_cross_stream.cuh)
   // decode chains: the batch is cut into independent row ranges that run concurrently (one
   // stream each inside the step graph); every chain sees pointer-offset views of the same buffers
   struct Chain {
@@ -1025,6 +1026,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_ctx, pl->ctx.p, M, I, 128);
   TMAP_FFO(h, &pl->tm_hff, pl->hff.p, M, F, 128);
   TMAP(h, &pl->tm_qkv_attn, pl->qkv.p, M, 3 * I, 128);
+  TMAP(h, &pl->tm_cross_kv, pl->cross_kv.p, static_cast<uint64_t>(c.Ld) * 2 * B * H * S, 64, kXsChunkKeys);
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
     // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
@@ -1236,37 +1238,37 @@ static int chain_layer_pre(b200t5_ctx* h, cudaStream_t s, const ChainView& v, in
   return B200T5_OK;
 }
 
-// One cross-attention launch over rows [b0, b0 + nb) of layer l's K/V planes (`ext` / `ok` are row-b0-relative).
+// One cross-attention launch over rows [b0, b0 + nb) of layer l (`q`, `ctx`, `ext`, `ok` are row-b0-relative).
 // `slot` < 0: no in-situ stamps.
-static cudaError_t launch_cross_attention(b200t5_ctx* h, cudaStream_t s, bool pdl, const act_t* q, const act_t* kplane,
-                                          const act_t* vplane, act_t* ctx, int nb, const int* ext, const unsigned char* ok,
-                                          int slot) {
+static cudaError_t launch_cross_attention(b200t5_ctx* h, cudaStream_t s, bool pdl, int l, int b0, int nb, const act_t* q,
+                                          act_t* ctx, const int* ext, const unsigned char* ok, int slot) {
   const Cfg& c = h->c;
   Plan& p = *h->plan;
+  const int B = p.B, S = p.S, I = c.I;
   XsStamps st{slot >= 0 && p.xs_stamps.p ? p.xs_stamps.as<unsigned long long>() : nullptr, slot >= 0 ? slot : 0};
   if (h->xattn_stream) {
     const int items = nb * c.H;
+    const int k_row0 = ((l * 2) * B + b0) * c.H * S, v_row0 = ((l * 2 + 1) * B + b0) * c.H * S;
     return launch_kernel(attn_cross_stream_kernel, dim3(xs_grid(items, h->num_sms)), dim3(kXsThreads),
-                         XsSmem::bytes(h->xs_stages, p.S), s, pdl, q, kplane, vplane, ctx, items, c.H, p.S, ext, ok, h->xs_stages,
-                         h->xs_late_pdl ? 1 : 0, st);
+                         XsSmem::bytes(h->xs_stages, S), s, pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, q, ctx, items, c.H, S,
+                         ext, ok, h->xs_stages, h->xs_late_pdl ? 1 : 0, st);
   }
-  return launch_kernel(attn_decode_kernel<false>, dim3(nb * c.H), dim3(kAttnDecThreads), p.S * sizeof(float), s, pdl, q, kplane,
-                       vplane, ctx, c.H, p.S, ext, ok, nullptr, nullptr, st, 0);
+  const act_t* kplane = p.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(b0) * I * S;
+  return launch_kernel(attn_decode_kernel<false>, dim3(nb * c.H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl, q, kplane,
+                       kplane + static_cast<size_t>(B) * I * S, ctx, c.H, S, ext, ok, nullptr, nullptr, st, 0);
 }
 
 // layer l, cross-attention over the encoder keys (the HBM-streaming kernel)
 static int chain_layer_cross(b200t5_ctx* h, cudaStream_t s, const ChainView& v, int l, int chain_index) {
-  const Cfg& c = h->c;
   Plan& p = *h->plan;
-  const int B = p.B, S = p.S, I = c.I;
-  act_t* ckv = p.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(v.b0) * I * S;
+  const int S = p.S;
   struct PrioGuard {
     int saved;
     PrioGuard() : saved(launch_priority()) { launch_priority() = 0; }
     ~PrioGuard() { launch_priority() = saved; }
   } guard;
-  CU_OK(h, launch_cross_attention(h, s, h->use_pdl, v.dq, ckv, ckv + static_cast<size_t>(B) * I * S, v.dctx, v.nb,
-                                  p.live_extent.as<int>() + v.b0, p.live_key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S,
+  CU_OK(h, launch_cross_attention(h, s, h->use_pdl, l, v.b0, v.nb, v.dq, v.dctx, p.live_extent.as<int>() + v.b0,
+                                  p.live_key_ok.as<unsigned char>() + static_cast<size_t>(v.b0) * S,
                                   h->profile_xattn ? l * p.n_chains + chain_index : -1));
   h->launches++;
   return B200T5_OK;
@@ -1740,7 +1742,6 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_l
   Plan& p = *h->plan;
   const Cfg& c = h->c;
   const int rows = rows_per_launch > 0 && rows_per_launch < p.B ? rows_per_launch : p.B;
-  const size_t cross_layer = static_cast<size_t>(2) * p.B * c.I * p.S;
   int launches = 0;
   cudaError_t le = cudaSuccess;
   auto sweep = [&]() {
@@ -1748,10 +1749,9 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_l
     for (int l = 0; l < c.Ld; ++l) {
       for (int b0 = 0; b0 < p.B; b0 += rows) {
         const int nb = p.B - b0 < rows ? p.B - b0 : rows;
-        act_t* ckv = p.cross_kv.as<act_t>() + l * cross_layer + static_cast<size_t>(b0) * c.I * p.S;
-        cudaError_t e = launch_cross_attention(h, s, false, p.dq.as<act_t>() + static_cast<size_t>(b0) * c.I, ckv,
-                                               ckv + static_cast<size_t>(p.B) * c.I * p.S, p.dctx.as<act_t>() + static_cast<size_t>(b0) * c.I,
-                                               nb, p.extent.as<int>() + b0, p.key_ok.as<unsigned char>() + static_cast<size_t>(b0) * p.S, -1);
+        cudaError_t e = launch_cross_attention(h, s, false, l, b0, nb, p.dq.as<act_t>() + static_cast<size_t>(b0) * c.I,
+                                               p.dctx.as<act_t>() + static_cast<size_t>(b0) * c.I, p.extent.as<int>() + b0,
+                                               p.key_ok.as<unsigned char>() + static_cast<size_t>(b0) * p.S, -1);
         if (e != cudaSuccess) le = e;
         ++launches;
       }
@@ -2104,9 +2104,11 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
     const int stages = step > 0 ? step : 5;
     if (stages < 2 || stages > kXsMaxStages || Tk > 4096) return fail(nullptr, B200T5_EINVAL, "attn_decode(stream): 2 <= stages <= %d, Tk <= 4096", kXsMaxStages);
     const int items = B * H;
+    CUtensorMap tk, tv;
+    if (!make_tmap(&tk, K, static_cast<uint64_t>(items) * Tk, 64, kXsChunkKeys) || !make_tmap(&tv, V, static_cast<uint64_t>(items) * Tk, 64, kXsChunkKeys))
+      return fail(nullptr, B200T5_ECUDA, "%s", g_err);
     attn_cross_stream_kernel<<<xs_grid(items, sms), kXsThreads, XsSmem::bytes(stages, Tk), s>>>(
-        static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), items, H, Tk,
-        extent, key_ok, stages, 1, XsStamps{nullptr, 0});
+        tk, tv, 0, 0, static_cast<const act_t*>(q), static_cast<act_t*>(ctx), items, H, Tk, extent, key_ok, stages, 1, XsStamps{nullptr, 0});
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
         static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), H,

@@ -294,10 +294,12 @@ def test_cross_attn_decode(lib, B, H, S, impl):
 
 @pytest.mark.parametrize("stages", [2, 5, 12])
 @pytest.mark.parametrize("B,H,S", [(256, 12, 512), (7, 3, 77), (64, 16, 200), (300, 12, 64), (5, 3, 513), (2, 1, 1)])
-def test_cross_attn_stream_kernel_is_bit_identical(lib, B, H, S, stages):
-    """The bulk-copy stream kernel keeps the per-thread-load kernel's key -> (warp, lane, slot) assignment and the
-    order of every fp32 accumulation, so the two return the same bits: ragged extents, mask holes, retired rows
-    (extent 0), persistent CTAs with several items each (B*H > 2 * SMs), every ring depth."""
+def test_cross_attn_stream_kernel_matches_the_per_thread_load_kernel(lib, B, H, S, stages):
+    """The TMA-stream / mma.sync kernel against the per-thread-load kernel on the same inputs: same rounding points, only
+    the order of the fp32 accumulations differs (tensor core vs sequential), so the outputs agree to 1 bf16 ulp and are
+    bit-identical in all but a few percent of the elements. Ragged extents, mask holes, retired rows (extent 0),
+    persistent CTAs with several items each (B*H > 2 * SMs), every ring depth, S not a multiple of the 64-key chunk
+    or of 16 (mask bytes read from global memory instead of riding the ring)."""
     g = torch.Generator(device="cuda").manual_seed(B * S + stages)
     q = (torch.randn(B, H, 64, device="cuda", generator=g) * 0.3).bfloat16()
     K = torch.randn(B, H, S, 64, device="cuda", generator=g).bfloat16()
@@ -318,9 +320,15 @@ def test_cross_attn_stream_kernel_is_bit_identical(lib, B, H, S, stages):
         torch.cuda.synchronize()
         out.append(ctx)
     assert torch.isfinite(out[1].float()).all()
-    assert torch.equal(out[0].view(torch.int16), out[1].view(torch.int16))
+    assert (ulp_close(out[0], out[1], 1.0) | ((out[0].float() - out[1].float()).abs() <= 2e-3)).all()
+    assert (out[0] == out[1]).float().mean().item() > 0.9
     if B > 3:
         assert (out[1][3] == 0).all()
+    # deterministic
+    again = torch.empty_like(out[1])
+    _lib.check(lib.b200t5_test_attn_decode(DEV, 2, P(q), P(K), P(V), P(again), B, H, S, P(extent), P(key_ok), stages, None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(again.view(torch.int16), out[1].view(torch.int16))
 
 
 def _argmax_case(lib, x, W, step, eos, min_new):
