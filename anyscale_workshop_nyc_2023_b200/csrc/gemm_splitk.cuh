@@ -45,10 +45,12 @@ struct SkCfg {
   static constexpr int kDefaultStages = BN == 64 ? 4 : 3;
   static constexpr int kRedLd = BN + 4;  // floats; +4 keeps the per-row v4 stores of a warp conflict-free
   static constexpr int kRedBytes = kBM * kRedLd * 4;  // [src rank][row of the owner] = 128 slots whatever the split
-  static constexpr int smem_bytes(int stages) {
-    return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRedBytes + kEpiSmemBytes;
+  // `epi`: the epilogue functor stages a table in shared memory (GeGLU); the others get no scratch, which is what
+  // lets a BN = 64 CTA (131 KB) share an SM with two CTAs of the cross-attention stream (2 x 46 KB)
+  static constexpr int smem_bytes(int stages, bool epi) {
+    return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRedBytes + (epi ? kEpiSmemBytes : 0);
   }
-  static constexpr int kMaxSmemBytes = smem_bytes(kSkMaxStages);
+  static constexpr int kMaxSmemBytes = smem_bytes(kSkMaxStages, true);
 };
 
 // ---------------------------------------------------------------- cluster PTX
@@ -307,7 +309,7 @@ cudaError_t launch_gemm_splitk(const CUtensorMap& tmA, const CUtensorMap& tmB, i
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(split, (N + BN - 1) / BN, (M + kBM - 1) / kBM);
   cfg.blockDim = dim3(kSkThreads);
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages);
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(stages, Epi::kPaired);
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int na = 0;

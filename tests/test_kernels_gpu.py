@@ -296,7 +296,7 @@ def test_cross_attn_decode(lib, B, H, S, impl):
 @pytest.mark.parametrize("B,H,S", [(256, 12, 512), (7, 3, 77), (64, 16, 200), (300, 12, 64), (5, 3, 513), (2, 1, 1)])
 def test_cross_attn_stream_kernel_matches_the_per_thread_load_kernel(lib, B, H, S, stages):
     """The TMA-stream / mma.sync kernel against the per-thread-load kernel on the same inputs: same rounding points, only
-    the order of the fp32 accumulations differs (tensor core vs sequential), so the outputs agree to 1 bf16 ulp and are
+    the order of the fp32 accumulations differs (tensor core vs sequential), so the outputs agree to 2 bf16 ulps and are
     bit-identical in all but a few percent of the elements. Ragged extents, mask holes, retired rows (extent 0),
     persistent CTAs with several items each (B*H > 2 * SMs), every ring depth, S not a multiple of the 64-key chunk
     or of 16 (mask bytes read from global memory instead of riding the ring)."""
@@ -320,7 +320,7 @@ def test_cross_attn_stream_kernel_matches_the_per_thread_load_kernel(lib, B, H, 
         torch.cuda.synchronize()
         out.append(ctx)
     assert torch.isfinite(out[1].float()).all()
-    assert (ulp_close(out[0], out[1], 1.0) | ((out[0].float() - out[1].float()).abs() <= 2e-3)).all()
+    assert (ulp_close(out[0], out[1], 2.0) | ((out[0].float() - out[1].float()).abs() <= 2e-3)).all()
     assert (out[0] == out[1]).float().mean().item() > 0.9
     if B > 3:
         assert (out[1][3] == 0).all()
