@@ -85,13 +85,15 @@ DEVINL void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32
 __global__ void __maxnreg__(64)
 attn_cross_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                          int k_row0, int v_row0,
+                         const act_t* __restrict__ kplane,  // = row k_row0 of tmK's tensor (L2 prefetch of whole slabs)
+                         const act_t* __restrict__ vplane,  // = row v_row0 of tmV's tensor
                          const act_t* __restrict__ q,    // [B, H*64]
                          act_t* __restrict__ ctx,        // [B, H*64]
                          int n_items,                    // B * H
                          int H, int Tk,
                          const int* __restrict__ extent,            // [B] keys to visit (0 = retired row)
                          const unsigned char* __restrict__ key_ok,  // [B][Tk] 1 = attended
-                         int stages, int late_pdl, XsStamps stamps) {
+                         int stages, int late_pdl, int l2_prefetch, XsStamps stamps) {
   extern __shared__ uint8_t xs_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_mask = ring + static_cast<size_t>(stages) * kXsChunkBytes;          // [stages][64]
@@ -136,12 +138,27 @@ attn_cross_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int n_next = first < n_items ? extent[first / H] : 0;
+      // The ring alone (2 CTAs x `stages` x 8 KB per SM, what fits next to a GEMM CTA) cannot cover the latency of
+      // DRAM under a saturating stream (~2.7 us: the per-thread-load kernel keeps ~114 KB per SM in flight): the
+      // HBM -> L2 leg is therefore driven one whole item ahead by L2 prefetches of the next item's K and V slabs (two
+      // instructions per item, no shared memory, no completion tracking), and the ring only has to cover an L2 hit.
+      auto prefetch_item = [&](int it, int n) {
+        if (l2_prefetch && n > 0) {
+          const uint64_t keep = l2_policy_evict_last();
+          prefetch_l2_bulk(kplane + static_cast<size_t>(it) * Tk * 64, static_cast<uint32_t>(n) * 128u, keep);
+          prefetch_l2_bulk(vplane + static_cast<size_t>(it) * Tk * 64, static_cast<uint32_t>(n) * 128u, keep);
+        }
+      };
+      if (first < n_items) prefetch_item(first, n_next);
       for (int it = first; it < n_items; it += stride) {
         const int b = it / H;
         const int n = n_next;
         // (the next item's extent is fetched a whole item ahead: the ring holds < 2 us of stream, an L2 round trip
         // under load is of that order)
-        if (it + stride < n_items) n_next = extent[(it + stride) / H];
+        if (it + stride < n_items) {
+          n_next = extent[(it + stride) / H];
+          prefetch_item(it + stride, n_next);
+        }
 #pragma unroll 1
         for (int kv = 0; kv < 2; ++kv) {
           const CUtensorMap* tm = kv ? &tmV : &tmK;

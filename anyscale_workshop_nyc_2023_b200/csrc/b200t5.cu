@@ -316,6 +316,7 @@ struct b200t5_ctx {
   bool xattn_stream = false;  // (round 2, first measurements: 0.63 of the HBM peak alone against 0.96 for the per-thread-load kernel)
   int xs_stages = 5;        // 8 KB ring stages per CTA (two CTAs per SM): B200T5_XS_STAGES
   bool xs_late_pdl = true;  // release the dependent GEMM when a CTA starts its last item instead of at once: B200T5_XS_LATE_PDL
+  bool xs_l2_prefetch = true;    // drive HBM -> L2 one item ahead with bulk L2 prefetches (B200T5_XS_L2PF, "xattn_l2pf")
   bool xattn_serialize = false;  // one cross-attention kernel at a time across the chains (B200T5_XS_SERIALIZE, "xattn_serialize")
   std::vector<cudaEvent_t> xattn_ev;
   bool profile_xattn = false;  // b200t5_set_option("profile_xattn"): stamp every cross-attention launch inside the step graph
@@ -578,6 +579,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   }
   if (const char* lp_env = getenv("B200T5_XS_LATE_PDL")) h->xs_late_pdl = atoi(lp_env) != 0;
   if (const char* se_env = getenv("B200T5_XS_SERIALIZE")) h->xattn_serialize = atoi(se_env) != 0;
+  if (const char* pf_env = getenv("B200T5_XS_L2PF")) h->xs_l2_prefetch = atoi(pf_env) != 0;
   if (const char* sk_env = getenv("B200T5_SK")) {
     int v[8];
     const int n = sscanf(sk_env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
@@ -1254,9 +1256,11 @@ static cudaError_t launch_cross_attention(b200t5_ctx* h, cudaStream_t s, bool pd
   if (h->xattn_stream) {
     const int items = nb * c.H;
     const int k_row0 = ((l * 2) * B + b0) * c.H * S, v_row0 = ((l * 2 + 1) * B + b0) * c.H * S;
+    const act_t* arena = p.cross_kv.as<act_t>();
     return launch_kernel(attn_cross_stream_kernel, dim3(xs_grid(items, h->num_sms)), dim3(kXsThreads),
-                         XsSmem::bytes(h->xs_stages, S), s, pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0, q, ctx, items, c.H, S,
-                         ext, ok, h->xs_stages, h->xs_late_pdl ? 1 : 0, st);
+                         XsSmem::bytes(h->xs_stages, S), s, pdl, p.tm_cross_kv, p.tm_cross_kv, k_row0, v_row0,
+                         arena + static_cast<size_t>(k_row0) * 64, arena + static_cast<size_t>(v_row0) * 64, q, ctx, items, c.H, S,
+                         ext, ok, h->xs_stages, h->xs_late_pdl ? 1 : 0, h->xs_l2_prefetch ? 1 : 0, st);
   }
   const act_t* kplane = p.cross_kv.as<act_t>() + l * (static_cast<size_t>(2) * B * I * S) + static_cast<size_t>(b0) * I * S;
   return launch_kernel(attn_decode_kernel<false>, dim3(nb * c.H), dim3(kAttnDecThreads), S * sizeof(float), s, pdl, q, kplane,
@@ -1828,6 +1832,7 @@ extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
     h->xs_stages = value;
   } else if (n == "xattn_late_pdl") h->xs_late_pdl = value != 0;
   else if (n == "xattn_serialize") h->xattn_serialize = value != 0;
+  else if (n == "xattn_l2pf") h->xs_l2_prefetch = value != 0;
   else if (n == "pdl") h->use_pdl = value != 0;
   else if (n == "admit_overlap") h->admit_overlap = value != 0;
   else if (n == "sk_stages64") h->sk_stages64 = value;
@@ -2135,7 +2140,8 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
     if (!make_tmap(&tk, K, static_cast<uint64_t>(items) * Tk, 64, kXsChunkKeys) || !make_tmap(&tv, V, static_cast<uint64_t>(items) * Tk, 64, kXsChunkKeys))
       return fail(nullptr, B200T5_ECUDA, "%s", g_err);
     attn_cross_stream_kernel<<<xs_grid(items, sms), kXsThreads, XsSmem::bytes(stages, Tk), s>>>(
-        tk, tv, 0, 0, static_cast<const act_t*>(q), static_cast<act_t*>(ctx), items, H, Tk, extent, key_ok, stages, 1, XsStamps{nullptr, 0});
+        tk, tv, 0, 0, static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<const act_t*>(q), static_cast<act_t*>(ctx), items, H,
+        Tk, extent, key_ok, stages, 1, 1, XsStamps{nullptr, 0});
   } else {
     attn_decode_kernel<false><<<B * H, kAttnDecThreads, Tk * sizeof(float), s>>>(
         static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx), H,

@@ -320,8 +320,23 @@ def test_cross_attn_stream_kernel_matches_the_per_thread_load_kernel(lib, B, H, 
         torch.cuda.synchronize()
         out.append(ctx)
     assert torch.isfinite(out[1].float()).all()
-    assert (ulp_close(out[0], out[1], 2.0) | ((out[0].float() - out[1].float()).abs() <= 2e-3)).all()
+    # A score whose fp32 value sits on a bf16 rounding boundary can round differently under the two accumulation
+    # orders; on a row with few keys that moves p (and the output) by up to a bf16 ulp of the SCORE, not of the
+    # output. Such flips are rare: bound their number and their size, and hold everything else to 2 ulps.
+    diff = (out[0].float() - out[1].float()).abs()
+    within = ulp_close(out[0], out[1], 2.0) | (diff <= 2e-3)
+    print(f"stream vs per-thread-load: equal {(out[0] == out[1]).float().mean().item():.4f}, beyond 2 ulp {(~within).float().mean().item():.2e}, max |diff| {diff.max().item():.4f}")
+    assert (~within).float().mean().item() <= 2e-4 and diff.max().item() <= 0.06
     assert (out[0] == out[1]).float().mean().item() > 0.9
+    # and both against the fp32 restatement with HF's rounding points (as test_cross_attn_decode)
+    okb = key_ok.bool()
+    mask_add = torch.where(okb, 0.0, BF16_MIN).to(torch.bfloat16)[:, None, :].expand(B, H, S)
+    keep = (extent > 0) & okb.any(1)
+    ref = torch_attn_decode(q, K, V, mask_add).reshape(B, H * 64)
+    for o in out:
+        err = (o.float() - ref.float()).abs()[keep]
+        tol = 2 * 2.0 ** -7 * ref.float().abs()[keep] + 2e-3
+        assert (err > tol).float().mean().item() <= 2e-4 and err.max().item() <= 0.06
     if B > 3:
         assert (out[1][3] == 0).all()
     # deterministic
