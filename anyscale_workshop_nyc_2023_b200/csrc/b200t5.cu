@@ -313,10 +313,11 @@ struct b200t5_ctx {
   // Cross-attention of the decode step: the bulk-copy stream kernel (attention_cross_stream.cuh; bandwidth independent
   // of the warps resident per SM, so it survives sharing the SMs with the other chain's GEMM CTAs) or, B200T5_XATTN=ldg,
   // the per-thread-load kernel of round 1 (attention_decode.cuh). Bit-identical results.
-  bool xattn_stream = false;  // (round 2, first measurements: 0.63 of the HBM peak alone against 0.96 for the per-thread-load kernel)
+  bool xattn_stream = true;
   int xs_stages = 5;        // 8 KB ring stages per CTA (two CTAs per SM): B200T5_XS_STAGES
   bool xs_late_pdl = true;  // release the dependent GEMM when a CTA starts its last item instead of at once: B200T5_XS_LATE_PDL
-  bool xs_l2_prefetch = true;    // drive HBM -> L2 one item ahead with bulk L2 prefetches (B200T5_XS_L2PF, "xattn_l2pf")
+  bool xs_l2_prefetch = false;   // drive HBM -> L2 one item ahead with bulk L2 prefetches (B200T5_XS_L2PF, "xattn_l2pf"): measured SLOWER
+                                 // (alone 0.71 instead of 0.82 of the HBM peak, decode 235 instead of 203 ms: profiles/decode_r2.md)
   bool xattn_serialize = false;  // one cross-attention kernel at a time across the chains (B200T5_XS_SERIALIZE, "xattn_serialize")
   std::vector<cudaEvent_t> xattn_ev;
   bool profile_xattn = false;  // b200t5_set_option("profile_xattn"): stamp every cross-attention launch inside the step graph
@@ -572,7 +573,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
-  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "stream") == 0;
+  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "ldg") != 0;
   if (const char* xs_env = getenv("B200T5_XS_STAGES")) {
     const int v = atoi(xs_env);
     if (v >= 2 && v <= kXsMaxStages) h->xs_stages = v;

@@ -240,11 +240,12 @@ def test_cross_attention_kernels_give_identical_tokens(models):
         gated_b, _ = gated_prefix_match(stream.numpy(), base.numpy(), margins)
         print(f"stream kernel: vs oracle gated={gated:.2f} full={full:.2f}; vs per-thread-load kernel gated={gated_b:.2f} equal rows={gated_prefix_match(stream.numpy(), base.numpy(), margins)[1]:.2f}")
         assert gated == 1.0 and gated_b == 1.0
-        for name, value in (("chains", 1), ("chains", 3), ("xattn_stages", 2), ("xattn_late_pdl", 0)):
+        for name, value in (("chains", 1), ("chains", 3), ("xattn_stages", 2), ("xattn_late_pdl", 0), ("xattn_serialize", 1), ("xattn_l2pf", 1)):
             model.set_option(name, value)
             assert torch.equal(model.generate(**kw).cpu(), stream), (name, value)
+        model.set_option("xattn_l2pf", 0)
     finally:
-        for name, value in (("xattn", 0), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1)):
+        for name, value in (("xattn", 1), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1), ("xattn_serialize", 0)):
             model.set_option(name, value)
 
 

@@ -1,21 +1,10 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_kernels_gpu.py -x -q -s -k "cross_attn" > gpurun_out/k1.log 2>&1; echo "K1 rc=$?"; grep "stream vs" gpurun_out/k1.log | sort | uniq -c | sort -rn | head -20; tail -3 gpurun_out/k1.log | cut -c1-300
-python - <<'PY'
-import sys, torch
-sys.path.insert(0, '.')
-from anyscale_workshop_nyc_2023_b200.modeling import B200T5ForConditionalGeneration
-from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_token_batch
-from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir
-m = B200T5ForConditionalGeneration.from_pretrained(checkpoint_dir("flan-t5-base", 0))
-ids, mask = synthetic_token_batch(256, 512, 32128, seed=1, lengths="full")
-ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
-m.set_option("xattn", 1)
-for pf in (0, 1):
-  for st in (3, 5, 7):
-    m.set_option("xattn_l2pf", pf); m.set_option("xattn_stages", st)
-    m.generate(input_ids=ids, attention_mask=mask, max_new_tokens=8, min_new_tokens=8)
-    for rows in (0, 128, 86, 64):
-        r = m.bench_cross_attention(reps=5, rows_per_launch=rows)
-        print("ISOLATED l2pf=%d stages=%d rows=%d us=%.1f frac=%.3f" % (pf, st, rows, r["ms_per_launch"] * 1e3, r["bytes_per_launch"] / r["ms_per_launch"] / 1e6 / 6572.2), flush=True)
-PY
-timeout 500 python tools/sweep_decode.py --configs "chains=2,xattn=1,xattn_serialize=1;chains=2,xattn=1,xattn_serialize=1,xattn_l2pf=0;chains=3,xattn=1,xattn_serialize=1;chains=4,xattn=1,xattn_serialize=1;chains=2,xattn=1,xattn_serialize=1,xattn_stages=4;chains=3,xattn=1,xattn_serialize=1,xattn_stages=4;chains=2,xattn=1,xattn_serialize=1,xattn_stages=3;chains=2,xattn=1;chains=3,xattn=1,xattn_serialize=1,xattn_stages=3;chains=3,xattn=1" --reps 3 > gpurun_out/sweep5.log 2>gpurun_out/sweep5.err; echo "SWEEP rc=$?"; cut -c1-300 gpurun_out/sweep5.log; tail -3 gpurun_out/sweep5.err
+rm -f gpurun_out/parity_headline.jsonl
+timeout 700 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "PYTEST rc=$?"; tail -6 gpurun_out/pytest_gpu.log | cut -c1-300
+timeout 400 python bench.py --steps 5 > gpurun_out/bench_r2_b.json 2>gpurun_out/bench_r2_b.err; echo "BENCH rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_r2_b.json')); print({k:d[k] for k in ('ms_per_step','value')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['frac_isolated_chain_rows'], d['decode_loop']['ms'], d['encoder']['ms'], d.get('parity'), d.get('incumbent_hf_gpu',{}).get('value'), d.get('cpu_baseline',{}).get('value'))"
+for X in stream ldg; do B200T5_XATTN=$X timeout 200 python bench.py --steps 5 --lengths alpaca --no-cpu-baseline --hf-gpu-batches 0 --parity-rows 0 > gpurun_out/bench_alpaca_$X.json 2>gpurun_out/bench_alpaca_$X.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_alpaca_$X.json')); print('ALPACA $X', d['ms_per_step'], d['decode_loop']['ms'], d['encoder']['ms'])"; done
+for X in stream ldg; do for O in 1 0; do B200T5_XATTN=$X B200T5_ADMIT_OVERLAP=$O timeout 200 python tools/bench_stream.py --n 4096 --lengths full > gpurun_out/stream_full_${X}_$O.json 2>gpurun_out/stream_err.log; echo "STREAM full $X overlap=$O"; cut -c1-600 gpurun_out/stream_full_${X}_$O.json; done; done
+B200T5_ADMIT_OVERLAP=1 timeout 200 python tools/bench_stream.py --n 4096 --lengths alpaca > gpurun_out/stream_alpaca_1.json 2>>gpurun_out/stream_err.log; echo "STREAM alpaca overlap=1"; cut -c1-600 gpurun_out/stream_alpaca_1.json
+B200T5_ADMIT_OVERLAP=0 timeout 200 python tools/bench_stream.py --n 4096 --lengths alpaca > gpurun_out/stream_alpaca_0.json 2>>gpurun_out/stream_err.log; echo "STREAM alpaca overlap=0"; cut -c1-600 gpurun_out/stream_alpaca_0.json
