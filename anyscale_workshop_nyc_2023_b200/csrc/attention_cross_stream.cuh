@@ -79,6 +79,23 @@ DEVINL void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Release of a ring slot. The arrive is PREDICATED ON THE ACCUMULATOR of the last mma that consumed the slot: mma.sync
+// has no memory semantics, so without a data dependency ptxas is free to schedule the arrive between the last
+// ldmatrix and the mma that waits for it (it did: LDSM, SYNCS.ARRIVE, HMMA) - the slot is then handed back while the
+// shared-memory read may still sit in the SM's memory queue, and with a GEMM CTA hammering shared memory on the same
+// SM the refill occasionally won (run-to-run different tokens, round 2; profiles/decode_r2.md section 7). The
+// compare is never false (an mma produces the canonical NaN only), but ptxas cannot know that.
+DEVINL void xs_release_slot(uint64_t* bar, float last_acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %1, 0x7fc12345;\n"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}"
+      ::"r"(smem_u32(bar)), "r"(__float_as_uint(last_acc))
+      : "memory");
+}
+
 // tmK / tmV: [rows, 64] views (box 64 x 64 rows, 128-byte swizzle) of the K and V planes; item `it` (= (row, head),
 // chain-relative) owns rows k_row0 + it * Tk .. + Tk of tmK and v_row0 + it * Tk .. of tmV.
 // <= 64 registers: two of these CTAs (20 K registers) and one split-K GEMM CTA (192 x 160) share an SM's 64 K
@@ -248,7 +265,7 @@ attn_cross_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (lane == 0) xs_release_slot(&empty[stage], acc[0]);
       if (++stage == stages) {
         stage = 0;
         phase ^= 1u;
@@ -297,7 +314,7 @@ attn_cross_stream_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         mma_16816(o, a, b0, b1);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (lane == 0) xs_release_slot(&empty[stage], o[0]);
       if (++stage == stages) {
         stage = 0;
         phase ^= 1u;

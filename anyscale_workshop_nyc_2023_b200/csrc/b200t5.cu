@@ -1633,7 +1633,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
   // no decode kernel reads: their live extent is 0 until admit_slots_kernel starts them); the admitted slots join
   // at the next poll boundary. B200T5_ADMIT_OVERLAP=0 keeps everything on one stream (round-1 behaviour).
   enum : char { FREE = 0, PENDING = 1, ACTIVE = 2 };
-  std::vector<char> state(B, FREE);
+  std::vector<char> state(B, FREE), stepped(B, 0);
   long long next = 0, done = 0;
   int active = 0, steps = 0, n_free = B;
   bool pending = false, enc_used = false;
@@ -1666,6 +1666,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     // ---- (b) `poll` decode steps for every slot (eight = one graph launch); queued BEFORE the next admission's
     //          encoder pass so that the two overlap
     const bool stepping = active > 0;
+    for (int b = 0; b < B; ++b) stepped[b] = state[b] == ACTIVE;  // slots admitted later in this round have not stepped yet
     if (stepping) {
       if (poll % kStepsPerGraph == 0) {
         for (int r = 0; r < poll / kStepsPerGraph; ++r) CU_OK(h, cudaGraphLaunch(p.gexec8, s));
@@ -1722,7 +1723,7 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     if (stepping) {
       CU_OK(h, cudaStreamSynchronize(s));
       for (int b = 0; b < B; ++b) {
-        if (state[b] == ACTIVE && !p.h_unf[b]) {
+        if (state[b] == ACTIVE && stepped[b] && !p.h_unf[b]) {
           state[b] = FREE;
           ++n_free;
           --active;

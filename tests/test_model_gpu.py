@@ -516,6 +516,25 @@ def test_headline_config_flan_t5_base_b256_s512_t128(models, models_fp16, dtype_
         assert m["tf_argmax_agreement"] >= fl["tf_argmax_agreement"] - 0.02, (mode, m, fl)
 
 
+def test_run_to_run_determinism_at_the_benched_shape(models):
+    """Two row-chains, eight steps per graph launch, PDL-chained kernels on two streams: the same call must return
+    the same tokens every time, forced length and natural EOS (retired rows), and the slot pool must equal the static
+    batches row for row at this size too (tools/diag_determinism.py is the long form of this test)."""
+    model, _ = models("flan-t5-base", 0)
+    spec = SPECS["flan-t5-base"]
+    ids, mask = synthetic_token_batch(512, 512, spec.vocab_size, seed=3, lengths="full")
+    forced = [model.generate_host(ids[:256], mask[:256], max_new_tokens=32, min_new_tokens=32)[0] for _ in range(3)]
+    assert all((forced[0] == f).all() for f in forced[1:])
+    nat = []
+    for _ in range(2):
+        o, ln = model.generate_host(ids[:256], mask[:256], max_new_tokens=128)
+        nat.append((pad_to(o, 129), ln))
+    assert (nat[0][0] == nat[1][0]).all() and (nat[0][1] == nat[1][1]).all()
+    assert len(set(nat[0][1].tolist())) > 5, "natural lengths should vary"
+    pool, plen = model.generate_stream(ids, mask, pool=256, max_new_tokens=128)
+    assert (pad_to(pool, 129)[:256] == nat[0][0]).all() and (plen[:256] == nat[0][1]).all()
+
+
 @pytest.mark.timeout(900, method="thread")
 def test_headline_config_flan_t5_large_b64(models):
     """BASELINE configs[3]'s model at a batch HF can anchor in seconds: 24 layers, d_model 1024, 16 heads."""

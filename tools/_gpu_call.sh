@@ -1,10 +1,10 @@
+#!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/parity_headline.jsonl
-timeout 700 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "PYTEST rc=$?"; tail -6 gpurun_out/pytest_gpu.log | cut -c1-300
-timeout 400 python bench.py --steps 5 > gpurun_out/bench_r2_b.json 2>gpurun_out/bench_r2_b.err; echo "BENCH rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_r2_b.json')); print({k:d[k] for k in ('ms_per_step','value')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['frac_isolated_chain_rows'], d['decode_loop']['ms'], d['encoder']['ms'], d.get('parity'), d.get('incumbent_hf_gpu',{}).get('value'), d.get('cpu_baseline',{}).get('value'))"
-for X in stream ldg; do B200T5_XATTN=$X timeout 200 python bench.py --steps 5 --lengths alpaca --no-cpu-baseline --hf-gpu-batches 0 --parity-rows 0 > gpurun_out/bench_alpaca_$X.json 2>gpurun_out/bench_alpaca_$X.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_alpaca_$X.json')); print('ALPACA $X', d['ms_per_step'], d['decode_loop']['ms'], d['encoder']['ms'])"; done
-for X in stream ldg; do for O in 1 0; do B200T5_XATTN=$X B200T5_ADMIT_OVERLAP=$O timeout 200 python tools/bench_stream.py --n 4096 --lengths full > gpurun_out/stream_full_${X}_$O.json 2>gpurun_out/stream_err.log; echo "STREAM full $X overlap=$O"; cut -c1-600 gpurun_out/stream_full_${X}_$O.json; done; done
-B200T5_ADMIT_OVERLAP=1 timeout 200 python tools/bench_stream.py --n 4096 --lengths alpaca > gpurun_out/stream_alpaca_1.json 2>>gpurun_out/stream_err.log; echo "STREAM alpaca overlap=1"; cut -c1-600 gpurun_out/stream_alpaca_1.json
-B200T5_ADMIT_OVERLAP=0 timeout 200 python tools/bench_stream.py --n 4096 --lengths alpaca > gpurun_out/stream_alpaca_0.json 2>>gpurun_out/stream_err.log; echo "STREAM alpaca overlap=0"; cut -c1-600 gpurun_out/stream_alpaca_0.json
+timeout 300 python tools/diag_determinism.py "xattn=1;xattn=1,chains=3;xattn=1,xattn_stages=2;xattn=1,sk_stages64=2,sk_stages128=2;xattn=0" > gpurun_out/diag_det5.log 2> gpurun_out/diag_det5.err
+cut -c1-200 gpurun_out/diag_det5.log
+timeout 600 python tools/sweep_decode.py --configs "chains=2,xattn=0;chains=2,xattn=1;chains=2,xattn=1,xattn_stages=6;chains=2,xattn=1,xattn_stages=4" > gpurun_out/sweep_fix_full.log 2>&1
+mv gpurun_out/sweep_decode.json gpurun_out/sweep_fix_full.json
+timeout 600 python tools/sweep_decode.py --lengths alpaca --configs "chains=2,xattn=0;chains=2,xattn=1" > gpurun_out/sweep_fix_alpaca.log 2>&1
+mv gpurun_out/sweep_decode.json gpurun_out/sweep_fix_alpaca.json
+tail -6 gpurun_out/sweep_fix_full.log; tail -3 gpurun_out/sweep_fix_alpaca.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -m gpu -x -q -k "attn or determinism or cross or slot_pool" > gpurun_out/pytest_fix.log 2>&1; tail -5 gpurun_out/pytest_fix.log

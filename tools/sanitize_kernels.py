@@ -126,6 +126,11 @@ def main():
             model.set_option("chains", 2)
             b = model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=4).cpu()
             assert torch.equal(a, b)
+            model.set_option("xattn", 1)  # the TMA-stream cross-attention kernel beside the other chain's GEMMs
+            model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=4)
+            ids2, mask2 = synthetic_token_batch(8, 192, spec.vocab_size, seed=4, lengths="full")
+            model.generate(input_ids=torch.from_numpy(ids2), attention_mask=torch.from_numpy(mask2), max_new_tokens=3)
+            model.set_option("xattn", 0)
             ids, mask = synthetic_token_batch(20, 24, spec.vocab_size, seed=3, lengths="uniform")
             model.generate_stream(ids, mask, pool=8, max_new_tokens=4)
             del model
