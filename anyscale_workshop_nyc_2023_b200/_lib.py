@@ -61,6 +61,8 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("decode_algo_bytes", C.c_double),
         ("encoder_flops", C.c_double),
+        ("xattn_kernel", C.c_int32),
+        ("row_chains", C.c_int32),
     ]
 
 
@@ -80,7 +82,7 @@ SIGNATURES = {
     "b200t5_get_stats": (_i, [_vp, C.POINTER(Stats)]),
     "b200t5_bench_cross_attn": (_i, [_vp, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_double), _vp]),
     "b200t5_set_option": (_i, [_vp, C.c_char_p, _i]),
-    "b200t5_get_xattn_profile": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "b200t5_get_xattn_profile": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200t5_test_lm_argmax": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200t5_encode": (_i, [_vp, _i64p, _i64p, _i, _i, _vp, _vp]),
     "b200t5_decode_logits": (_i, [_vp, _i64p, _i64p, _i, _i, _i64p, _i, _vp, _vp]),

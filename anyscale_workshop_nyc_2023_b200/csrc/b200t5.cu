@@ -223,13 +223,16 @@ struct Plan {
   // (retired: its K/V are no longer streamed). In slot-pool mode they describe the slots' CURRENT prompts while
   // extent / key_ok describe the prompts of the encoder pass being admitted.
   DevBuf live_extent, live_key_ok;
-  DevBuf xs_stamps, xs_acc;  // in-situ profile of the cross-attention launches: [Ld * chains][2] stamps / {ns, launches}
+  DevBuf xs_stamps, xs_acc;  // in-situ profile of the cross-attention launches: [Ld * chains][2] stamps / {ns, launches}, then [Ld][2] {busy ns, layers}
   // slot pool (b200t5_generate_stream): per-slot position and result row, admission lists, [N, Tmax+1] results
   DevBuf pos, out_row, admit;
   DevBuf stream_out, stream_len;
   size_t stream_cap = 0;   // rows stream_out / stream_len hold (the step graph bakes their addresses)
   bool stream_mode = false;
   int g_stream = -1;
+  int g_xattn = -1;           // cross-attention kernel baked into the step graph (0 per-thread-load, 1 stream)
+  bool xattn_stream = false;  // ... and the one launch_cross_attention issues now
+  long long rows_valid = 0;   // valid prompt tokens of the last encoder pass (packed rows)
   int* h_unf = nullptr;    // pinned: unfinished[B] read back every graph launch
   int* h_admit = nullptr;  // pinned: [3][B] = row_on flags, slots, rows
   int n_vtiles = 0;
@@ -310,10 +313,14 @@ struct b200t5_ctx {
   bool use_2cta = true;   // encoder GEMMs on CTA pairs (gemm_2cta.cuh); B200T5_2CTA=0 selects the single-CTA kernel
   bool self_block = true;  // decoder self-attention with a 4-warp CTA per (row, head): two memory round trips whatever t is
                            // (measured: decode 201.5 -> 188.3 ms per batch); B200T5_SELF=warp selects one warp per (row, head)
-  // Cross-attention of the decode step: the bulk-copy stream kernel (attention_cross_stream.cuh; bandwidth independent
-  // of the warps resident per SM, so it survives sharing the SMs with the other chain's GEMM CTAs) or, B200T5_XATTN=ldg,
-  // the per-thread-load kernel of round 1 (attention_decode.cuh). Bit-identical results.
-  bool xattn_stream = true;
+  // Cross-attention of the decode step: the TMA-ring + mma.sync stream kernel (attention_cross_stream.cuh: small
+  // footprint, shares the SMs with the other chain's GEMM CTAs; the faster step when every prompt fills the window:
+  // decode 187.6 vs 191.0 ms at 512 keys per row, the layer's K/V stream at 0.92 vs 0.84 of the HBM peak in situ) or the
+  // per-thread-load kernel (attention_decode.cuh: one short-lived CTA per (row, head), seven per SM; the faster one on
+  // ragged prompts: 148.3 vs 165.7 ms at uniform lengths, 117.8 vs 123.4 at alpaca-like ones). 2 = choose per call from
+  // the batch's fill (valid prompt tokens / B*S >= kXattnStreamFill -> stream); B200T5_XATTN=ldg|stream|auto, option
+  // "xattn" 0|1|2. The kernels differ only in the order of their fp32 accumulations (same tokens up to near-ties).
+  int xattn_mode = 2;
   int xs_stages = 5;        // 8 KB ring stages per CTA (two CTAs per SM): B200T5_XS_STAGES
   bool xs_late_pdl = true;  // release the dependent GEMM when a CTA starts its last item instead of at once: B200T5_XS_LATE_PDL
   bool xs_l2_prefetch = false;   // drive HBM -> L2 one item ahead with bulk L2 prefetches (B200T5_XS_L2PF, "xattn_l2pf"): measured SLOWER
@@ -573,7 +580,7 @@ extern "C" int b200t5_create(const b200t5_config* cfg, int device, b200t5_handle
   if (const char* pk_env = getenv("B200T5_PACK")) h->pack_rows = atoi(pk_env) != 0;
   if (const char* tc_env = getenv("B200T5_2CTA")) h->use_2cta = atoi(tc_env) != 0;
   if (const char* sf_env = getenv("B200T5_SELF")) h->self_block = strcmp(sf_env, "warp") != 0;
-  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_stream = strcmp(xa_env, "ldg") != 0;
+  if (const char* xa_env = getenv("B200T5_XATTN")) h->xattn_mode = strcmp(xa_env, "ldg") == 0 ? 0 : strcmp(xa_env, "stream") == 0 ? 1 : 2;
   if (const char* xs_env = getenv("B200T5_XS_STAGES")) {
     const int v = atoi(xs_env);
     if (v >= 2 && v <= kXsMaxStages) h->xs_stages = v;
@@ -977,7 +984,7 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   CU_OK(h, pl->admit.alloc(static_cast<size_t>(3) * B * 4));
   CU_OK(h, cudaMemset(pl->pos.p, 0, pl->pos.bytes));
   CU_OK(h, pl->xs_stamps.alloc(static_cast<size_t>(c.Ld) * kMaxChains * 2 * 8));
-  CU_OK(h, pl->xs_acc.alloc(static_cast<size_t>(c.Ld) * kMaxChains * 2 * 8));
+  CU_OK(h, pl->xs_acc.alloc(static_cast<size_t>(c.Ld) * (kMaxChains + 1) * 2 * 8));
   CU_OK(h, cudaMemset(pl->xs_stamps.p, 0, pl->xs_stamps.bytes));
   CU_OK(h, cudaMemset(pl->xs_acc.p, 0, pl->xs_acc.bytes));
   CU_OK(h, cudaMemset(pl->out_row.p, 0, pl->out_row.bytes));
@@ -1089,11 +1096,13 @@ static int run_encoder(b200t5_ctx* h, const long long* ids, const long long* mas
   if (row_on && !p.packed)
     return fail(h, B200T5_EINVAL, "slot-pool admission needs the packed encoder path (S <= %d, B200T5_PACK/B200T5_ENC_ATTN at their defaults)", kEncTcMaxS);
   const int* cu = nullptr;
+  p.rows_valid = M;
   if (p.packed) {
     pack_offsets_kernel<<<1, 256, 0, s>>>(p.extent.as<int>(), p.cu.as<int>(), B);
     CU_OK(h, cudaMemcpyAsync(p.h_cu, p.cu.as<int>() + B, 4, cudaMemcpyDeviceToHost, s));
     CU_OK(h, cudaStreamSynchronize(s));
     M = *p.h_cu;
+    p.rows_valid = M;
     cu = p.cu.as<int>();
     embed_rows_packed_kernel<<<dim3((S + 7) / 8, B), 256, 0, s>>>(ids, h->shared.as<act_t>(), p.x.as<res_t>(), cu, p.row_b.as<int>(),
                                                                p.row_s.as<int>(), S, d, c.V);
@@ -1254,7 +1263,7 @@ static cudaError_t launch_cross_attention(b200t5_ctx* h, cudaStream_t s, bool pd
   Plan& p = *h->plan;
   const int B = p.B, S = p.S, I = c.I;
   XsStamps st{slot >= 0 && p.xs_stamps.p ? p.xs_stamps.as<unsigned long long>() : nullptr, slot >= 0 ? slot : 0};
-  if (h->xattn_stream) {
+  if (p.xattn_stream) {
     const int items = nb * c.H;
     const int k_row0 = ((l * 2) * B + b0) * c.H * S, v_row0 = ((l * 2 + 1) * B + b0) * c.H * S;
     const act_t* arena = p.cross_kv.as<act_t>();
@@ -1411,15 +1420,23 @@ static int run_decode_step(b200t5_ctx* h, cudaStream_t s, bool fork, float* logi
   CU_OK(h, launch_kernel(advance_step_kernel, dim3(1), dim3(32), 0, s, false, p.state.as<DecodeState>(),
                          h->profile_xattn ? p.xs_stamps.as<unsigned long long>() : static_cast<unsigned long long*>(nullptr),
                          h->profile_xattn ? p.xs_acc.as<unsigned long long>() : static_cast<unsigned long long*>(nullptr),
-                         c.Ld * nc));
+                         c.Ld, nc));
   h->launches++;
   return B200T5_OK;
 }
 
 // Graph of one decode step; eos/pad/min_new are baked in, so the graph is rebuilt when they change.
-static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new) {
+// The cross-attention kernel is baked in as well: `fill` = valid prompt tokens / (B * S) of the batch at hand.
+constexpr double kXattnStreamFill = 0.9;
+static int pick_xattn(const b200t5_ctx* h, double fill) {
+  return h->xattn_mode == 2 ? (fill >= kXattnStreamFill ? 1 : 0) : h->xattn_mode;
+}
+static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new, double fill) {
   Plan& p = *h->plan;
-  if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new && p.g_stream == (p.stream_mode ? 1 : 0)) return B200T5_OK;
+  const int want = pick_xattn(h, fill);
+  p.xattn_stream = want != 0;
+  if (p.gexec && p.g_eos == eos && p.g_pad == pad && p.g_min_new == min_new && p.g_stream == (p.stream_mode ? 1 : 0) && p.g_xattn == want)
+    return B200T5_OK;
   if (p.gexec) cudaGraphExecDestroy(p.gexec);
   if (p.graph) cudaGraphDestroy(p.graph);
   if (p.gexec8) cudaGraphExecDestroy(p.gexec8);
@@ -1444,6 +1461,7 @@ static int ensure_graph(b200t5_ctx* h, long long eos, long long pad, int min_new
   p.g_pad = pad;
   p.g_min_new = min_new;
   p.g_stream = p.stream_mode ? 1 : 0;
+  p.g_xattn = want;
   return B200T5_OK;
 }
 
@@ -1492,11 +1510,12 @@ static int generate_impl(b200t5_ctx* h, const long long* ids, const long long* m
   TRY(ensure_plan(h, B, S, T));
   Plan& p = *h->plan;
   p.stream_mode = false;
-  TRY(ensure_graph(h, eos, pad, min_new));
   h->launches = 0;
   CU_OK(h, cudaEventRecord(h->ev[0], s));
   TRY(run_encoder(h, ids, mask, s));
   TRY(run_cross_kv(h, s));
+  // (host-side capture, only when something baked into the graph changed; the GPU is busy with the encoder meanwhile)
+  TRY(ensure_graph(h, eos, pad, min_new, static_cast<double>(p.rows_valid) / (static_cast<double>(B) * S)));
   CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
   CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   decode_init_kernel<<<B, 128, 0, s>>>(p.state.as<DecodeState>(), p.unfinished.as<int>(), p.out_ids.as<long long>(),
@@ -1614,7 +1633,14 @@ extern "C" int b200t5_generate_stream(b200t5_handle h, const int64_t* input_ids,
     p.g_stream = -1;
   }
   p.stream_mode = true;
-  TRY(ensure_graph(h, eos, pad, min_new));
+  double fill = 1.0;
+  if (attention_mask) {  // fill of the first prompts (up to four pools' worth): picks the cross-attention kernel
+    const long long rows = N < 4LL * B ? N : 4LL * B;
+    long long ones = 0;
+    for (long long i = 0; i < rows * S; ++i) ones += attention_mask[i] != 0;
+    fill = static_cast<double>(ones) / static_cast<double>(rows * S);
+  }
+  TRY(ensure_graph(h, eos, pad, min_new, fill));
   h->launches = 0;
   CU_OK(h, cudaEventRecord(h->ev[0], s));
   {
@@ -1756,6 +1782,8 @@ extern "C" int b200t5_get_stats(b200t5_handle h, b200t5_stats* out) {
   fill_stats_model(h, h->last_steps);
   out->decode_algo_bytes = h->last_decode_bytes;
   out->encoder_flops = h->last_enc_flops;
+  out->xattn_kernel = h->plan->xattn_stream ? 1 : 0;
+  out->row_chains = h->plan->n_chains;
   return B200T5_OK;
 }
 
@@ -1828,7 +1856,7 @@ extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
   if (!h || !name) return fail(h, B200T5_EINVAL, "null argument");
   const std::string n(name);
   if (n == "chains") h->chains_override = value < 0 ? 0 : value;
-  else if (n == "xattn") h->xattn_stream = value != 0;
+  else if (n == "xattn") h->xattn_mode = value < 0 || value > 2 ? 2 : value;
   else if (n == "xattn_stages") {
     if (value < 2 || value > kXsMaxStages) return fail(h, B200T5_EINVAL, "xattn_stages must be in [2, %d]", kXsMaxStages);
     h->xs_stages = value;
@@ -1850,27 +1878,35 @@ extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
 // Cross-attention launches of the step graph since profiling was switched on: their mean in-situ duration
 // (first CTA's start to last CTA's end, %globaltimer), the number of launches seen, and the algorithmic bytes of
 // one launch at the moment of the call (K and V rows of the keys the live rows still attend).
-extern "C" int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch) {
-  if (!h || !avg_us_per_launch || !launches || !bytes_per_launch) return fail(h, B200T5_EINVAL, "null argument");
+extern "C" int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch,
+                                        double* busy_us_per_layer, double* bytes_per_layer) {
+  if (!h || !avg_us_per_launch || !launches || !bytes_per_launch || !busy_us_per_layer || !bytes_per_layer)
+    return fail(h, B200T5_EINVAL, "null argument");
   if (!h->plan || !h->profile_xattn) return fail(h, B200T5_ESTATE, "profiling is off (b200t5_set_option(h, \"profile_xattn\", 1), then generate)");
   CU_OK(h, cudaSetDevice(h->device));
   CU_OK(h, cudaDeviceSynchronize());
   Plan& p = *h->plan;
   const int n = h->c.Ld * p.n_chains;
-  std::vector<unsigned long long> acc(static_cast<size_t>(n) * 2);
+  std::vector<unsigned long long> acc(static_cast<size_t>(n + h->c.Ld) * 2);
   CU_OK(h, cudaMemcpy(acc.data(), p.xs_acc.p, acc.size() * 8, cudaMemcpyDeviceToHost));
-  unsigned long long ns = 0, cnt = 0;
+  unsigned long long ns = 0, cnt = 0, busy = 0, layers = 0;
   for (int i = 0; i < n; ++i) {
     ns += acc[2 * i];
     cnt += acc[2 * i + 1];
   }
+  for (int l = 0; l < h->c.Ld; ++l) {
+    busy += acc[2 * (n + l)];
+    layers += acc[2 * (n + l) + 1];
+  }
   *avg_us_per_launch = cnt ? static_cast<double>(ns) / static_cast<double>(cnt) / 1e3 : 0.0;
+  *busy_us_per_layer = layers ? static_cast<double>(busy) / static_cast<double>(layers) / 1e3 : 0.0;
   *launches = static_cast<int64_t>(cnt);
   std::vector<int> ext(p.B);
   CU_OK(h, cudaMemcpy(ext.data(), p.extent.p, p.B * 4, cudaMemcpyDeviceToHost));
   double sum_s = 0;
   for (int v : ext) sum_s += v;
-  *bytes_per_launch = 2.0 * 2.0 * h->c.I * sum_s / p.n_chains;
+  *bytes_per_layer = 2.0 * 2.0 * h->c.I * sum_s;
+  *bytes_per_launch = *bytes_per_layer / p.n_chains;
   return B200T5_OK;
 }
 
@@ -1905,6 +1941,7 @@ extern "C" int b200t5_decode_logits(b200t5_handle h, const int64_t* input_ids, c
   TRY(run_encoder(h, reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(attention_mask), s));
   TRY(run_cross_kv(h, s));
   p.stream_mode = false;
+  p.xattn_stream = pick_xattn(h, static_cast<double>(p.rows_valid) / (static_cast<double>(B) * S)) != 0;
   CU_OK(h, cudaMemcpyAsync(p.live_extent.p, p.extent.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
   CU_OK(h, cudaMemcpyAsync(p.live_key_ok.p, p.key_ok.p, static_cast<size_t>(B) * S, cudaMemcpyDeviceToDevice, s));
   set_state_kernel<<<1, 1, 0, s>>>(p.state.as<DecodeState>(), 0);

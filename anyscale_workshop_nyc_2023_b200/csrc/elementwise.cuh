@@ -357,21 +357,55 @@ __global__ void finalize_step_kernel(const float* __restrict__ pval, const int* 
 }
 
 // End of a step (joins every chain). With in-situ profiling on, fold the cross-attention launch stamps of this
-// step ({min start, max end} per launch, attention_decode.cuh: XsStamps) into {sum of durations in ns, launches}.
+// step ({min start, max end} per launch, attention_decode.cuh: XsStamps; slot = layer * n_chains + chain) into
+//   acc[slot]                = {sum of launch durations in ns, launches}               and
+//   acc[n_slots + layer]     = {sum over steps of the time during which AT LEAST ONE of the layer's launches ran, layers}
+// - the second is what the HBM stream of a layer costs the step when the chains' launches overlap each other.
 __global__ void advance_step_kernel(DecodeState* st, unsigned long long* __restrict__ stamps,
-                                    unsigned long long* __restrict__ acc, int n_slots) {
+                                    unsigned long long* __restrict__ acc, int n_layers, int n_chains) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) st->step += 1;
   if (stamps != nullptr) {
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
-      const unsigned long long t0 = stamps[2 * i], t1 = stamps[2 * i + 1];
-      if (t1 > t0 && t0 != 0 && t0 != ~0ull) {  // (slots start zeroed: the first step after a plan is built is skipped)
-        acc[2 * i] += t1 - t0;
-        acc[2 * i + 1] += 1;
+    const int n_slots = n_layers * n_chains;
+    for (int l = threadIdx.x; l < n_layers; l += blockDim.x) {
+      unsigned long long t0[8], t1[8];
+      int n = 0;
+      bool all = true;
+      for (int c = 0; c < n_chains && c < 8; ++c) {
+        const int i = l * n_chains + c;
+        const unsigned long long a = stamps[2 * i], b = stamps[2 * i + 1];
+        stamps[2 * i] = ~0ull;
+        stamps[2 * i + 1] = 0;
+        if (b > a && a != 0 && a != ~0ull) {  // (slots start zeroed: the first step after a plan is built is skipped)
+          acc[2 * i] += b - a;
+          acc[2 * i + 1] += 1;
+          int k = n++;  // insertion sort by start time
+          for (; k > 0 && t0[k - 1] > a; --k) {
+            t0[k] = t0[k - 1];
+            t1[k] = t1[k - 1];
+          }
+          t0[k] = a;
+          t1[k] = b;
+        } else {
+          all = false;
+        }
       }
-      stamps[2 * i] = ~0ull;
-      stamps[2 * i + 1] = 0;
+      if (all && n > 0) {
+        unsigned long long busy = 0, lo = t0[0], hi = t1[0];
+        for (int k = 1; k < n; ++k) {
+          if (t0[k] > hi) {
+            busy += hi - lo;
+            lo = t0[k];
+            hi = t1[k];
+          } else if (t1[k] > hi) {
+            hi = t1[k];
+          }
+        }
+        busy += hi - lo;
+        acc[2 * (n_slots + l)] += busy;
+        acc[2 * (n_slots + l) + 1] += 1;
+      }
     }
   }
 }

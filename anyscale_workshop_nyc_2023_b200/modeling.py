@@ -365,10 +365,13 @@ class B200T5ForConditionalGeneration:
         _chk(self, self._lib.b200t5_set_option(self._h, name.encode(), int(value)), self._h)
 
     def xattn_profile(self) -> Dict[str, float]:
-        """In-situ duration of the cross-attention launches of the step graph since set_option("profile_xattn", 1)."""
-        us, n, nbytes = C.c_double(), C.c_int64(), C.c_double()
-        _chk(self, self._lib.b200t5_get_xattn_profile(self._h, C.byref(us), C.byref(n), C.byref(nbytes)), self._h)
-        return {"us_per_launch": us.value, "launches": int(n.value), "bytes_per_launch": nbytes.value}
+        """In-situ timing of the cross-attention launches of the step graph since set_option("profile_xattn", 1): per
+        launch, and per layer as the union of the row-chains' (possibly overlapping) launches."""
+        us, n, nbytes, busy, lbytes = C.c_double(), C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+        _chk(self, self._lib.b200t5_get_xattn_profile(self._h, C.byref(us), C.byref(n), C.byref(nbytes), C.byref(busy),
+                                                      C.byref(lbytes)), self._h)
+        return {"us_per_launch": us.value, "launches": int(n.value), "bytes_per_launch": nbytes.value,
+                "busy_us_per_layer": busy.value, "bytes_per_layer": lbytes.value}
 
     # ------------------------------------------------------------------ parity hooks (tests)
     @torch.no_grad()

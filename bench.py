@@ -378,6 +378,7 @@ def main_b200(a):
         dec_ms += st["decode_ms"]
         dec_bytes += st["decode_algo_bytes"]
         enc_flops += st["encoder_flops"]
+        xattn_kernel, row_chains = int(st["xattn_kernel"]), int(st["row_chains"])
         assert out.shape == (B, T + 1)
     e1.record()
     barrier()
@@ -407,7 +408,7 @@ def main_b200(a):
     model.set_option("profile_xattn", 0)
     model.generate(input_ids=dev_batches[0][0], attention_mask=dev_batches[0][1], **gen_kw)  # plan for the calls below
     full_bytes = roofline.cross_attention_bytes_per_launch(spec, host[0][1].sum(axis=1).tolist())
-    n_chains = max(1, int(round(full_bytes / max(prof["bytes_per_launch"], 1.0))))
+    n_chains = max(1, row_chains)
     rows_per_launch = (B + n_chains - 1) // n_chains
     ca_chain = model.bench_cross_attention(reps=5, rows_per_launch=rows_per_launch)
     ca_full = model.bench_cross_attention(reps=5, rows_per_launch=0)
@@ -436,7 +437,8 @@ def main_b200(a):
         tokens = world * K * B * T
         value = tokens / (elapsed_ms / 1e3)
         gbs = lambda nbytes, ms: nbytes / (ms / 1e3) / 1e9  # noqa: E731
-        ach_situ = gbs(prof["bytes_per_launch"], prof["us_per_launch"] / 1e3) if prof["launches"] else None
+        ach_launch = gbs(prof["bytes_per_launch"], prof["us_per_launch"] / 1e3) if prof["launches"] else None
+        ach_situ = gbs(prof["bytes_per_layer"], prof["busy_us_per_layer"] / 1e3) if prof["busy_us_per_layer"] > 0 else ach_launch
         ach_chain = gbs(ca_chain["bytes_per_launch"], ca_chain["ms_per_launch"])
         ach_full = gbs(ca_full["bytes_per_launch"], ca_full["ms_per_launch"])
         dec_frac = dec_bytes / (dec_ms / 1e3) / 1e9 / hbm_peak
@@ -457,14 +459,20 @@ def main_b200(a):
                     "api": "HuggingFaceModelPredictor._predict_numpy (numpy batch -> DataFrame[generated_output])"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            # frac = the dominant kernel AS THE TIMED PATH LAUNCHES IT: one row-chain's rows per launch, inside the step
-            # graph, overlapped with the other chain's GEMMs (first CTA start -> last CTA end, %globaltimer, averaged
-            # over every launch of two extra untimed passes). frac_isolated_*: the same kernel alone, back to back.
-            "roofline": {"bound": "hbm", "kernel": "cross-attention decode (attn_cross_stream_kernel; B200T5_XATTN=ldg: attn_decode_kernel<false>)",
+            # frac = the dominant kernel AS THE TIMED PATH RUNS IT: inside the step graph, one launch per row-chain and
+            # layer, next to the other chain's kernels. Every launch stamps first-CTA-start / last-CTA-end
+            # (%globaltimer; two extra untimed passes). The chains' launches of a layer may OVERLAP each other and then
+            # share the HBM, so the rate is taken per layer: bytes all of the layer's launches read / time during
+            # which at least one of them ran (union of the intervals). frac_per_launch_in_situ = one launch's bytes /
+            # its own duration (equal to frac when the launches do not overlap). frac_isolated_*: the kernel alone.
+            "roofline": {"bound": "hbm", "kernel": "cross-attention decode: " + ("attn_cross_stream_kernel (TMA ring + mma.sync)" if xattn_kernel else "attn_decode_kernel<false> (per-thread loads)")
+                                   + "; chosen per call from the prompt fill (B200T5_XATTN=ldg|stream|auto)",
                          "achieved": ach_situ, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (ach_situ / hbm_peak) if ach_situ else None, "traffic": traffic, "peak_source": peak_src,
+                         "frac_per_launch_in_situ": (ach_launch / hbm_peak) if ach_launch else None,
                          "in_situ": {"rows_per_launch": rows_per_launch, "launches_timed": prof["launches"],
-                                     "algo_bytes_per_launch": prof["bytes_per_launch"], "us_per_launch": prof["us_per_launch"]},
+                                     "algo_bytes_per_launch": prof["bytes_per_launch"], "us_per_launch": prof["us_per_launch"],
+                                     "algo_bytes_per_layer": prof["bytes_per_layer"], "busy_us_per_layer": prof["busy_us_per_layer"]},
                          "frac_isolated_chain_rows": ach_chain / hbm_peak, "frac_isolated_full_batch": ach_full / hbm_peak,
                          "isolated": {"chain_rows": {"rows": rows_per_launch, **ca_chain}, "full_batch": {"rows": B, **ca_full}},
                          "decode_loop_frac_of_hbm_peak": dec_frac, "encoder_frac_of_bf16_sustained": enc_frac,

@@ -92,6 +92,8 @@ typedef struct b200t5_stats {
   int64_t kernel_launches;/* kernels launched by this library in the last generate call */
   double decode_algo_bytes;  /* algorithmic HBM bytes of the decode loop (SURVEY 8d model) */
   double encoder_flops;      /* encoder + cross-KV projection FLOPs */
+  int32_t xattn_kernel;      /* decode cross-attention kernel of the last call: 0 per-thread-load, 1 TMA stream */
+  int32_t row_chains;        /* row-chains the decode step was split into */
 } b200t5_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
@@ -143,14 +145,19 @@ int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_launch, floa
                             double* bytes_per_launch, void* stream);
 /* Runtime options: what the B200T5_* environment variables set at create time, on a live handle (a sweep need not
  * reload the model). A change drops the execution plan; the next call re-captures the step graph. Names: "chains"
- * (row-chains per decode step, 0 = default), "xattn" (1 = bulk-copy stream kernel, 0 = per-thread-load kernel),
+ * (row-chains per decode step, 0 = default), "xattn" (decode cross-attention: 0 = per-thread-load kernel, 1 = TMA stream kernel, 2 = per call by prompt fill),
  * "xattn_stages" (8 KB ring stages per CTA), "xattn_late_pdl", "pdl", "sk_stages64", "sk_stages128" (pipeline stages of
  * the split-K decode GEMM tiles, 0 = default), "profile_xattn" (1 = every cross-attention launch inside the step graph
  * records %globaltimer stamps; never on in a timed region). */
 int b200t5_set_option(b200t5_handle h, const char* name, int value);
 /* With "profile_xattn" on: mean in-situ duration (first CTA start to last CTA end) of the cross-attention launches the
- * step graph made since the option was set, how many there were, and the algorithmic bytes of one such launch. */
-int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch);
+ * step graph made since the option was set, how many there were, and the algorithmic bytes of one such launch; and,
+ * per decoder layer and step, the time during which AT LEAST ONE of the row-chains' cross-attention launches was
+ * running (the union of their intervals: the chains' launches may overlap each other) with the bytes the layer's
+ * launches read together. bytes_per_layer / busy_us_per_layer is the HBM rate of the cross-attention stream as the
+ * step runs it. */
+int b200t5_get_xattn_profile(b200t5_handle h, double* avg_us_per_launch, int64_t* launches, double* bytes_per_launch,
+                             double* busy_us_per_layer, double* bytes_per_layer);
 /* lm_head + fused greedy arg-max exactly as the decode step runs them (csrc/gemm.cuh EpiArgmax -> finalize_step_kernel):
  * x [M,K] and W [V,K] in the build's 2-byte type (device), `step` the decode position, EOS masked while
  * step < min_new. tokens: int64 [M] (device) = argmax_n act(x . W[n]) with torch.argmax's first-index tie rule

@@ -245,7 +245,7 @@ def test_cross_attention_kernels_give_identical_tokens(models):
             assert torch.equal(model.generate(**kw).cpu(), stream), (name, value)
         model.set_option("xattn_l2pf", 0)
     finally:
-        for name, value in (("xattn", 1), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1), ("xattn_serialize", 0)):
+        for name, value in (("xattn", 2), ("chains", 0), ("xattn_stages", 5), ("xattn_late_pdl", 1), ("xattn_serialize", 0)):
             model.set_option(name, value)
 
 

@@ -18,7 +18,7 @@ from anyscale_workshop_nyc_2023_b200.modeling import B200T5ForConditionalGenerat
 from anyscale_workshop_nyc_2023_b200.synth import SPECS, synthetic_token_batch  # noqa: E402
 from anyscale_workshop_nyc_2023_b200.workload import checkpoint_dir  # noqa: E402
 
-DEFAULTS = {"chains": 0, "xattn": 1, "xattn_serialize": 0, "xattn_l2pf": 0, "xattn_stages": 5, "xattn_late_pdl": 1, "pdl": 1, "sk_stages64": 0, "sk_stages128": 0}
+DEFAULTS = {"chains": 0, "xattn": 2, "xattn_serialize": 0, "xattn_l2pf": 0, "xattn_stages": 5, "xattn_late_pdl": 1, "pdl": 1, "sk_stages64": 0, "sk_stages128": 0}
 DEFAULT_CONFIGS = ("chains=1,xattn=0;chains=2,xattn=0;chains=1;chains=2;chains=3;chains=4;"
                    "chains=2,xattn_late_pdl=0;chains=2,xattn_stages=4;chains=2,xattn_stages=6,sk_stages64=3,sk_stages128=2;"
                    "chains=2,xattn_stages=8,sk_stages64=2,sk_stages128=2;chains=3,xattn_stages=4;chains=2,sk_stages64=3")
@@ -72,6 +72,8 @@ def main():
                 rec["xattn_in_situ_us"] = p["us_per_launch"]
                 rec["xattn_in_situ_gbs"] = p["bytes_per_launch"] / max(p["us_per_launch"], 1e-9) / 1e3
                 rec["xattn_launches"] = p["launches"]
+                rec["xattn_busy_us_per_layer"] = p["busy_us_per_layer"]
+                rec["xattn_layer_gbs"] = p["bytes_per_layer"] / max(p["busy_us_per_layer"], 1e-9) / 1e3
         except Exception as e:  # noqa: BLE001 - keep sweeping; a CUDA fault poisons the context and shows up below
             rec = {"config": cfg, "error": f"{type(e).__name__}: {e}"}
         print(json.dumps(rec), flush=True)
