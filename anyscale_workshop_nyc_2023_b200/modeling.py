@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import threading
 import warnings
 from pathlib import Path
 from types import SimpleNamespace
@@ -89,6 +90,9 @@ class B200T5ForConditionalGeneration:
         # generate() switches to the continuous-batching path for batches larger than pool_size; that path runs
         # pool_slots decode slots (512 measured best on B200 for FLAN-T5-base: +18 % over 256, profiles/stream_r1.md)
         self.pool_size = int(os.environ.get("B200T5_POOL", "256"))
+        # one handle = one execution plan: calls are serialised. Two host threads may alternate on it (the detokenise /
+        # DataFrame tail of block i overlaps the GPU part of block i+1: rayshim/train.py:_overlap_tail).
+        self._gpu_lock = threading.RLock()
         self.pool_slots = int(os.environ.get("B200T5_POOL_SLOTS", "512"))
 
     # ------------------------------------------------------------------ loading
@@ -237,9 +241,14 @@ class B200T5ForConditionalGeneration:
                 raise NotImplementedError(f"generate({k}=...) is not supported by the B200 path")
         gp = self._gen_params(max_new_tokens, max_length, min_new_tokens, min_length, eos_token_id, pad_token_id,
                               decoder_start_token_id, poll_interval)
-        ids = torch.as_tensor(input_ids).to(device=self._device, dtype=torch.long).contiguous()
-        if ids.dim() != 2:
-            raise ValueError(f"input_ids must be [batch, seq], got {tuple(ids.shape)}")
+        host = torch.as_tensor(input_ids)
+        if host.dim() != 2:
+            raise ValueError(f"input_ids must be [batch, seq], got {tuple(host.shape)}")
+        if self.takes_host_batches(host.shape[0], host.shape[1]) and host.device.type == "cpu":
+            # more rows than one pool of decode slots, still in host memory: the slot pool admits prompts from host
+            # buffers as slots free up, so nothing is copied to the device (and back) up front
+            return self._generate_pool_from_host(host, attention_mask, gp)
+        ids = host.to(device=self._device, dtype=torch.long).contiguous()
         B, S = ids.shape
         if ids.numel():
             lo, hi = torch.aminmax(ids)  # one kernel, one synchronisation
@@ -253,7 +262,7 @@ class B200T5ForConditionalGeneration:
         else:
             mask = self._infer_attention_mask(ids, gp)
         if B > self.pool_size:
-            if S <= _POOL_MAX_S and os.environ.get("B200T5_STREAM", "1") != "0":
+            if self.takes_host_batches(B, S):
                 # more rows than one pool of decode slots: continuous batching, same tokens row for row. The pool
                 # admits prompts from host memory as slots free up (its entry point takes host buffers).
                 out_np, _ = self.generate_stream(ids.cpu().numpy(), None if mask is None else mask.cpu().numpy(), _gen_params=gp)
@@ -265,6 +274,24 @@ class B200T5ForConditionalGeneration:
             pad = gp.pad_token_id if gp.pad_token_id >= 0 else self.generation_config.pad_token_id
             return torch.cat([torch.nn.functional.pad(o, (0, width - o.shape[1]), value=pad) for o in outs], dim=0)
         return self._generate_static(ids, mask, gp)
+
+    def takes_host_batches(self, B: int, S: int) -> bool:
+        """True when a [B, S] batch would go through the slot pool, whose entry point takes HOST buffers: a caller that
+        still has the batch in host memory (predictor.py) hands it over as it is."""
+        return B > self.pool_size and S <= _POOL_MAX_S and os.environ.get("B200T5_STREAM", "1") != "0"
+
+    def _generate_pool_from_host(self, ids: torch.Tensor, attention_mask, gp) -> torch.Tensor:
+        ids_np = np.ascontiguousarray(ids.numpy(), dtype=np.int64)
+        if ids_np.size and (int(ids_np.min()) < 0 or int(ids_np.max()) >= self.config.vocab_size):
+            raise IndexError("input_ids contain token ids outside [0, vocab_size)")
+        if attention_mask is not None:
+            mask_np = np.ascontiguousarray(torch.as_tensor(attention_mask).cpu().numpy(), dtype=np.int64)
+            if mask_np.shape != ids_np.shape:
+                raise ValueError("attention_mask shape must match input_ids")
+        else:
+            mask_np = self._infer_mask_np(ids_np, gp)
+        out_np, _ = self.generate_stream(ids_np, mask_np, _gen_params=gp)
+        return torch.from_numpy(out_np).to(self._device)
 
     def _infer_attention_mask(self, ids: torch.Tensor, gp) -> Optional[torch.Tensor]:
         """GenerationMixin._prepare_attention_mask_for_generation (transformers generation/utils.py): without an
@@ -288,10 +315,11 @@ class B200T5ForConditionalGeneration:
             out = torch.empty((B, T + 1), dtype=torch.long, device=self._device)
             lens = torch.empty((B,), dtype=torch.int32, device=self._device)
             stream = torch.cuda.current_stream(self._device)
-            _chk(self, self._lib.b200t5_generate(self._h, _ptr(ids), _ptr(mask), B, S, C.byref(gp), _ptr(out),
-                                                 _ptr(lens), C.c_void_p(stream.cuda_stream)), self._h)
-            self.last_lengths = lens
-            steps = int(lens.max().item())  # synchronises; HF returns exactly the steps it ran
+            with self._gpu_lock:
+                _chk(self, self._lib.b200t5_generate(self._h, _ptr(ids), _ptr(mask), B, S, C.byref(gp), _ptr(out),
+                                                     _ptr(lens), C.c_void_p(stream.cuda_stream)), self._h)
+                self.last_lengths = lens
+                steps = int(lens.max().item())  # synchronises; HF returns exactly the steps it ran
         return out[:, : steps + 1]
 
     def _infer_mask_np(self, ids: np.ndarray, gp) -> Optional[np.ndarray]:
@@ -312,9 +340,10 @@ class B200T5ForConditionalGeneration:
         mask = self._infer_mask_np(ids, gp) if attention_mask is None else np.ascontiguousarray(attention_mask, dtype=np.int64)
         out = np.empty((B, gp.max_new_tokens + 1), dtype=np.int64)
         lens = np.empty((B,), dtype=np.int32)
-        _chk(self, self._lib.b200t5_generate_host(
-            self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), B, S,
-            C.byref(gp), out.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)), self._h)
+        with self._gpu_lock:
+            _chk(self, self._lib.b200t5_generate_host(
+                self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), B, S,
+                C.byref(gp), out.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p)), self._h)
         return out[:, : int(lens.max()) + 1], lens
 
     def generate_stream(self, input_ids: np.ndarray, attention_mask: Optional[np.ndarray] = None, *, pool: Optional[int] = None,
@@ -338,10 +367,11 @@ class B200T5ForConditionalGeneration:
             raise ValueError("attention_mask shape must match input_ids")
         out = np.empty((N, gp.max_new_tokens + 1), dtype=np.int64)
         lens = np.empty((N,), dtype=np.int32)
-        _chk(self, self._lib.b200t5_generate_stream(
-            self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), N, S,
-            C.byref(gp), int(pool or self.pool_slots), int(admit_min), out.ctypes.data_as(C.c_void_p),
-            lens.ctypes.data_as(C.c_void_p)), self._h)
+        with self._gpu_lock:
+            _chk(self, self._lib.b200t5_generate_stream(
+                self._h, ids.ctypes.data_as(C.c_void_p), None if mask is None else mask.ctypes.data_as(C.c_void_p), N, S,
+                C.byref(gp), int(pool or self.pool_slots), int(admit_min), out.ctypes.data_as(C.c_void_p),
+                lens.ctypes.data_as(C.c_void_p)), self._h)
         self.last_lengths = torch.from_numpy(lens)
         return out[:, : int(lens.max()) + 1], lens
 

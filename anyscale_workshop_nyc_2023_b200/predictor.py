@@ -4,7 +4,9 @@ Interface source: NLP_workloads/Anyscale_job/predictor.py:14-106 (identical copy
 Model_finetuning_and_batch_inference.ipynb:760-852). Names, argument meaning and error behaviour
 are kept so the notebook cells run unchanged; the body is written for the B200 path:
 
-  * columns are staged through pinned host memory and copied with non-blocking H2D copies;
+  * columns are staged through pinned host memory (one set of buffers per calling thread) and copied with
+    non-blocking H2D copies; a batch larger than the model's pool of decode slots is handed over in HOST memory
+    (the slot pool admits prompts from host buffers as slots free up: no copy to the device and back);
     `labels` - which the reference's preprocessor emits as a copy of `input_ids`
     (JOB/utils.py:31) and `generate` ignores - is not shipped to the device;
   * works with any `model` exposing `.device` and `.generate(**kw) -> LongTensor[B, 1+T]`
@@ -13,6 +15,8 @@ are kept so the notebook cells run unchanged; the body is written for the B200 p
 from __future__ import annotations
 
 from typing import Any, Dict, List, Optional
+
+import threading
 
 import numpy as np
 import pandas as pd
@@ -39,7 +43,7 @@ class HuggingFaceModelPredictor(Predictor):
         self.model = model
         self.tokenizer = tokenizer
         self.use_gpu = use_gpu
-        self._pinned: Dict[str, torch.Tensor] = {}
+        self._pinned: Dict[Any, torch.Tensor] = {}
 
     @classmethod
     def from_checkpoint(cls, checkpoint: Any, model_cls: Any, *, tokenizer: Optional[Any] = None,
@@ -61,10 +65,11 @@ class HuggingFaceModelPredictor(Predictor):
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if device.type != "cuda":
             return t.to(device)
-        buf = self._pinned.get(name)
+        key = (name, threading.get_ident())  # two scoring threads may alternate on one predictor (rayshim/train.py)
+        buf = self._pinned.get(key)
         if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
             buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            self._pinned[name] = buf
+            self._pinned[key] = buf
         buf.copy_(t)
         return buf.to(device, non_blocking=True)
 
@@ -77,7 +82,12 @@ class HuggingFaceModelPredictor(Predictor):
         if feature_columns:
             data = {k: v for k, v in data.items() if k in feature_columns}
         on_gpu = torch.device(self.model.device).type == "cuda"
-        tensors = {k: self._to_device(k, v) for k, v in data.items() if not (on_gpu and k in _NOT_MODEL_INPUTS)}
+        first = next(iter(data.values()), None)
+        host_ok = getattr(self.model, "takes_host_batches", None)
+        if on_gpu and host_ok is not None and getattr(first, "ndim", 0) == 2 and host_ok(first.shape[0], first.shape[1]):
+            tensors = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in data.items() if k not in _NOT_MODEL_INPUTS}
+        else:
+            tensors = {k: self._to_device(k, v) for k, v in data.items() if not (on_gpu and k in _NOT_MODEL_INPUTS)}
         outputs = self.model.generate(**{**tensors, **generate_kwargs})
         texts = self.tokenizer.batch_decode(outputs, skip_special_tokens=True)
         return pd.DataFrame(texts, columns=["generated_output"])

@@ -11,7 +11,8 @@ per pool, not once per call.
 The CPU stage runs inside the workers: when the checkpoint carries a preprocessor, a worker receives the RAW rows of
 its blocks (strings - small messages) and tokenises block i+1 on a producer thread while the GPU generates block i,
 instead of the driver process tokenising the whole dataset up front. Tokenised arrays therefore never cross a process
-boundary; what crosses it is strings in, strings out.
+boundary; what crosses it is strings in, strings out. A worker also keeps two blocks in flight on two threads, so the
+host tail of block i (detokenise, DataFrame) overlaps the generation of block i+1 (`train._overlap_tail`).
 
 Failure handling: every wait on a worker polls its liveness, so a worker killed by a native failure (CUDA abort,
 segfault, OOM kill - which post no Python exception) surfaces as a RuntimeError with its exit code instead of a hang.
@@ -36,7 +37,7 @@ def _worker_main(visible: str, payload: bytes, task_q, result_q) -> None:
     os.environ["CUDA_VISIBLE_DEVICES"] = visible
     try:
         from .data import _to_block, _to_pandas
-        from .train import _prefetch, _ScoringWorker
+        from .train import _overlap_ok, _overlap_tail, _prefetch, _ScoringWorker
 
         checkpoint, predictor_cls, kwargs, override_prep = cloudpickle.loads(payload)
         worker = _ScoringWorker(checkpoint, predictor_cls, kwargs, override_prep)
@@ -51,8 +52,10 @@ def _worker_main(visible: str, payload: bytes, task_q, result_q) -> None:
                 stream = _prefetch(items, lambda it: (it[0], _to_pandas(_to_block(prep.transform_batch(it[1])))))
             else:
                 stream = iter(items)
-            for idx, batch in stream:
-                out = worker(batch, feature_columns, keep_columns, predict_kwargs)
+            # (two blocks in flight: the detokenise tail of block i overlaps the generation of block i+1)
+            scored = _overlap_tail(lambda it: (it[0], worker(it[1], feature_columns, keep_columns, predict_kwargs)), stream,
+                                   _overlap_ok(worker))
+            for idx, out in scored:
                 result_q.put(("ok", call_id, idx, pickle.dumps(out, protocol=pickle.HIGHEST_PROTOCOL)))
             result_q.put(("done", call_id, visible, None))
     except BaseException:  # noqa: BLE001 - surface the failure to the driver instead of hanging it

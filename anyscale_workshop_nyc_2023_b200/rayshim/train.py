@@ -188,6 +188,36 @@ def _prefetch(items: List[Any], fn, depth: int = 2):
         t.join(timeout=5)
 
 
+def _overlap_tail(fn, items, enabled: bool = True):
+    """Yield fn(item) in input order with TWO calls in flight on two threads. The GPU part of a call is serialised by
+    the model's own lock and runs with the GIL released (ctypes), so the host tail of block i (detokenise, DataFrame
+    assembly: predictor.py:103-106 of the reference) overlaps the generation of block i+1. `enabled` False (a model
+    that does not declare such a lock): plain sequential map."""
+    if not enabled:
+        for it in items:
+            yield fn(it)
+        return
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=2, thread_name_prefix="b200t5-score") as ex:
+        pending: "collections.deque" = collections.deque()
+        try:
+            for it in items:
+                pending.append(ex.submit(fn, it))
+                if len(pending) == 2:
+                    yield pending.popleft().result()
+            while pending:
+                yield pending.popleft().result()
+        finally:
+            for f in pending:
+                f.cancel()
+
+
+def _overlap_ok(worker: "_ScoringWorker") -> bool:
+    return hasattr(getattr(worker.predictor, "model", None), "_gpu_lock")
+
+
 class BatchPredictor:
     def __init__(self, checkpoint: Any, predictor_cls: Type[Predictor], **predictor_kwargs: Any):
         self._checkpoint = checkpoint
@@ -259,10 +289,12 @@ class BatchPredictor:
                 self._worker = _ScoringWorker(self._checkpoint, self._predictor_cls, kwargs, override_prep)
                 self._worker_key = key
             if worker_prep is not None:
-                outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs)
-                        for b in _prefetch(batches, lambda raw: _to_pandas(_to_block(worker_prep.transform_batch(raw))))]
+                outs = list(_overlap_tail(lambda b: self._worker(b, feature_columns, keep_columns, predict_kwargs),
+                                          _prefetch(batches, lambda raw: _to_pandas(_to_block(worker_prep.transform_batch(raw)))),
+                                          _overlap_ok(self._worker)))
             else:
-                outs = [self._worker(b, feature_columns, keep_columns, predict_kwargs) for b in batches]
+                outs = list(_overlap_tail(lambda b: self._worker(b, feature_columns, keep_columns, predict_kwargs), batches,
+                                          _overlap_ok(self._worker)))
         else:
             from .pool import GpuWorkerPool
 

@@ -427,8 +427,9 @@ def main_b200(a):
     traffic = None
     tf = ROOT / "profiles" / "cross_attn_traffic.json"
     if tf.exists() and a.model == "flan-t5-base" and (S, a.lengths) == (512, "full"):
-        tj = json.loads(tf.read_text())
-        traffic = tj["dram_bytes_per_launch"] * rows_per_launch / float(tj.get("rows_per_launch", 256))
+        tj = json.loads(tf.read_text()).get("attn_cross_stream_kernel" if xattn_kernel else "attn_decode_kernel<false>")
+        if tj:
+            traffic = tj["dram_bytes_per_launch"] * rows_per_launch / float(tj["rows_per_launch"])
 
     kv_gb = roofline.cross_attention_bytes_per_launch(spec, [S] * B) * spec.num_decoder_layers / 1e9
     w_gb = 2.0 * roofline.step_weight_elements(spec) / 1e9

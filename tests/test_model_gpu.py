@@ -249,6 +249,29 @@ def test_cross_attention_kernels_give_identical_tokens(models):
             model.set_option(name, value)
 
 
+def test_cross_attention_kernel_is_chosen_from_the_prompt_fill(models):
+    """Default ("xattn" = 2): the TMA stream kernel when the prompts fill the window (valid tokens / B*S >= 0.9), the
+    per-thread-load kernel on ragged batches; 0 / 1 pin one of them. b200t5_get_stats reports what the last call ran."""
+    model, _ = models("mini", 2)
+    spec = SPECS["mini"]
+    full = synthetic_token_batch(16, 64, spec.vocab_size, seed=5, lengths="full")
+    ragged = synthetic_token_batch(16, 64, spec.vocab_size, seed=5, lengths="uniform")
+
+    def kernel(batch):
+        model.generate(input_ids=torch.from_numpy(batch[0]), attention_mask=torch.from_numpy(batch[1]), max_new_tokens=4)
+        return model.stats()["xattn_kernel"]
+
+    try:
+        model.set_option("xattn", 2)
+        assert kernel(full) == 1 and kernel(ragged) == 0 and kernel(full) == 1
+        model.set_option("xattn", 0)
+        assert kernel(full) == 0
+        model.set_option("xattn", 1)
+        assert kernel(ragged) == 1
+    finally:
+        model.set_option("xattn", 2)
+
+
 def test_determinism_and_batch_invariance(models):
     """Same inputs -> identical tokens; a row's result does not depend on its batch neighbours
     (each (b,h) problem is independent and tile shapes do not change the per-row arithmetic)."""

@@ -80,3 +80,78 @@ def test_native_death_of_a_worker_is_reported_not_hung():
     assert pool.closed
     with pytest.raises(RuntimeError, match="shut down"):
         pool.map_ordered(_blocks(1), None, None, {})
+
+
+def test_overlap_tail_keeps_order_overlaps_and_propagates_errors():
+    """train._overlap_tail: results in input order, two calls in flight (the host tail of block i runs while the
+    lock-serialised 'GPU part' of block i+1 does), an exception of any call surfaces at its position."""
+    import threading
+    import time
+
+    from anyscale_workshop_nyc_2023_b200.rayshim.train import _overlap_tail
+
+    gpu = threading.Lock()
+    gpu_span, tail_span = {}, {}
+
+    def fn(i):
+        with gpu:                      # the model's lock: one generate at a time
+            a = time.perf_counter()
+            time.sleep(0.05)
+            gpu_span[i] = (a, time.perf_counter())
+        a = time.perf_counter()
+        time.sleep(0.05)               # detokenise / DataFrame tail
+        tail_span[i] = (a, time.perf_counter())
+        return i * i
+
+    t0 = time.perf_counter()
+    assert list(_overlap_tail(fn, range(6))) == [i * i for i in range(6)]
+    overlapped = time.perf_counter() - t0
+    assert sorted(gpu_span) == list(range(6))
+    spans = sorted(gpu_span.values())
+    assert all(b[0] >= a[1] - 1e-4 for a, b in zip(spans, spans[1:]))  # the 'GPU parts' never overlap each other
+    # ... but some block's tail ran while another block was generating
+    assert any(min(tail_span[i][1], gpu_span[j][1]) - max(tail_span[i][0], gpu_span[j][0]) > 0.01
+               for i in range(6) for j in range(6) if i != j)
+    assert overlapped < 6 * 0.1 * 0.9  # sequential would be 0.6 s; two in flight ~0.35 s
+    assert list(_overlap_tail(fn, range(3), enabled=False)) == [0, 1, 4]
+
+    def boom(i):
+        if i == 2:
+            raise ValueError("block 2")
+        return i
+
+    got = []
+    with pytest.raises(ValueError, match="block 2"):
+        for v in _overlap_tail(boom, range(5)):
+            got.append(v)
+    assert got == [0, 1]
+
+
+def test_predictor_hands_oversized_batches_over_in_host_memory():
+    """predictor._predict_numpy: a batch larger than the model's pool of decode slots stays in host memory (the slot
+    pool admits prompts from host buffers); `labels` is never passed on; smaller batches take the device path."""
+    import numpy as np
+    import torch
+
+    from anyscale_workshop_nyc_2023_b200.predictor import HuggingFaceModelPredictor
+
+    class Model:
+        device = "cuda:0"
+        seen = None
+
+        def takes_host_batches(self, B, S):
+            return B > 4
+
+        def generate(self, **kw):
+            Model.seen = kw
+            return torch.zeros((kw["input_ids"].shape[0], 2), dtype=torch.long)
+
+    class Tok:
+        def batch_decode(self, out, skip_special_tokens=True):
+            return ["x"] * len(out)
+
+    pred = HuggingFaceModelPredictor(Model(), tokenizer=Tok())
+    ids = np.arange(8 * 6, dtype=np.int64).reshape(8, 6)
+    df = pred._predict_numpy({"input_ids": ids, "attention_mask": np.ones_like(ids), "labels": ids}, max_new_tokens=3)
+    assert len(df) == 8 and set(Model.seen) == {"input_ids", "attention_mask", "max_new_tokens"}
+    assert Model.seen["input_ids"].device.type == "cpu" and torch.equal(Model.seen["input_ids"], torch.from_numpy(ids))

@@ -1,15 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/sweep_decode.py --configs "chains=2,xattn=0;chains=2,xattn=1;chains=1,xattn=0;chains=3,xattn=1" > gpurun_out/sweep_union_full.log 2>&1
-mv gpurun_out/sweep_decode.json gpurun_out/sweep_union_full.json
-timeout 600 python tools/sweep_decode.py --lengths uniform --configs "chains=2,xattn=0;chains=2,xattn=1" > gpurun_out/sweep_union_uniform.log 2>&1
-mv gpurun_out/sweep_decode.json gpurun_out/sweep_union_uniform.json
-timeout 600 python tools/sweep_decode.py --lengths alpaca --configs "chains=2,xattn=0;chains=2,xattn=1;chains=2,xattn=2" > gpurun_out/sweep_union_alpaca.log 2>&1
-mv gpurun_out/sweep_decode.json gpurun_out/sweep_union_alpaca.json
-for f in full uniform alpaca; do echo == $f; python - <<PY
-import json
-for r in json.load(open("gpurun_out/sweep_union_$f.json")):
-    print({k: (round(v,2) if isinstance(v,float) else v) for k,v in r.items() if k not in ("decode_ms_all","launches")})
-PY
-done
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_all_r2b.log 2>&1; tail -5 gpurun_out/pytest_all_r2b.log
+B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --parity-rows 0 --hf-gpu-batches 0"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_r2.csv $B > gpurun_out/ncu_launch.log 2>&1
+wc -l gpurun_out/launches_r2.csv
+python tools/summarize_launches.py gpurun_out/launches_r2.csv > gpurun_out/launches_r2.md 2>&1; head -40 gpurun_out/launches_r2.md
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_cross_stream_kernel -s 40 -c 2 -f -o gpurun_out/prof_xs_r2_final $B > gpurun_out/ncu_xs.log 2>&1
+ncu -i gpurun_out/prof_xs_r2_final.ncu-rep --page raw --csv > gpurun_out/prof_xs_r2_final_raw.csv 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:encoder_attn_tc_kernel -s 3 -c 1 -f -o gpurun_out/prof_encattn_r2 $B > gpurun_out/ncu_enc.log 2>&1
+ncu -i gpurun_out/prof_encattn_r2.ncu-rep --page raw --csv > gpurun_out/prof_encattn_r2_raw.csv 2>&1
+ls -la gpurun_out/*.ncu-rep gpurun_out/*_raw.csv | tail -6

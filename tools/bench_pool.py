@@ -44,16 +44,19 @@ def main():
     ap.add_argument("--max-new-tokens", type=int, default=128)
     ap.add_argument("--reps", type=int, default=2, help="warm predict() calls per worker count")
     ap.add_argument("--tag", default="base")
+    ap.add_argument("--weak", action="store_true", help="--n prompts PER WORKER (the dataset grows with the pool, as bench.py's per-rank work does)")
     a = ap.parse_args()
     ckpt = checkpoint_dir(a.model, seed=0)
-    rows = synthetic_alpaca_rows(a.n)
-    ds = rayshim.data.from_huggingface(rows)
+    counts = [int(x) for x in a.workers.split(",")]
+    all_rows = synthetic_alpaca_rows(a.n * (max(counts) if a.weak else 1))
     prep = BatchMapper(make_preprocess_function(str(ckpt)), batch_format="pandas", batch_size=4096)
     tok = T5Tokenizer.from_pretrained(str(ckpt))
-    res = {"model": a.model, "prompts": a.n, "batch_size": a.batch_size, "max_new_tokens": a.max_new_tokens,
+    res = {"model": a.model, "prompts": a.n, "per_worker": bool(a.weak), "batch_size": a.batch_size, "max_new_tokens": a.max_new_tokens,
            "gpus_visible": torch.cuda.device_count(), "runs": []}
     first = None
-    for n_workers in [int(x) for x in a.workers.split(",")]:
+    for n_workers in counts:
+        n = a.n * n_workers if a.weak else a.n
+        ds = rayshim.data.from_huggingface({k: v[:n] for k, v in all_rows.items()})  # (sequential generator: a prefix)
         checkpoint = HuggingFaceCheckpoint.from_directory(str(ckpt))
         checkpoint.set_preprocessor(prep)
         bp = BatchPredictor.from_checkpoint(checkpoint=checkpoint, predictor_cls=HuggingFaceModelPredictor,
@@ -68,15 +71,16 @@ def main():
             prediction_pd = prediction.to_pandas()
             times.append(time.perf_counter() - t0)
         joined = ds.to_pandas().join(prediction_pd, how="inner")
-        assert len(joined) == a.n
+        assert len(joined) == n
         texts = prediction_pd["generated_output"].tolist()
         if first is None:
             first = texts
         warm = min(times[1:])
-        gen_tokens = sum(len(t) for t in tok(texts[: min(a.n, 2048)], add_special_tokens=True)["input_ids"]) * (a.n / min(a.n, 2048))
-        res["runs"].append({"workers": n_workers, "cold_s": times[0], "warm_s": warm, "warm_all_s": times[1:],
-                            "prompts_per_s": a.n / warm, "generated_tokens_per_s_est": gen_tokens / warm,
-                            "rows_equal_first_run": texts == first})
+        gen_tokens = sum(len(t) for t in tok(texts[: min(n, 2048)], add_special_tokens=True)["input_ids"]) * (n / min(n, 2048))
+        common = min(len(first), len(texts))
+        res["runs"].append({"workers": n_workers, "prompts": n, "cold_s": times[0], "warm_s": warm, "warm_all_s": times[1:],
+                            "prompts_per_s": n / warm, "generated_tokens_per_s_est": gen_tokens / warm,
+                            "rows_equal_first_run": texts[:common] == first[:common], "rows_compared": common})
         print(json.dumps(res["runs"][-1]), file=sys.stderr, flush=True)
         bp.shutdown()
     base = res["runs"][0]
