@@ -236,7 +236,7 @@ def main_reference(a):
 
 
 # --------------------------------------------------------------------------- HF on the same GPU: parity + incumbent
-def hf_gpu_legs(a, ckpt, spec, last_batch, last_out, dtype):
+def hf_gpu_legs(a, ckpt, spec, last_batch, last_out, dtype, model=None):
     """transformers' eager model in the same dtype on this GPU (torch 2.11 + cuBLAS: 'the existing Blackwell path').
     (1) parity of a sample of the last TIMED batch, (2) its own throughput on the same workload."""
     import numpy as np
@@ -272,6 +272,20 @@ def hf_gpu_legs(a, ckpt, spec, last_batch, last_out, dtype):
             "rows_fully_equal": full / len(sub), "token_agreement": float((ours == ref).mean()),
             "first_tokens_equal": float((ours[:, 1] == ref[:, 1]).mean()),
         }
+        if model is not None:
+            # every decision with HF's own tokens fed back (nothing excluded, no divergence to compound): the
+            # B200 arg-max at each of the rows x T positions against HF's, and the logit error itself
+            mine = model.decode_logits(ids[sub], mask[sub], ref[:, :-1]).float().cpu().numpy()
+            mine[:, :, spec.eos_token_id] = -np.inf
+            same = mine.argmax(-1) == lg.argmax(-1)
+            clear = margins > tau
+            fin = np.isfinite(lg) & np.isfinite(mine)
+            out["parity"].update({
+                "teacher_forced_decisions": int(same.size), "teacher_forced_argmax_agreement": float(same.mean()),
+                "teacher_forced_agreement_outside_near_ties": float(same[clear].mean()) if clear.any() else None,
+                "mean_abs_logit_error_vs_hf": float(np.abs(np.where(fin, mine - lg, 0.0)).mean()),
+            })
+        log(f"parity vs HF on this GPU: {out['parity']}")
         log(f"parity vs HF on this GPU: {out['parity']}")
     if a.hf_gpu_batches > 0:
         B = a.batch
@@ -393,9 +407,12 @@ def main_b200(a):
         predictor._predict_numpy({"input_ids": host[s][0], "attention_mask": host[s][1], "labels": host[s][0]}, **gen_kw)
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for s in range(W, W + K):
+        ts = time.perf_counter()
         df = predictor._predict_numpy({"input_ids": host[s][0], "attention_mask": host[s][1], "labels": host[s][0]}, **gen_kw)
         assert len(df) == B and isinstance(df["generated_output"].iloc[0], str)
+        e2e_steps.append(1e3 * (time.perf_counter() - ts))  # (the DataFrame of strings is on the host: the step is complete)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
@@ -457,6 +474,7 @@ def main_b200(a):
             "prompts_per_s": world * K * B / (elapsed_ms / 1e3),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * S * 8,
                     "d2h_bytes_per_step": B * (T + 1) * 8, "ms_per_step": e2e_ms / K,
+                    "ms_per_step_min_median_max": [min(e2e_steps), sorted(e2e_steps)[len(e2e_steps) // 2], max(e2e_steps)],
                     "api": "HuggingFaceModelPredictor._predict_numpy (numpy batch -> DataFrame[generated_output])"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -485,7 +503,7 @@ def main_b200(a):
         }
         if world == 1 and (a.parity_rows > 0 or a.hf_gpu_batches > 0):
             try:
-                line.update(hf_gpu_legs(a, ckpt, spec, host[W + K - 1], last_out, tdtype))
+                line.update(hf_gpu_legs(a, ckpt, spec, host[W + K - 1], last_out, tdtype, model))
             except Exception as e:  # noqa: BLE001 - the headline number must still be printed
                 line["parity"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not a.no_cpu_baseline:
