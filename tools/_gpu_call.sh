@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --model flan-t5-large --steps 2 --warmup 3 --no-cpu-baseline --hf-gpu-batches 0 --parity-rows 0 > gpurun_out/bench_r2_large_n8.json 2> gpurun_out/bench_r2_large_n8.err; head -c 500 gpurun_out/bench_r2_large_n8.json; echo
-timeout 900 python tools/bench_pool.py --model flan-t5-large --weak --workers 1,8 --n 4096 --reps 1 --tag r2_large_g8 > gpurun_out/pool_r2_large_g8.log 2>&1; grep '^{"workers"' gpurun_out/pool_r2_large_g8.log | cut -c1-330; tail -2 gpurun_out/pool_r2_large_g8.log | cut -c1-200
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "geglu or gemm" > gpurun_out/pytest_geglu.log 2>&1; tail -4 gpurun_out/pytest_geglu.log
+timeout 600 python tools/sweep_decode.py --no-profile --configs "geglu_pairwise=1;geglu_pairwise=0;geglu_pairwise=1" > gpurun_out/sweep_geglu.log 2>&1
+grep '^{"config"' gpurun_out/sweep_geglu.log | python -c "
+import sys,json
+for l in sys.stdin:
+    r=json.loads(l); print(r['config'], 'encoder_ms', round(r['encoder_ms'],2), 'decode_ms', round(r['decode_ms'],2), 'tokens equal first', r['tokens_equal_first_config'])"
+timeout 900 python -m pytest tests/test_model_gpu.py -m gpu -x -q -k "golden or headline" > gpurun_out/pytest_geglu_model.log 2>&1; tail -3 gpurun_out/pytest_geglu_model.log
