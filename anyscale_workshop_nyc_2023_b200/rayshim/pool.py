@@ -40,7 +40,7 @@ def _worker_main(visible: str, payload: bytes, task_q, result_q) -> None:
         from .train import _overlap_ok, _overlap_tail, _prefetch, _ScoringWorker
 
         checkpoint, predictor_cls, kwargs, override_prep = cloudpickle.loads(payload)
-        worker = _ScoringWorker(checkpoint, predictor_cls, kwargs, override_prep)
+        worker = _ScoringWorker(checkpoint, predictor_cls, kwargs, override_prep, dedicated_process=True)
         result_q.put(("ready", visible, None))
         while True:
             task = task_q.get()

@@ -125,17 +125,20 @@ Checkpoint = HuggingFaceCheckpoint
 class _ScoringWorker:
     """What runs inside one scoring worker (Ray's ScoringWrapper actor)."""
 
-    def __init__(self, checkpoint, predictor_cls, predictor_kwargs: Dict[str, Any], override_prep: bool):
+    def __init__(self, checkpoint, predictor_cls, predictor_kwargs: Dict[str, Any], override_prep: bool,
+                 dedicated_process: bool = False):
         self.predictor = predictor_cls.from_checkpoint(checkpoint, **predictor_kwargs)
         if override_prep:
             self.predictor.set_preprocessor(None)
-        # a long-lived scoring process: the objects created while loading (model, tokenizer, imported modules) will
-        # never be garbage - keep the collector from re-walking them (a full collection otherwise stalls a ~220 ms
-        # scoring call by tens of ms every so often)
-        import gc
+        if dedicated_process or os.environ.get("B200T5_GC_FREEZE") == "1":
+            # a long-lived scoring process (one per GPU, rayshim/pool.py): the objects created while loading (model,
+            # tokenizer, imported modules) will never be garbage - keep the collector from re-walking them (a full
+            # collection otherwise stalls a ~220 ms scoring call by tens of ms every so often). Not done to the caller's
+            # own process unless asked for (B200T5_GC_FREEZE=1): it is a process-wide setting.
+            import gc
 
-        gc.collect()
-        gc.freeze()
+            gc.collect()
+            gc.freeze()
 
     def __call__(self, batch: pd.DataFrame, feature_columns, keep_columns, predict_kwargs) -> pd.DataFrame:
         data = batch[feature_columns] if feature_columns else batch

@@ -345,6 +345,7 @@ def main_b200(a):
 
     log(f"rank {rank}/{world}: checkpoint at {ckpt}; loading the model")
     tdtype = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    os.environ.setdefault("B200T5_GC_FREEZE", "1")  # this process is a dedicated scoring process, like a pool worker
     bp = make_batch_predictor(ckpt, device_map="auto", torch_dtype=tdtype)
     from anyscale_workshop_nyc_2023_b200.rayshim.train import _ScoringWorker
 
@@ -470,7 +471,8 @@ def main_b200(a):
                        "parallelism": f"dataset sharded over {world} replica(s), no collective",
                        "l2": f"inputs exceed L2 (cross-KV arena {kv_gb:.1f} GB and {w_gb:.2f} GB of decoder weights "
                              "are streamed every step vs 126 MB L2)",
-                       "forced_length": "min_new_tokens == max_new_tokens", "row_chains": n_chains},
+                       "forced_length": "min_new_tokens == max_new_tokens", "row_chains": n_chains,
+                       "host": "dedicated scoring process: gc.freeze() after the model is loaded, as rayshim/pool.py workers do"},
             "prompts_per_s": world * K * B / (elapsed_ms / 1e3),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * S * 8,
                     "d2h_bytes_per_step": B * (T + 1) * 8, "ms_per_step": e2e_ms / K,
