@@ -130,6 +130,14 @@ def main():
             model.generate(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), max_new_tokens=4)
             ids2, mask2 = synthetic_token_batch(8, 192, spec.vocab_size, seed=4, lengths="full")
             model.generate(input_ids=torch.from_numpy(ids2), attention_mask=torch.from_numpy(mask2), max_new_tokens=3)
+            model.set_option("profile_xattn", 1)  # %globaltimer stamps + the per-layer union fold in advance_step_kernel
+            model.generate(input_ids=torch.from_numpy(ids2), attention_mask=torch.from_numpy(mask2), max_new_tokens=3)
+            prof = model.xattn_profile()
+            assert prof["launches"] > 0 and prof["busy_us_per_layer"] > 0
+            model.set_option("profile_xattn", 0)
+            model.set_option("xattn", 2)  # per call by prompt fill: full-length -> stream kernel, ragged -> per-thread loads
+            model.generate(input_ids=torch.from_numpy(ids2), attention_mask=torch.from_numpy(mask2), max_new_tokens=3)
+            assert model.stats()["xattn_kernel"] == 1
             model.set_option("xattn", 0)
             ids, mask = synthetic_token_batch(20, 24, spec.vocab_size, seed=3, lengths="uniform")
             model.generate_stream(ids, mask, pool=8, max_new_tokens=4)
