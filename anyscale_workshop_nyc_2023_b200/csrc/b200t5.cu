@@ -1849,8 +1849,9 @@ extern "C" int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_l
 
 // Runtime options (what the B200T5_* environment variables set at create time, changeable on a live handle so
 // that a sweep does not reload the model). Any change drops the execution plan: the next call re-captures the
-// step graph. Names: "chains" (row-chains per step, 0 = default), "xattn" (1 = bulk-copy stream kernel, 0 = the
-// per-thread-load kernel), "xattn_stages", "xattn_late_pdl", "pdl", "profile_xattn" (1 = every cross-attention launch
+// step graph. Names: "chains" (row-chains per step, 0 = default), "xattn" (decode cross-attention: 0 = per-thread-load
+// kernel, 1 = TMA stream kernel, 2 = per call by prompt fill), "xattn_stages", "xattn_late_pdl", "xattn_serialize",
+// "xattn_l2pf", "pdl", "admit_overlap", "sk_stages64", "sk_stages128", "profile_xattn" (1 = every cross-attention launch
 // inside the step graph stamps %globaltimer; read with b200t5_get_xattn_profile; off in any timed region).
 extern "C" int b200t5_set_option(b200t5_handle h, const char* name, int value) {
   if (!h || !name) return fail(h, B200T5_EINVAL, "null argument");
@@ -2171,7 +2172,7 @@ extern "C" int b200t5_test_attn_decode(int device, int self, const void* q, cons
         static_cast<const act_t*>(q), static_cast<const act_t*>(K), static_cast<const act_t*>(V), static_cast<act_t*>(ctx),
         B * H, H, Tk, &st.as<DecodeState>()->step, dist_bias);
     cudaStreamSynchronize(s);
-  } else if (self == 2) {  // the bulk-copy stream kernel (attention_cross_stream.cuh); `step` = ring stages (0: 5)
+  } else if (self == 2) {  // the TMA stream kernel (attention_cross_stream.cuh); `step` = ring stages (0: 5)
     const int stages = step > 0 ? step : 5;
     if (stages < 2 || stages > kXsMaxStages || Tk > 4096) return fail(nullptr, B200T5_EINVAL, "attn_decode(stream): 2 <= stages <= %d, Tk <= 4096", kXsMaxStages);
     const int items = B * H;

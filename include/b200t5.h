@@ -146,7 +146,8 @@ int b200t5_bench_cross_attn(b200t5_handle h, int reps, int rows_per_launch, floa
 /* Runtime options: what the B200T5_* environment variables set at create time, on a live handle (a sweep need not
  * reload the model). A change drops the execution plan; the next call re-captures the step graph. Names: "chains"
  * (row-chains per decode step, 0 = default), "xattn" (decode cross-attention: 0 = per-thread-load kernel, 1 = TMA stream kernel, 2 = per call by prompt fill),
- * "xattn_stages" (8 KB ring stages per CTA), "xattn_late_pdl", "pdl", "sk_stages64", "sk_stages128" (pipeline stages of
+ * "xattn_stages" (8 KB ring stages per CTA), "xattn_late_pdl", "xattn_serialize", "xattn_l2pf", "pdl", "admit_overlap",
+ * "sk_stages64", "sk_stages128" (pipeline stages of
  * the split-K decode GEMM tiles, 0 = default), "profile_xattn" (1 = every cross-attention launch inside the step graph
  * records %globaltimer stamps; never on in a timed region). */
 int b200t5_set_option(b200t5_handle h, const char* name, int value);
@@ -196,8 +197,8 @@ int b200t5_test_ffo(int device, const void* A, const void* W, void* R, int M, in
                     void* stream);
 int b200t5_test_rmsnorm(int device, const void* x, const void* w, void* y, int M, int d, float eps, void* stream);
 /* self == 1: keys = step+1, dist_bias float [H][Tk]; self == 0: extent int32 [B], key_ok uint8 [B][Tk];
- * self == 2: as 0 through the bulk-copy stream kernel (csrc/attention_cross_stream.cuh), `step` = ring stages (0: 5);
- * results are bit-identical to self == 0. */
+ * self == 2: as 0 through the TMA stream kernel (csrc/attention_cross_stream.cuh), `step` = ring stages (0: 5);
+ * same rounding points as self == 0, the fp32 accumulations in the tensor core's order. */
 int b200t5_test_attn_decode(int device, int self, const void* q, const void* K, const void* V, void* ctx, int B,
                             int H, int Tk, const int32_t* extent, const uint8_t* key_ok, int step,
                             const float* dist_bias, void* stream);
