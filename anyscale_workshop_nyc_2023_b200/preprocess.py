@@ -37,6 +37,8 @@ def get_tokenizer(name_or_path: str = None):
 def encode_pairs_padded(tokenizer, first, second, max_length: int = None):
     """`tokenizer(first, second, padding="max_length", truncation=True, return_tensors="np")` without the
     per-row Python padding: returns (input_ids, attention_mask), int64 [N, max_length]."""
+    from itertools import chain
+
     import numpy as np
 
     length = int(max_length or tokenizer.model_max_length)
@@ -48,7 +50,7 @@ def encode_pairs_padded(tokenizer, first, second, max_length: int = None):
     keep = np.arange(length)[None, :] < lens[:, None]
     if getattr(tokenizer, "padding_side", "right") != "right":
         keep = keep[:, ::-1]
-    ids[keep] = np.fromiter((t for r in rows for t in r), dtype=np.int64, count=int(lens.sum()))
+    ids[keep] = np.fromiter(chain.from_iterable(rows), dtype=np.int64, count=int(lens.sum()))
     return ids, keep.astype(np.int64)
 
 

@@ -36,8 +36,7 @@ _POLL_S = 1.0
 def _worker_main(visible: str, payload: bytes, task_q, result_q) -> None:
     os.environ["CUDA_VISIBLE_DEVICES"] = visible
     try:
-        from .data import _to_block, _to_pandas
-        from .train import _overlap_ok, _overlap_tail, _prefetch, _ScoringWorker
+        from .train import _model_batch, _overlap_ok, _overlap_tail, _prefetch, _ScoringWorker
 
         checkpoint, predictor_cls, kwargs, override_prep = cloudpickle.loads(payload)
         worker = _ScoringWorker(checkpoint, predictor_cls, kwargs, override_prep, dedicated_process=True)
@@ -49,7 +48,7 @@ def _worker_main(visible: str, payload: bytes, task_q, result_q) -> None:
             call_id, blob = task
             items, feature_columns, keep_columns, predict_kwargs, prep = cloudpickle.loads(blob)
             if prep is not None:  # this worker's own CPU stage, one block ahead of its GPU stage
-                stream = _prefetch(items, lambda it: (it[0], _to_pandas(_to_block(prep.transform_batch(it[1])))))
+                stream = _prefetch(items, lambda it: (it[0], _model_batch(prep.transform_batch(it[1]))))
             else:
                 stream = iter(items)
             # (two blocks in flight: the detokenise tail of block i overlaps the generation of block i+1)

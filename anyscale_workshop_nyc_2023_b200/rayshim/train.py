@@ -140,7 +140,18 @@ class _ScoringWorker:
             gc.collect()
             gc.freeze()
 
-    def __call__(self, batch: pd.DataFrame, feature_columns, keep_columns, predict_kwargs) -> pd.DataFrame:
+    def __call__(self, batch, feature_columns, keep_columns, predict_kwargs) -> pd.DataFrame:
+        """`batch`: a pandas batch, or - what the worker-side CPU stage hands over - a block of numpy columns (the
+        tokenised [N, 512] arrays go to `_predict_numpy` as they are: no DataFrame of 4096 row objects in between,
+        which cost more host time per block than the GPU needs to score it)."""
+        if isinstance(batch, dict):
+            data = {k: batch[k] for k in feature_columns} if feature_columns else batch
+            out = self.predictor.predict(data, **predict_kwargs)
+            if keep_columns:
+                out = out.copy()
+                for c in keep_columns:
+                    out[c] = batch[c] if batch[c].ndim == 1 else list(batch[c])
+            return out
         data = batch[feature_columns] if feature_columns else batch
         out = self.predictor.predict(data, **predict_kwargs)
         if keep_columns:
@@ -196,6 +207,13 @@ def _prefetch(items: List[Any], fn, depth: int = 2):
     finally:
         stop.set()
         t.join(timeout=5)
+
+
+def _model_batch(transformed: Any):
+    """Output of a worker-side preprocessor as the scoring stage takes it: numpy columns stay numpy columns."""
+    if isinstance(transformed, dict) and all(isinstance(v, np.ndarray) for v in transformed.values()):
+        return transformed
+    return _to_pandas(_to_block(transformed))
 
 
 def _overlap_tail(fn, items, enabled: bool = True):
@@ -300,7 +318,7 @@ class BatchPredictor:
                 self._worker_key = key
             if worker_prep is not None:
                 outs = list(_overlap_tail(lambda b: self._worker(b, feature_columns, keep_columns, predict_kwargs),
-                                          _prefetch(batches, lambda raw: _to_pandas(_to_block(worker_prep.transform_batch(raw)))),
+                                          _prefetch(batches, lambda raw: _model_batch(worker_prep.transform_batch(raw))),
                                           _overlap_ok(self._worker)))
             else:
                 outs = list(_overlap_tail(lambda b: self._worker(b, feature_columns, keep_columns, predict_kwargs), batches,

@@ -155,3 +155,45 @@ def test_predictor_hands_oversized_batches_over_in_host_memory():
     df = pred._predict_numpy({"input_ids": ids, "attention_mask": np.ones_like(ids), "labels": ids}, max_new_tokens=3)
     assert len(df) == 8 and set(Model.seen) == {"input_ids", "attention_mask", "max_new_tokens"}
     assert Model.seen["input_ids"].device.type == "cpu" and torch.equal(Model.seen["input_ids"], torch.from_numpy(ids))
+
+
+class NumpyPredictor(Predictor):
+    """`_predict_numpy` only, like the reference's HuggingFaceModelPredictor: must be handed the tokenised COLUMNS."""
+
+    @classmethod
+    def from_checkpoint(cls, checkpoint, use_gpu=False, **kw):
+        return cls(preprocessor=checkpoint.get_preprocessor())
+
+    def _predict_numpy(self, data, **kw):
+        import numpy as np
+
+        ids = data["input_ids"]
+        assert isinstance(ids, np.ndarray) and ids.ndim == 2 and ids.dtype == np.int64 and "text" not in data
+        return pd.DataFrame({"generated_output": [f"{int(r.sum())}" for r in ids]})
+
+
+def _tokenise(batch):
+    import numpy as np
+
+    ids = np.array([[len(t), ord(t[1]), 0, 0] for t in batch["text"]], dtype=np.int64)
+    return {"input_ids": ids, "attention_mask": (ids != 0).astype(np.int64), "labels": ids.copy()}
+
+
+def test_tokenised_blocks_reach_the_predictor_as_numpy_columns():
+    """The worker-side CPU stage hands the predictor the preprocessor's numpy columns as they are (no DataFrame of
+    per-row array objects in between: that round trip cost more host time per 4096-row block than the GPU needs to
+    score it), in the pool and in the single-worker path alike; keep_columns still works on such a block."""
+    from anyscale_workshop_nyc_2023_b200.rayshim.train import _ScoringWorker, _model_batch
+
+    prep = rayshim.data.BatchMapper(_tokenise, batch_format="pandas")
+    want = [[str(len(f"b{i}r{j}") + ord("0") + i) for j in range(3)] for i in range(5)]
+    with GpuWorkerPool(2, Ckpt(), NumpyPredictor, {}, True) as pool:
+        outs = pool.map_ordered(_blocks(5), None, None, {}, prep=prep)
+        assert [o["generated_output"].tolist() for o in outs] == want
+    worker = _ScoringWorker(Ckpt(), NumpyPredictor, {}, True)
+    block = _model_batch(prep.transform_batch(_blocks(1)[0]))
+    assert isinstance(block, dict)
+    out = worker(block, ["input_ids"], ["labels"], {})
+    assert out["generated_output"].tolist() == want[0] and len(out["labels"]) == 3
+    # a preprocessor that returns a DataFrame keeps the pandas path
+    assert isinstance(_model_batch(_upper(_blocks(1)[0])), pd.DataFrame)

@@ -7,7 +7,9 @@ NLP_workloads/Anyscale_job/flan-t5-batch-inference.py:119-138 (predict -> to_pan
 
 For every worker count: a cold predict (spawns the pool: model load + graph capture) and warm ones (the pool stays
 alive between predict calls); prompts/s and generated tokens/s from wall-clock around predict(); the output rows of
-every count are compared with the first count's, row for row. One JSON line; also written to gpurun_out/pool_<tag>.json."""
+every count are compared with the first count's, row for row. One JSON line; also written to gpurun_out/pool_<tag>.json.
+(`generated_tokens_per_s_est` re-tokenises the output strings: a lower bound that is far off for random-weight checkpoints,
+whose token ids do not round-trip through text; tools/profile_pool_block.py reports the library's own count.)"""
 import argparse
 import json
 import sys
