@@ -1044,8 +1044,10 @@ static int build_plan(b200t5_ctx* h, int B, int S, int Tmax) {
   TMAP(h, &pl->tm_cross_kv, pl->cross_kv.p, static_cast<uint64_t>(c.Ld) * 2 * B * H * S, 64, kXsChunkKeys);
   CU_OK(h, cudaMemset(pl->ctx.p, 0, pl->ctx.bytes));  // padded query tiles are skipped: keep them finite
   {
-    // chains: ~64 rows each (at least 1, at most kMaxChains); B200T5_CHAINS overrides
-    int nc = B >= 128 ? 2 : 1;
+    // chains of 128 rows (one M-tile per split-K GEMM): two for a 256-row batch, four for the slot pool's 512 rows
+    // (measured, natural EOS, 4096 full-length prompts: 138.8 k tok/s with four chains, 133.4 k with two; three: 123.9 k -
+    // uneven M-tiles; profiles/stream_r2_chains.log); B200T5_CHAINS overrides
+    int nc = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
     if (h->chains_override > 0) nc = h->chains_override;
     if (nc > kMaxChains) nc = kMaxChains;
     if (nc > B) nc = B;

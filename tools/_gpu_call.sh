@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/profile_pool_block.py > gpurun_out/profile_pool_block.log 2>&1; tail -4 gpurun_out/profile_pool_block.log
+timeout 200 python -m pytest tests/test_model_gpu.py -m gpu -q -k "slot_pool or run_to_run or retired" --durations=8 2>&1 | tail -14
